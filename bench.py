@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- atom-timesteps/s of the short-range MD hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload: 3-D Lennard-Jones, f32, fcc at rho=0.8442, r_c=2.5,
+skin 0.3, dt=0.005, kT=1.0, N = 4*n^3 atoms per GPU (n=63 -> 1,000,188).  One
+"step" = `nbrs.update(R)` (skin predicate, rebuild when needed) + one
+velocity-Verlet step through the public API.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RHO, R_CUT, SKIN, DT, KT = 0.8442, 2.5, 0.3, 0.005, 1.0
+
+
+def fcc(n_cells, dtype=np.float32):
+  a = (4.0 / RHO) ** (1.0 / 3.0)
+  nx, ny, nz = n_cells
+  basis = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]])
+  g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz),
+                           indexing='ij'), -1).reshape(-1, 1, 3)
+  R = ((g + basis[None]) * a).reshape(-1, 3).astype(dtype)
+  box = np.array([nx * a, ny * a, nz * a], np.float32)
+  return R, box
+
+
+def momenta(N, seed=0):
+  rng = np.random.default_rng(seed)
+  p = rng.normal(0, np.sqrt(KT), (N, 3))
+  return (p - p.mean(0, keepdims=True)).astype(np.float32)
+
+
+class ClockSampler(threading.Thread):
+  """Samples SM clocks / throttle reasons of one GPU through NVML while the
+  timed region runs (the profiling recipe's clocks line)."""
+
+  def __init__(self, index, period=0.05):
+    super().__init__(daemon=True)
+    self.index, self.period = index, period
+    self.samples, self.reasons = [], set()
+    self.max_mhz = None
+    self._stop_evt = threading.Event()
+    self.ok = False
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+      self.ok = True
+    except Exception:   # pragma: no cover
+      self.ok = False
+
+  def run(self):
+    if not self.ok:
+      return
+    nv = self.nv
+    names = {
+        getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+        getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+        getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+        getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
+    }
+    while not self._stop_evt.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in names.items():
+          if r & bit:
+            self.reasons.add(name)
+      except Exception:   # pragma: no cover
+        pass
+      time.sleep(self.period)
+
+  def stop(self):
+    self._stop_evt.set()
+    self.join(timeout=2)
+    med = float(np.median(self.samples)) if self.samples else None
+    return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz,
+            'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+def peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    with open(p) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------
+# reference arm / cpu baseline: the NumPy oracle port on the host cores
+# ------------------------------------------------------------------------------
+
+def cpu_port_run(n, steps, warmup):
+  """Times the oracle (a CPU port of the reference path) on a bounded sample:
+  fcc N = 4 n^3, `steps` update+NVE steps.  Returns (atom-steps/s, N, seconds)."""
+  from oracle import energy as oenergy, partition as opart
+  from oracle import simulate as osim, space as ospace
+  R, box = fcc((n, n, n))
+  L = box[0]
+  d, s = ospace.periodic(L)
+  pot = oenergy.PairPotential('lj', np.float32(2.0), np.float32(2.5))
+  nf = opart.neighbor_list(d, L, np.float32(R_CUT), np.float32(SKIN),
+                           format=opart.OrderedSparse)
+  holder = {'nb': nf.allocate(R)}
+
+  def force(Rx):
+    holder['nb'] = holder['nb'].update(Rx)
+    return oenergy.pair_neighbor_list_energy(
+        pot, d, Rx, holder['nb'], want_grads=True, sigma=np.float32(1.0),
+        epsilon=np.float32(1.0))[1]
+  init, step = osim.nve(force, s, DT)
+  st = init(R, momenta(len(R)), mass=np.float32(1.0))
+  for _ in range(warmup):
+    st = step(st)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    st = step(st)
+  dt = time.perf_counter() - t0
+  return len(R) * steps / dt, len(R), dt
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  n = args.cpu_cells
+  steps = max(1, min(args.steps, args.cpu_steps))
+  warm = 1
+  v, N, secs = cpu_port_run(n, steps, warm)
+  ms = secs / steps * 1e3
+  sample = (f'LJ fcc N={N} (n={n}), {steps} update+NVE steps through the NumPy '
+            f'oracle port (jax is not installable here; reference not runnable)')
+  line = {
+      'impl': 'reference', 'metric': 'atom-timesteps/s', 'value': v,
+      'unit': 'atom-timesteps/s', 'n_gpus': args.gpus, 'steps': steps,
+      'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+      'data': 'synthetic',
+      'config': {'workload': f'LJ fcc rho={RHO} rc={R_CUT} skin={SKIN} NVE, '
+                             f'bounded CPU sample N={N}'},
+      'cpu_baseline': {'value': v, 'unit': 'atom-timesteps/s', 'cores': 1,
+                       'kind': 'port', 'sample': sample},
+      'e2e': {'value': v, 'unit': 'atom-timesteps/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------
+
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  import jax_md_b200 as jmd
+  from jax_md_b200 import _lib
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+
+  n = args.cells
+  if world > 1:
+    from jax_md_b200 import domain
+    return domain.bench_domain(args, world, rank, dev)
+
+  R_h, box = fcc((n, n, n))
+  N = len(R_h)
+  P_h = momenta(N)
+  L = box[0]
+  disp, shift = jmd.space.periodic(L)
+  fmt = jmd.partition.NeighborListFormat[args.format]
+  nf, efn = jmd.energy.lennard_jones_neighbor_list(
+      disp, L, r_onset=2.0, r_cutoff=R_CUT, dr_threshold=SKIN, format=fmt)
+  init_fn, apply_fn = jmd.simulate.nve(efn, shift, DT)
+
+  R_pin = torch.from_numpy(R_h).pin_memory()
+  P_pin = torch.from_numpy(P_h).pin_memory()
+  Rd = R_pin.to(dev, non_blocking=True)
+  Pd = P_pin.to(dev, non_blocking=True)
+  nbrs = nf.allocate(Rd)
+  state = init_fn(0, Rd, kT=KT, momenta=Pd, neighbor=nbrs)
+
+  def md_steps(state, nbrs, k):
+    for _ in range(k):
+      nbrs = nbrs.update(state.position)
+      state = apply_fn(state, neighbor=nbrs)
+    return state, nbrs
+
+  def barrier():
+    torch.cuda.synchronize()
+
+  # ---- warm-up (also melts the perfect lattice a little so rebuilds happen) ----
+  state, nbrs = md_steps(state, nbrs, args.warmup)
+  barrier()
+  if bool(nbrs.did_buffer_overflow):
+    nbrs = nf.allocate(state.position)
+  builds0 = nbrs._ws.state_host()[_lib.ST_BUILDS]
+
+  # ---- timed region: exactly K steps, device timed ------------------------------
+  sampler = ClockSampler(local)
+  sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  state, nbrs = md_steps(state, nbrs, args.steps)
+  e1.record()
+  barrier()
+  ms_total = e0.elapsed_time(e1)
+  clocks = sampler.stop()
+  builds = nbrs._ws.state_host()[_lib.ST_BUILDS] - builds0
+  overflow = bool(nbrs.did_buffer_overflow)
+  value = N * args.steps / (ms_total * 1e-3)
+
+  # ---- neighbour rebuild time (one full forced rebuild) -------------------------
+  ws = nbrs._ws
+  pp = _lib.ptr(state.position)
+  rb = []
+  for _ in range(5):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    st = _lib.stream()
+    _lib.call('jmd_nbr_bin', ws.ref(), pp, 0, st)
+    _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 0, st)
+    _lib.call('jmd_nbr_export', ws.ref(), pp, 0, st)
+    b.record()
+    torch.cuda.synchronize()
+    rb.append(a.elapsed_time(b))
+  rebuild_ms = float(np.median(rb))
+
+  # ---- roofline of the dominant kernel (fused force + half kick), timed alone ---
+  pairs = int(torch.minimum(ws.t['cnt'][:N], torch.tensor(ws.c.m_int, device=dev)).sum())
+  kernel_bytes = pairs * 20 + N * 60       # DESIGN.md "algorithmic bytes"
+  step_bytes = pairs * 20 + N * 72
+  fstep = apply_fn._stepper
+  kt = []
+  P_tmp = state.momentum.clone()
+  kw = {}
+  _, species, params = efn._resolve(nbrs, kw)
+  for i in range(args.kernel_reps + 3):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    efn.launch(state.position, nbrs, species, params, want_energy=False,
+               momentum=P_tmp, mass=state.mass, dt_2=0.0, red=fstep.red(state.position),
+               refresh_positions=False)
+    b.record()
+    torch.cuda.synchronize()
+    if i >= 3:
+      kt.append(a.elapsed_time(b))
+  k_ms = float(np.mean(kt))
+  peak, peak_src = peaks()
+  achieved = kernel_bytes / (k_ms * 1e-3) / 1e9
+  roofline = {'bound': 'hbm', 'kernel': 'k_pair_force<float,3,LJ,scalar,kick>',
+              'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+              'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+              'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': kernel_bytes,
+              'step_frac': step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}
+
+  # ---- end to end through the public API with host buffers ----------------------
+  blk = args.block
+  n_blocks = max(1, args.steps // blk)
+  out_R = torch.empty_like(R_pin).pin_memory()
+  out_P = torch.empty_like(P_pin).pin_memory()
+  flags = torch.zeros(2, dtype=torch.float64).pin_memory()
+  R_pin.copy_(state.position.cpu())
+  P_pin.copy_(state.momentum.cpu())
+  barrier()
+  t0 = time.perf_counter()
+  Rd = R_pin.to(dev, non_blocking=True)
+  Pd = P_pin.to(dev, non_blocking=True)
+  nb2 = nf.allocate(Rd)
+  st2 = init_fn(0, Rd, kT=KT, momenta=Pd, neighbor=nb2)
+  d2h = 0
+  for _ in range(n_blocks):
+    st2, nb2 = md_steps(st2, nb2, blk)
+    flags[0] = float(nb2.did_buffer_overflow)          # sync, like the example loop
+    flags[1] = float(fstep.red(st2.position)[_lib.RED_KINETIC])
+    d2h += 1 + 8
+  out_R.copy_(st2.position, non_blocking=True)
+  out_P.copy_(st2.momentum, non_blocking=True)
+  barrier()
+  e2e_s = time.perf_counter() - t0
+  e2e_steps = n_blocks * blk
+  h2d = R_pin.numel() * 4 + P_pin.numel() * 4
+  d2h += out_R.numel() * 4 + out_P.numel() * 4
+  e2e = {'value': N * e2e_steps / e2e_s, 'unit': 'atom-timesteps/s',
+         'h2d_bytes_per_step': h2d / e2e_steps, 'd2h_bytes_per_step': d2h / e2e_steps,
+         'steps': e2e_steps, 'includes': 'H2D of state, neighbour allocate, '
+         f'{e2e_steps} update+apply steps, overflow/KE readback every {blk} steps, D2H of state'}
+
+  # ---- CPU baseline (oracle port, bounded sample) -------------------------------
+  cpu = None
+  if not args.no_cpu:
+    v, Nc, secs = cpu_port_run(args.cpu_cells, args.cpu_steps, 1)
+    cpu = {'value': v, 'unit': 'atom-timesteps/s', 'cores': 1, 'kind': 'port',
+           'sample': f'LJ fcc N={Nc}, {args.cpu_steps} update+NVE steps, NumPy oracle '
+                     f'port ({secs:.1f} s); host has {os.cpu_count()} cores'}
+
+  rebuild_kernels = 12 if args.format == 'Dense' else 16
+  line = {
+      'metric': 'atom-timesteps/s', 'value': value, 'unit': 'atom-timesteps/s',
+      'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': f'LJ fcc N={N} rho={RHO} rc={R_CUT} skin={SKIN} dt={DT} '
+                             f'kT={KT} NVE, neighbour format {args.format}',
+                 'atoms': N, 'l2_policy': 'working set (idx rows %.0f MB + state) exceeds L2'
+                 % (pairs * 4 / 1e6), 'rebuilds_in_timed_region': int(builds),
+                 'neighbor_overflow': overflow},
+      'neighbor_rebuild_ms': rebuild_ms,
+      'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+      'gpu_launches': int(args.steps * 3 + builds * rebuild_kernels),
+      'clocks': clocks,
+  }
+  print(json.dumps(line))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=1000)
+  ap.add_argument('--warmup', type=int, default=300)
+  ap.add_argument('--impl', default='b200')
+  ap.add_argument('--cells', type=int, default=63, help='fcc cells per side per GPU')
+  ap.add_argument('--format', default='OrderedSparse',
+                  choices=['Dense', 'Sparse', 'OrderedSparse'])
+  ap.add_argument('--block', type=int, default=100)
+  ap.add_argument('--kernel-reps', type=int, default=20)
+  ap.add_argument('--cpu-cells', type=int, default=20)
+  ap.add_argument('--cpu-steps', type=int, default=3)
+  ap.add_argument('--no-cpu', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    return run_reference(args)
+  run_b200(args)
+
+
+if __name__ == '__main__':
+  main()

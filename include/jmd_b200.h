@@ -1,0 +1,244 @@
+/* jmd_b200.h -- C ABI of libjmd_b200.so: B200 (sm_100a) kernels for the JAX MD
+ * short-range hot path (neighbour list -> pair / Stillinger-Weber forces ->
+ * velocity-Verlet / Nose-Hoover / FIRE step).
+ *
+ * Boundary rules:
+ *   - extern "C", plain pointers and sizes, no torch / XLA types.
+ *   - every entry point only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *     void*); none of them synchronises or allocates, so they are legal inside
+ *     XLA FFI handlers and CUDA-graph capture.  The only exceptions are the
+ *     `jmd_*_host` queries used by the (non-jittable) `allocate` path, which
+ *     the reference also runs eagerly with host syncs (partition.py:249,1094).
+ *   - data conditions (capacity overflow) never fail a call: they set bits in
+ *     the device-side error code exactly like the reference's
+ *     PartitionErrorCode (partition.py:494-561).
+ *   - return value: 0 on success, a cudaError_t (>0) from the launch, or
+ *     JMD_EINVAL (-1) for an invalid descriptor.
+ *
+ * All device pointers are owned by the caller (XLA / torch).  Positions,
+ * momenta and forces are row-major [n, dim] arrays of `dtype`.
+ */
+#ifndef JMD_B200_H_
+#define JMD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMD_EINVAL (-1)
+
+enum { JMD_F32 = 0, JMD_F64 = 1 };
+/* partition.py:641-657 NeighborListFormat */
+enum { JMD_DENSE = 0, JMD_SPARSE = 1, JMD_ORDERED_SPARSE = 2 };
+/* partition.py:494-520 PartitionErrorCode */
+enum { JMD_ERR_NEIGHBOR_LIST_OVERFLOW = 1, JMD_ERR_CELL_LIST_OVERFLOW = 2,
+       JMD_ERR_CELL_SIZE_TOO_SMALL = 4, JMD_ERR_MALFORMED_BOX = 8 };
+enum { JMD_SPACE_FREE = 0, JMD_SPACE_PERIODIC = 1 };
+enum { JMD_POT_LJ = 0, JMD_POT_SOFT_SPHERE = 1, JMD_POT_MORSE = 2 };
+/* smap.py:697-846 parameter modes */
+enum { JMD_PARAM_SCALAR = 0, JMD_PARAM_PER_ATOM = 1, JMD_PARAM_SPECIES = 2,
+       JMD_PARAM_MATRIX = 3 };
+
+/* space.py:258-329: free() / periodic(side).  `side` and `half` hold the
+ * values of `side` and `f32(0.5) * side` in the position dtype, widened to
+ * double (exact).  replaces: space.py:213-224 periodic_displacement,
+ * space.py:250-252 periodic_shift. */
+typedef struct {
+  int32_t dim;        /* 2 or 3 */
+  int32_t kind;       /* JMD_SPACE_* */
+  int32_t wrapped;    /* shift_fn wraps into [0, side) */
+  int32_t _pad;
+  double side[3];
+  double half[3];
+} jmd_space_t;
+
+/* Slots of the device scalar block `jmd_nbr_t.state` (int64 each). */
+enum {
+  JMD_ST_REBUILD = 0,      /* 1 when the next gated rebuild must run */
+  JMD_ST_MAX_CELL_OCC = 1, /* max atoms in one cell (last binning) */
+  JMD_ST_MAX_ROW = 2,      /* max neighbours in one row (last build) */
+  JMD_ST_TOTAL = 3,        /* total entries in requested sparse format */
+  JMD_ST_BUILDS = 4,       /* number of rebuilds executed */
+  JMD_ST_SCAN_TICKET = 5,
+  JMD_ST_COUNT = 8
+};
+
+/* Neighbour-list workspace: the hidden part of partition.NeighborList
+ * (partition.py:684-737).  Filled by the host; all buffers device-resident. */
+typedef struct {
+  /* static configuration */
+  int32_t n;               /* atoms */
+  int32_t dtype;           /* JMD_F32 / JMD_F64 */
+  int32_t format;          /* requested public format */
+  int32_t use_cells;       /* 1: cell list path, 0: all-pairs candidates */
+  int32_t mask_self;
+  int32_t always_rebuild;  /* dr_threshold == 0, partition.py:892 */
+  int32_t cps[3];          /* cells per side (x, y, z) */
+  int32_t n_cells;
+  int32_t cell_capacity;   /* reference cell_list_capacity (slot rotation, flag) */
+  int32_t m_int;           /* internal row capacity (rows of `nl`) */
+  int64_t n_pad;           /* row stride of `nl` (n rounded up to 32) */
+  int64_t max_occupancy;   /* public capacity: per row (Dense) / total (Sparse) */
+  double cell_size[3];     /* f32 cell size, partition.py:162-163 */
+  double cutoff_sq;        /* (r_cutoff + dr_threshold)^2, partition.py:900 */
+  double threshold_sq;     /* (dr_threshold / 2)^2, partition.py:901 */
+  jmd_space_t space;       /* metric of the user's displacement function */
+  /* device buffers */
+  int32_t* cell_count;     /* [n_cells + 1] */
+  int32_t* cell_start;     /* [n_cells + 1] exclusive scan of cell_count */
+  int32_t* cell_cursor;    /* [n_cells] */
+  int32_t* scan_tmp;       /* [>= n_cells / 1024 + 2] */
+  int32_t* hash;           /* [n] cell hash per atom (user order) */
+  int32_t* tmp_ids;        /* [n] */
+  int32_t* perm;           /* [n_pad] sorted slot -> atom id */
+  int32_t* inv_perm;       /* [n] atom id -> sorted slot */
+  void* pos_sorted;        /* [n_pad] float4 / double4: x y z species */
+  int32_t* nl;             /* [m_int, n_pad] transposed rows, slot indices */
+  int32_t* cnt;            /* [n_pad] entries per slot row */
+  int32_t* cnt_lower;      /* [n_pad] entries with id < row id */
+  int64_t* offsets;        /* [n + 1] sparse export offsets (user order) */
+  void* reference_position;/* [n, dim] positions at last build */
+  int32_t* idx;            /* public idx: [n, max_occ] or [2, max_occ] */
+  uint8_t* error;          /* PartitionError.code */
+  int64_t* state;          /* [JMD_ST_COUNT] */
+  const int32_t* species;  /* [n] or NULL (copied into pos_sorted.w) */
+} jmd_nbr_t;
+
+/* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */
+
+/* Skin predicate of NeighborList.update (partition.py:1146-1154): sets
+ * state[REBUILD] = any_i |d(R_i, ref_i)|^2 > threshold_sq (or 1 when
+ * always_rebuild).  tail_launch != 0: when the predicate is true the kernel
+ * itself enqueues bin + build + export on the device (CUDA dynamic parallelism,
+ * tail-launch stream), so the steady-state step issues no launches for the
+ * lax.cond of partition.py:1146; the host then must NOT call the gated
+ * bin/build/export for this update. */
+int jmd_nbr_skin_check(const jmd_nbr_t* nb, const void* position,
+                       int tail_launch, void* stream);
+
+/* Bin atoms into cells and sort them (partition.py:421-460).  gated != 0:
+ * kernels exit early unless state[REBUILD] is set (the lax.cond of
+ * partition.py:1146).  Leaves state[MAX_CELL_OCC]. */
+int jmd_nbr_bin(const jmd_nbr_t* nb, const void* position, int gated,
+                void* stream);
+
+/* Candidate scan + compaction (partition.py:911-1032) into the internal rows.
+ * count_only != 0 just measures state[MAX_ROW] / state[TOTAL] (allocate). */
+int jmd_nbr_build(const jmd_nbr_t* nb, const void* position, int count_only,
+                  int gated, void* stream);
+
+/* Export internal rows to the public idx in nb->format, update the error
+ * code (partition.py:1066,1110), store reference_position, clear REBUILD. */
+int jmd_nbr_export(const jmd_nbr_t* nb, const void* position, int gated,
+                   void* stream);
+
+/* allocate-time host query: copies state[] to `out[JMD_ST_COUNT]` after
+ * synchronising the stream (partition.py:249,1094 do the same via int()). */
+int jmd_nbr_state_host(const jmd_nbr_t* nb, int64_t* out, void* stream);
+
+/* Refresh pos_sorted from user-order positions (no rebuild). */
+int jmd_nbr_pack(const jmd_nbr_t* nb, const void* position, void* stream);
+
+/* ---- pair potentials (replaces smap.py:922-979 + energy.py:125-371,534-580) */
+
+typedef struct {
+  int32_t kind;            /* JMD_POT_* */
+  int32_t has_cutoff;      /* multiplicative_isotropic_cutoff applied */
+  int32_t mode[3];         /* JMD_PARAM_* for sigma, epsilon, alpha */
+  int32_t n_species;       /* table side for SPECIES / MATRIX modes */
+  int32_t transposed;      /* table lookups as p[neighbour, row] (Sparse formats:
+                              smap.py:716,792 index with idx[0]=receiver first) */
+  int32_t _pad;
+  double scalar[3];        /* sigma, epsilon, alpha when SCALAR */
+  const void* array[3];    /* device arrays (position dtype) otherwise */
+  double r_onset, r_cutoff;
+} jmd_pair_t;
+
+/* Slots of the double reduction block written by the force kernels. */
+enum {
+  JMD_RED_ENERGY = 0, JMD_RED_KINETIC = 1, JMD_RED_VIRIAL = 2, /* 2..7: xx yy zz xy xz yz */
+  JMD_RED_DSIGMA = 8, JMD_RED_DEPSILON = 9, JMD_RED_FF = 10, JMD_RED_PP = 11,
+  JMD_RED_FP = 12, JMD_RED_COUNT = 16
+};
+
+/* Fused force (+energy/virial/parameter gradients) over the internal rows.
+ *   force      [n, dim] out (user order)
+ *   e_atom     [n] out or NULL: per-atom energy (reduce_axis=(1,), smap.py:958)
+ *   red        double[JMD_RED_COUNT] out or NULL (energy, virial, dE/dparam)
+ *   dparam     out or NULL: dE/dsigma then dE/depsilon tables (SPECIES mode:
+ *              2 * n_species^2 doubles; PER_ATOM: 2 * n doubles)
+ *   partials   scratch double[>= jmd_red_scratch_doubles(n)]
+ * want_energy != 0 also produces red[ENERGY, VIRIAL.., DSIGMA, DEPSILON]
+ * (dparam tables must be zeroed by the caller).
+ * If momentum != NULL the second half-kick of velocity Verlet is fused
+ * (simulate.py:241: p += dt_2 * F) and red[KINETIC] = 0.5 sum p^2/m; dt_dev
+ * (device scalar, position dtype) overrides dt_2 with f32(f32(*dt_dev)/2). */
+int jmd_pair_force(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force,
+                   void* e_atom, double* red, double* dparam, double* partials,
+                   void* momentum, const void* mass, int mass_is_array,
+                   double dt_2, const void* dt_dev, int want_energy,
+                   void* stream);
+
+int64_t jmd_red_scratch_doubles(int64_t n);
+
+/* ---- Stillinger-Weber (replaces energy.py:842-893, 994-1012) -------------- */
+typedef struct {
+  double sigma, A, B, lam, gamma, epsilon, three_body_strength, cutoff;
+} jmd_sw_t;
+
+int jmd_sw_force(const jmd_nbr_t* nb, const jmd_sw_t* sw, void* force,
+                 double* red, double* partials, void* momentum,
+                 const void* mass, int mass_is_array, double dt_2,
+                 const void* dt_dev, void* stream);
+
+/* ---- integrators (replaces simulate.py:168-243, 444-517; minimize.py:184-224) */
+
+/* First half of velocity Verlet: p = scale*p + dt_2*F;  R = shift(R, dt*p/m)
+ * (simulate.py:238-239), out of place; also refreshes nb->pos_sorted when
+ * nb != NULL.  `dt_dev`/`scale_dev` (device scalars of the position dtype)
+ * override dt/scale when non-NULL (FIRE's traced dt, minimize.py:185; the NHC
+ * momentum scale, simulate.py:471-473). */
+int jmd_nve_kick_drift(const jmd_space_t* sp, int dtype, int n,
+                       const jmd_nbr_t* nb, const void* r_in, const void* p_in,
+                       const void* f_in, const void* mass, int mass_is_array,
+                       double dt, const void* dt_dev, const void* scale_dev,
+                       void* r_out, void* p_out, void* stream);
+
+/* Generic second half-kick for force functions we do not own:
+ * p += dt_2 * F, red[KINETIC] = 0.5 sum p^2/m, plus FF / PP / FP sums. */
+int jmd_kick_reduce(int dtype, int n, int dim, void* momentum, const void* force,
+                    const void* mass, int mass_is_array, double dt_2,
+                    const void* dt_dev, double* red, double* partials,
+                    void* stream);
+
+/* p *= *scale_dev (NHC second half step). */
+int jmd_scale_momentum(int dtype, int64_t count, void* momentum,
+                       const void* scale_dev, void* stream);
+
+/* Nose-Hoover chain half step on device scalars (simulate.py:444-507).
+ * chain = [xi[cl] | p_xi[cl] | Q[cl] | KE] of the position dtype.  ke_red:
+ * NULL -> use the chain's own KE, else the double KE slot written by the
+ * force+kick kernel (simulate.py:662).  Writes the product of the sub-step
+ * momentum scales to scale_out (position dtype). */
+int jmd_nhc_half_step(int dtype, int chain_length, int chain_steps, int sy_steps,
+                      double dt, double tau, int64_t dof, const void* kT_dev,
+                      void* chain, const double* ke_red, void* scale_out,
+                      void* stream);
+
+/* FIRE momentum mixing + schedule (minimize.py:190-224) from red[FF,PP,FP].
+ * fire_in/out = [dt, alpha] (position dtype), n_pos int32; out of place so
+ * every thread mixes with the OLD alpha. */
+int jmd_fire_mix(int dtype, int64_t count, void* momentum, const void* force,
+                 const double* red, const void* fire_in, void* fire_out,
+                 const int32_t* npos_in, int32_t* npos_out, double dt_max,
+                 double n_min, double f_inc, double f_dec, double alpha_start,
+                 double f_alpha, void* stream);
+
+const char* jmd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* JMD_B200_H_ */

@@ -1,0 +1,152 @@
+// Shared device helpers for libjmd_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "jmd_b200.h"
+
+#define JMD_WARP 32
+#define JMD_SM_COUNT 148
+
+#define JMD_LAUNCH_CHECK()                         \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; };
+template <> struct Vec4<double> { typedef double4 type; };
+
+// ---- separately rounded IEEE ops: the compiler must not contract these into
+// FMAs (the oracle / reference spell the ops out; SURVEY 7 hard-part 1). -------
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// jnp.mod(t, L) for L > 0 (space.py:224,252): fmod, then +L when the remainder
+// is negative.  The three fast branches are exact restatements of that for
+// t in (-L, 2L); everything else takes the fmod path.
+template <typename T>
+__device__ __forceinline__ T mod_pos(T t, T L) {
+  if (t >= T(0) && t < L) return t;
+  if (t >= L && t < L + L) return sub_rn(t, L);          // exact (Sterbenz)
+  if (t < T(0) && t > -L) return add_rn(t, L);           // fmod(t, L) == t
+  T m = fmod(t, L);
+  if (m != T(0) && m < T(0)) m = add_rn(m, L);
+  return m;
+}
+
+template <typename T, int DIM>
+struct Space {
+  T side[DIM];
+  T half[DIM];
+  int periodic;
+  int wrapped;
+  __host__ void init(const jmd_space_t& s) {
+    for (int k = 0; k < DIM; ++k) { side[k] = (T)s.side[k]; half[k] = (T)s.half[k]; }
+    periodic = s.kind == JMD_SPACE_PERIODIC;
+    wrapped = s.wrapped;
+  }
+  // Exact displacement component d(a, b)_k (space.py:213-224).
+  __device__ __forceinline__ T disp(T a, T b, int k) const {
+    T d = sub_rn(a, b);
+    if (periodic) {
+      T t = add_rn(d, half[k]);
+      d = sub_rn(mod_pos(t, side[k]), half[k]);
+    }
+    return d;
+  }
+  // Fast minimum image for the force kernels (tolerance-level, not bit-level):
+  // positions may be unwrapped, so use rint.
+  __device__ __forceinline__ T disp_fast(T a, T b, int k) const {
+    T d = a - b;
+    if (periodic) {
+      T h = half[k];
+      if (d >= h) { d -= side[k]; if (d >= h) d -= side[k] * rint(d / side[k]); }
+      else if (d < -h) { d += side[k]; if (d < -h) d -= side[k] * rint(d / side[k]); }
+    }
+    return d;
+  }
+  // shift_fn (space.py:250-252 / 268-270)
+  __device__ __forceinline__ T shift(T r, T dr, int k) const {
+    T s = add_rn(r, dr);
+    if (periodic && wrapped) s = mod_pos(s, side[k]);
+    return s;
+  }
+};
+
+// Exact squared distance sum_k d_k^2, sequential (space.py:227-235).
+template <typename T, int DIM>
+__device__ __forceinline__ T dist2_exact(const Space<T, DIM>& sp, const T* a, const T* b) {
+  T dx = sp.disp(a[0], b[0], 0);
+  T acc = mul_rn(dx, dx);
+#pragma unroll
+  for (int k = 1; k < DIM; ++k) {
+    T d = sp.disp(a[k], b[k], k);
+    acc = add_rn(acc, mul_rn(d, d));
+  }
+  return acc;
+}
+
+// ---- block reduction of NV doubles, deterministic ----------------------------
+template <int NV, int BLOCK>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* smem /*[NV*BLOCK/32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    if (lane == 0) smem[i * (BLOCK / 32) + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = lane < BLOCK / 32 ? smem[i * (BLOCK / 32) + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      v[i] = x;
+    }
+  }
+  __syncthreads();
+}
+
+// Per-block partials -> final sum by the last block to finish (fixed order, so
+// results are bitwise reproducible).  partials: [gridDim.x, NV] then a ticket.
+template <int NV, int BLOCK>
+__device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* partials,
+                                                   unsigned int* ticket, double* out,
+                                                   const int* slots, double* smem) {
+  block_reduce<NV, BLOCK>(v, smem);
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) partials[(size_t)blockIdx.x * NV + i] = v[i];
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] += __ldcg(&partials[(size_t)b * NV + i]);
+  }
+  block_reduce<NV, BLOCK>(acc, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) out[slots[i]] = acc[i];
+    *ticket = 0u;
+  }
+}
+
+__host__ inline int64_t jmd_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,212 @@
+// Stillinger-Weber force / energy over Dense neighbour rows, atomics-free.
+//
+// Replaces energy.py:842-893 (+ :994-1012) and its autodiff gradient.  The
+// reference evaluates the full M x M neighbour square per atom (97 % masked for
+// diamond Si); here each thread owns one atom i and
+//   (1) loops the unordered in-range pairs (a, b) of its own row for the
+//       triplets centred on i (energy + force on i),
+//   (2) for every in-range neighbour j walks j's row for the triplets centred
+//       on j that have i as an end atom (force on i only).
+// So every force component is produced by exactly one thread in a fixed order:
+// no atomics, bitwise reproducible.  Needs symmetric rows (the Dense build
+// guarantees that).
+#include <cuda_runtime.h>
+#include <math.h>
+#include "jmd_common.cuh"
+
+namespace {
+
+constexpr int SWB = 128;
+
+template <typename T>
+struct SwP {
+  int n, m_int;
+  long long n_pad;
+  Space<T, 3> sp;
+  const typename Vec4<T>::type* pos_sorted;
+  const int* nl;
+  const int* cnt;
+  const int* perm;
+  T sigma, A, B, lam, gamma, eps, tbs, cutoff, a;
+  T* force;
+  double* red;
+  double* partials;
+  T* momentum;
+  const T* mass;
+  int mass_is_array;
+  T dt_2;
+  const T* dt_dev;
+  int kick;
+};
+
+// h(r) = exp(gamma / (r/sigma - a)) and dh/dr, r < cutoff
+template <typename T>
+__device__ __forceinline__ void sw_h(const SwP<T>& S, T r, T& h, T& dh) {
+  T x = r / S.sigma - S.a;
+  h = exp(S.gamma / x);
+  dh = -h * S.gamma / (S.sigma * x * x);
+}
+
+// triplet term g = h1 h2 (cos + 1/3)^2 with cos = d1.d2 / ((r1+1e-7)(r2+1e-7)),
+// clipped to [-1, 1] (quantity.py:285-289).  Returns g and dg/dd1, dg/dd2.
+template <typename T>
+__device__ __forceinline__ T sw_triplet(const SwP<T>& S, const T* d1, T r1, const T* d2, T r2, T* g1, T* g2) {
+  T h1, dh1, h2, dh2;
+  sw_h(S, r1, h1, dh1);
+  sw_h(S, r2, h2, dh2);
+  const T n1 = r1 + T(1e-7), n2 = r2 + T(1e-7);
+  const T dot = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
+  T c = dot / n1 / n2;
+  const bool live = (c >= T(-1)) && (c <= T(1));
+  const T cc = c < T(-1) ? T(-1) : (c > T(1) ? T(1) : c);
+  const T ct = cc + T(1.0 / 3.0);
+  const T hh = h1 * h2;
+  const T g = hh * ct * ct;
+  const T pre = live ? T(2) * hh * ct : T(0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const T u1 = d1[k] / r1, u2 = d2[k] / r2;
+    g1[k] = dh1 * h2 * ct * ct * u1 + pre * (d2[k] / (n1 * n2) - c / n1 * u1);
+    g2[k] = dh2 * h1 * ct * ct * u2 + pre * (d1[k] / (n1 * n2) - c / n2 * u2);
+  }
+  return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
+  using V4 = typename Vec4<T>::type;
+  const int t = blockIdx.x * SWB + threadIdx.x;
+  double rv[5] = {0, 0, 0, 0, 0};
+  if (t < S.n) {
+    const V4 pi = S.pos_sorted[t];
+    const int cnt = min(S.cnt[t], S.m_int);
+    const int* col = S.nl + t;
+    T f[3] = {0, 0, 0};
+    T e2 = 0, e3 = 0;
+    for (int ka = 0; ka < cnt; ++ka) {
+      const int j = __ldg(col + (size_t)ka * S.n_pad);
+      const V4 pj = S.pos_sorted[j];
+      T da[3];
+      da[0] = S.sp.disp_fast(pj.x, pi.x, 0);
+      da[1] = S.sp.disp_fast(pj.y, pi.y, 1);
+      da[2] = S.sp.disp_fast(pj.z, pi.z, 2);
+      const T ra = sqrt(da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
+      if (!(ra > T(0)) || !(ra < S.cutoff)) continue;
+      // two-body, energy.py:883-893: [B (r/s)^-4 - 1] exp(1/(r/s - a))
+      {
+        const T x = ra / S.sigma;
+        const T x2 = x * x;
+        const T t1 = S.B / (x2 * x2) - T(1);
+        const T xa = x - S.a;
+        const T t2 = exp(T(1) / xa);
+        e2 += t1 * t2;
+        const T df = (T(-4) * S.B / (x2 * x2 * x) * t2 - t1 * t2 / (xa * xa)) / S.sigma;
+        const T c2 = S.eps * S.A * df / ra;       // d/dR_i of (1/2)(f_ij + f_ji) = -df * da/ra
+        f[0] += c2 * da[0]; f[1] += c2 * da[1]; f[2] += c2 * da[2];
+      }
+      // (1) triplets centred on i: unordered pairs (a, b), b > a
+      for (int kb = ka + 1; kb < cnt; ++kb) {
+        const int k2 = __ldg(col + (size_t)kb * S.n_pad);
+        const V4 pk = S.pos_sorted[k2];
+        T db[3];
+        db[0] = S.sp.disp_fast(pk.x, pi.x, 0);
+        db[1] = S.sp.disp_fast(pk.y, pi.y, 1);
+        db[2] = S.sp.disp_fast(pk.z, pi.z, 2);
+        const T rb = sqrt(db[0] * db[0] + db[1] * db[1] + db[2] * db[2]);
+        if (!(rb > T(0)) || !(rb < S.cutoff)) continue;
+        const T s0 = da[0] - db[0], s1 = da[1] - db[1], s2 = da[2] - db[2];
+        if (!(sqrt(s0 * s0 + s1 * s1 + s2 * s2) > T(1e-5))) continue;    // energy.py:872-874
+        T g1[3], g2[3];
+        e3 += sw_triplet(S, da, ra, db, rb, g1, g2);
+        const T w = S.eps * S.lam * S.tbs;
+        // d_a = R_j - R_i, so dE/dR_i = -(g1 + g2); force = +w (g1 + g2)
+        f[0] += w * (g1[0] + g2[0]); f[1] += w * (g1[1] + g2[1]); f[2] += w * (g1[2] + g2[2]);
+      }
+      // (2) triplets centred on j with i as an end atom: d1 = R_i - R_j = -da
+      {
+        const T d1[3] = {-da[0], -da[1], -da[2]};
+        const int cj = min(S.cnt[j], S.m_int);
+        const int* colj = S.nl + j;
+        for (int kc = 0; kc < cj; ++kc) {
+          const int k3 = __ldg(colj + (size_t)kc * S.n_pad);
+          if (k3 == t) continue;
+          const V4 pk = S.pos_sorted[k3];
+          T dc[3];
+          dc[0] = S.sp.disp_fast(pk.x, pj.x, 0);
+          dc[1] = S.sp.disp_fast(pk.y, pj.y, 1);
+          dc[2] = S.sp.disp_fast(pk.z, pj.z, 2);
+          const T rc = sqrt(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]);
+          if (!(rc > T(0)) || !(rc < S.cutoff)) continue;
+          const T s0 = d1[0] - dc[0], s1 = d1[1] - dc[1], s2 = d1[2] - dc[2];
+          if (!(sqrt(s0 * s0 + s1 * s1 + s2 * s2) > T(1e-5))) continue;
+          T g1[3], g2[3];
+          sw_triplet(S, d1, ra, dc, rc, g1, g2);
+          const T w = S.eps * S.lam * S.tbs;
+          f[0] -= w * g1[0]; f[1] -= w * g1[1]; f[2] -= w * g1[2];
+        }
+      }
+    }
+    const int ai = S.perm[t];
+    T* fo = S.force + (size_t)ai * 3;
+    fo[0] = f[0]; fo[1] = f[1]; fo[2] = f[2];
+    // E = eps (A/2 sum f2 + tbs lam sum_unordered g)   (energy.py:1001-1012)
+    rv[0] = (double)(S.eps * (S.A * T(0.5) * e2 + S.tbs * S.lam * e3));
+    if (S.kick) {
+      T* po = S.momentum + (size_t)ai * 3;
+      const T m = S.mass_is_array ? S.mass[ai] : S.mass[0];
+      T ke = 0, ff = 0, pp = 0, fp = 0;
+      const T dt_2 = S.dt_dev ? (T)(float)((T)(float)(*S.dt_dev) / T(2)) : S.dt_2;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        T p = po[k] + dt_2 * f[k];
+        po[k] = p;
+        ke += p * p / m; ff += f[k] * f[k]; pp += p * p; fp += f[k] * p;
+      }
+      rv[1] = 0.5 * (double)ke; rv[2] = ff; rv[3] = pp; rv[4] = fp;
+    }
+  }
+  __shared__ double sm[5 * (SWB / 32)];
+  __shared__ int slots[5];
+  if (threadIdx.x == 0) {
+    slots[0] = JMD_RED_ENERGY; slots[1] = JMD_RED_KINETIC; slots[2] = JMD_RED_FF; slots[3] = JMD_RED_PP;
+    slots[4] = JMD_RED_FP;
+  }
+  __syncthreads();
+  grid_reduce_finish<5, SWB>(rv, S.partials + 2, (unsigned int*)S.partials, S.red, slots, sm);
+}
+
+template <typename T>
+int launch_sw(const jmd_nbr_t* nb, const jmd_sw_t* sw, void* force, double* red, double* partials,
+              void* momentum, const void* mass, int mass_is_array, double dt_2, const void* dt_dev,
+              cudaStream_t s) {
+  SwP<T> S;
+  S.n = nb->n; S.m_int = nb->m_int; S.n_pad = nb->n_pad;
+  S.sp.init(nb->space);
+  S.pos_sorted = (const typename Vec4<T>::type*)nb->pos_sorted;
+  S.nl = nb->nl; S.cnt = nb->cnt; S.perm = nb->perm;
+  S.sigma = (T)sw->sigma; S.A = (T)sw->A; S.B = (T)sw->B; S.lam = (T)sw->lam; S.gamma = (T)sw->gamma;
+  S.eps = (T)sw->epsilon; S.tbs = (T)sw->three_body_strength; S.cutoff = (T)sw->cutoff;
+  S.a = S.cutoff / S.sigma;
+  S.force = (T*)force; S.red = red; S.partials = partials;
+  S.momentum = (T*)momentum; S.mass = (const T*)mass; S.mass_is_array = mass_is_array; S.dt_2 = (T)dt_2;
+  S.dt_dev = (const T*)dt_dev;
+  S.kick = momentum != nullptr;
+  k_sw<T><<<(int)jmd_div_up(S.n > 0 ? S.n : 1, SWB), SWB, 0, s>>>(S);
+  JMD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int jmd_sw_force(const jmd_nbr_t* nb, const jmd_sw_t* sw, void* force, double* red, double* partials,
+                            void* momentum, const void* mass, int mass_is_array, double dt_2,
+                            const void* dt_dev, void* stream) {
+  if (!nb || !sw || !force || !red || !partials) return JMD_EINVAL;
+  if (nb->space.dim != 3 || nb->format != JMD_DENSE) return JMD_EINVAL;   // energy.py:1007-1010
+  if (momentum && !mass) return JMD_EINVAL;
+  if (nb->dtype == JMD_F32)
+    return launch_sw<float>(nb, sw, force, red, partials, momentum, mass, mass_is_array, dt_2, dt_dev, (cudaStream_t)stream);
+  if (nb->dtype == JMD_F64)
+    return launch_sw<double>(nb, sw, force, red, partials, momentum, mass, mass_is_array, dt_2, dt_dev, (cudaStream_t)stream);
+  return JMD_EINVAL;
+}

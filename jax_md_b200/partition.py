@@ -1,0 +1,436 @@
+"""Neighbour lists: drop-in for the reference `jax_md/partition.py`
+(`neighbor_list`, `NeighborList`, `NeighborListFns`, `NeighborListFormat`,
+`PartitionError(Code)`, `neighbor_list_mask`, `is_sparse`).
+
+Host logic (capacity rules, the cell-list decision, error-bit bookkeeping)
+follows partition.py:801-1164 line by line; all array work is done by
+libjmd_b200.so (csrc/jmd_neighbor.cu).  `allocate` syncs with the device to
+read occupancies, as the reference does (partition.py:249,1094); `update` never
+syncs and is CUDA-graph capturable.
+"""
+import ctypes as C
+import logging
+from enum import Enum, IntEnum
+from typing import Any, Callable, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, dataclasses, space
+
+f32 = np.float32
+i32 = np.int32
+
+
+class PartitionErrorCode(IntEnum):
+  """partition.py:494-520."""
+  NONE = 0
+  NEIGHBOR_LIST_OVERFLOW = 1 << 0
+  CELL_LIST_OVERFLOW = 1 << 1
+  CELL_SIZE_TOO_SMALL = 1 << 2
+  MALFORMED_BOX = 1 << 3
+
+
+PEC = PartitionErrorCode
+
+
+@dataclasses.dataclass
+class PartitionError:
+  """partition.py:523-561.  `code` is a uint8 device scalar."""
+  code: Any
+
+  def update(self, bit, pred):
+    zero = torch.zeros_like(self.code)
+    bit_t = torch.full_like(self.code, int(bit))
+    pred_t = torch.as_tensor(pred, device=self.code.device)
+    return PartitionError(self.code | torch.where(pred_t, bit_t, zero))
+
+  def __str__(self):
+    code = int(self.code)
+    if code == PEC.NONE:
+      return ''
+    if code & PEC.NEIGHBOR_LIST_OVERFLOW:
+      return 'Partition Error: Neighbor list buffer overflow.'
+    if code & PEC.CELL_LIST_OVERFLOW:
+      return 'Partition Error: Cell list buffer overflow'
+    if code & PEC.CELL_SIZE_TOO_SMALL:
+      return 'Partition Error: Cell size too small'
+    if code & PEC.MALFORMED_BOX:
+      return 'Partition Error: Incorrect box format. Expecting upper triangular.'
+    raise ValueError(f'Unexpected error code {code}.')
+
+  __repr__ = __str__
+
+
+class NeighborListFormat(Enum):
+  """partition.py:641-657."""
+  Dense = 0
+  Sparse = 1
+  OrderedSparse = 2
+
+
+Dense = NeighborListFormat.Dense
+Sparse = NeighborListFormat.Sparse
+OrderedSparse = NeighborListFormat.OrderedSparse
+
+
+def is_sparse(fmt: NeighborListFormat) -> bool:
+  return fmt is Sparse or fmt is OrderedSparse
+
+
+def is_format_valid(fmt):
+  if fmt not in list(NeighborListFormat):
+    raise ValueError('Neighbor list format must be a member of '
+                     f'NeighborListFormat found {fmt}.')
+
+
+# ----------------------------------------------------------------------------
+# device workspace: the hidden part of a NeighborList
+# ----------------------------------------------------------------------------
+
+class Workspace:
+  """Owns the device buffers behind one allocated neighbour list and the
+  `jmd_nbr_t` descriptor handed to the C ABI."""
+
+  def __init__(self, n, dim, dtype, device):
+    self.n, self.dim, self.dtype, self.device = n, dim, dtype, device
+    self.c = _lib.NbrT()
+    self.t = {}          # name -> tensor (keeps buffers alive)
+    self.species = None
+    self.update_mode = 'tail'   # 'tail' | 'gated'
+
+  def buf(self, name, shape, dtype, fill=None):
+    if fill is None:
+      t = torch.empty(shape, dtype=dtype, device=self.device)
+    else:
+      t = torch.full(shape, fill, dtype=dtype, device=self.device)
+    self.t[name] = t
+    setattr(self.c, name, t.data_ptr())
+    return t
+
+  def ref(self):
+    return C.byref(self.c)
+
+  def set_species(self, species):
+    """Registers per-atom species ids (copied into pos_sorted.w on every
+    refresh); None clears it."""
+    if species is None:
+      self.species = None
+      self.c.species = None
+      return
+    if species.dtype != torch.int32 or not species.is_contiguous():
+      species = species.to(torch.int32).contiguous()
+    self.species = species
+    self.c.species = species.data_ptr()
+
+  def state_host(self):
+    out = (C.c_int64 * _lib.ST_COUNT)()
+    _lib.call('jmd_nbr_state_host', self.ref(), out, _lib.stream())
+    return list(out)
+
+
+@dataclasses.dataclass
+class NeighborList:
+  """partition.py:684-737 (same field names / static-dynamic split).
+
+  `idx` is materialised in the requested format on every rebuild.  `_ws` is
+  the hidden device workspace (cell-sorted float4 positions, permutation and
+  the transposed full-row list the force kernels read); updates reuse these
+  buffers in place, like the reference under jit with donated buffers."""
+  idx: Any
+  reference_position: Any
+  error: PartitionError
+  cell_list_capacity: Optional[int] = dataclasses.static_field()
+  max_occupancy: int = dataclasses.static_field()
+  format: NeighborListFormat = dataclasses.static_field()
+  cell_size: Any = dataclasses.static_field()
+  cell_list_fn: Any = dataclasses.static_field()
+  update_fn: Callable = dataclasses.static_field()
+  _ws: Any = dataclasses.static_field(default=None)
+
+  def update(self, position, **kwargs) -> 'NeighborList':
+    return self.update_fn(position, self, **kwargs)
+
+  @property
+  def did_buffer_overflow(self):
+    return self.error.code & (PEC.NEIGHBOR_LIST_OVERFLOW | PEC.CELL_LIST_OVERFLOW)
+
+  @property
+  def cell_size_too_small(self):
+    return self.error.code & PEC.CELL_SIZE_TOO_SMALL
+
+  @property
+  def malformed_box(self):
+    return self.error.code & PEC.MALFORMED_BOX
+
+  @property
+  def internal_list_is_current(self) -> bool:
+    """True while `idx` is the array our builder wrote (nobody swapped it)."""
+    return self._ws is not None and self._ws.t.get('idx') is self.idx
+
+
+@dataclasses.dataclass
+class NeighborListFns:
+  """partition.py:740-785."""
+  allocate: Callable = dataclasses.static_field()
+  update: Callable = dataclasses.static_field()
+
+  def __call__(self, position, neighbors=None, extra_capacity: int = 0,
+               **kwargs):
+    logging.warning('Using a deprecated code path to create / update neighbor '
+                    'lists. Using `neighbor_fn.allocate` and '
+                    '`neighbor_fn.update` is preferred.')
+    if neighbors is None:
+      return self.allocate(position, extra_capacity, **kwargs)
+    return self.update(position, neighbors, **kwargs)
+
+  def __iter__(self):
+    return iter((self.allocate, self.update))
+
+
+def _cell_dimensions(spatial_dimension, box_size, minimum_cell_size):
+  """partition.py:146-188 (NumPy on the host, as in the reference)."""
+  if isinstance(box_size, (int, float)):
+    box_size = float(box_size)
+  cells_per_side = np.floor(box_size / minimum_cell_size)
+  cell_size = box_size / cells_per_side
+  cells_per_side = np.array(cells_per_side, dtype=i32)
+  if isinstance(box_size, np.ndarray):
+    if box_size.ndim == 1 or box_size.ndim == 2:
+      assert box_size.size == spatial_dimension
+      flat = np.reshape(cells_per_side, (-1,))
+      for cells in flat:
+        if cells < 3:
+          raise ValueError('Box must be at least 3x the size of the grid '
+                           'spacing in each dimension.')
+      cell_count = int(np.prod(flat.astype(np.int64)))
+    elif box_size.ndim == 0:
+      cell_count = int(cells_per_side) ** spatial_dimension
+    else:
+      raise ValueError('Box must be either: a scalar, a vector, or a matrix. '
+                       f'Found {box_size}.')
+  else:
+    cell_count = int(cells_per_side) ** spatial_dimension
+  return box_size, cell_size, cells_per_side, int(cell_count)
+
+
+def _host_scalar(x):
+  """Python / NumPy scalar view of a (possibly torch) scalar, keeping dtype."""
+  if isinstance(x, torch.Tensor):
+    return x.detach().cpu().numpy()[()]
+  return x
+
+
+def neighbor_list(displacement_or_metric,
+                  box,
+                  r_cutoff,
+                  dr_threshold=0.0,
+                  capacity_multiplier: float = 1.25,
+                  disable_cell_list: bool = False,
+                  mask_self: bool = True,
+                  custom_mask_function=None,
+                  fractional_coordinates: bool = False,
+                  format: NeighborListFormat = NeighborListFormat.Dense,
+                  **static_kwargs) -> NeighborListFns:
+  """partition.py:801-1164.  Same arguments, same allocate/update contract,
+  same capacity rules and error bits; the displacement function must come from
+  `jax_md_b200.space` so its metric can be inlined into the kernels."""
+  is_format_valid(format)
+  if fractional_coordinates:
+    raise NotImplementedError(
+        'fractional_coordinates / periodic_general: SURVEY.md 8(f) row 3.')
+  if custom_mask_function is not None:
+    raise NotImplementedError(
+        'custom_mask_function needs the uncompacted [N, 3^d*capacity] candidate '
+        'array (partition.py:1079-1080); not provided by the fused build.')
+  spec = space.get_spec(displacement_or_metric)
+  r_cutoff = _host_scalar(r_cutoff)
+  dr_threshold = _host_scalar(dr_threshold)
+  _always_rebuild = bool(dr_threshold == 0)                       # :892
+  box_np = _host_scalar(box)
+  box_np = f32(box_np) if np.ndim(box_np) == 0 else np.asarray(box_np, f32)  # :897
+  if np.ndim(box_np) == 2:
+    raise NotImplementedError('matrix boxes: SURVEY.md 8(f) row 3.')
+  cutoff = r_cutoff + dr_threshold                                # :899
+  cutoff_sq = cutoff ** 2                                         # :900
+  threshold_sq = (dr_threshold / f32(2)) ** 2                     # :901
+  fmt_code = {Dense: _lib.DENSE, Sparse: _lib.SPARSE,
+              OrderedSparse: _lib.ORDERED_SPARSE}[format]
+
+  def _typed(x, np_dtype):
+    # `arr < python_float` compares in the array dtype (weak type); an f32
+    # NumPy scalar against an f64 array promotes exactly.
+    return float(np_dtype(x)) if isinstance(x, (float, int)) else float(x)
+
+  def _make_workspace(position, extra_capacity):
+    _lib.require_cuda()
+    if not isinstance(position, torch.Tensor) or not position.is_cuda:
+      raise TypeError('positions must be a CUDA torch.Tensor [N, dim]')
+    N, dim = position.shape
+    if dim not in (2, 3):
+      raise ValueError(f'Cell list spatial dimension must be 2 or 3. Found {dim}.')
+    np_dtype = np.float32 if position.dtype == torch.float32 else np.float64
+    ws = Workspace(N, dim, position.dtype, position.device)
+    c = ws.c
+    c.n, c.dtype, c.format = N, _lib.dtype_code(position.dtype), fmt_code
+    c.mask_self = 1 if mask_self else 0
+    c.always_rebuild = 1 if _always_rebuild else 0
+    c.cutoff_sq = _typed(cutoff_sq, np_dtype)
+    c.threshold_sq = _typed(threshold_sq, np_dtype)
+    c.space = space.space_struct(spec, dim, position.dtype)
+    c.n_pad = ((N + 31) // 32) * 32 if N else 32
+
+    use_cells, cell_size, cps, n_cells = False, None, np.ones(3, i32), 0
+    if not disable_cell_list:
+      cell_size = cutoff                                           # :1046
+      if np.all(np.asarray(cell_size) < box_np / 3.0):             # :1052
+        _, cs, cpside, n_cells = _cell_dimensions(dim, box_np, cell_size)
+        use_cells = True
+        cps[:dim] = np.broadcast_to(np.reshape(cpside, (-1,)), (dim,))
+        cs = np.broadcast_to(np.reshape(np.asarray(cs, f32), (-1,)), (dim,))
+        for k in range(dim):
+          c.cell_size[k] = float(cs[k])
+    c.use_cells = 1 if use_cells else 0
+    for k in range(3):
+      c.cps[k] = int(cps[k])
+    c.n_cells = n_cells
+    i4 = torch.int32
+    ws.buf('cell_count', (n_cells + 1,), i4, 0)
+    ws.buf('cell_start', (n_cells + 1,), i4, 0)
+    ws.buf('cell_cursor', (max(n_cells, 1),), i4, 0)
+    ws.buf('scan_tmp', (2 * (max(n_cells, N) // 2048 + 2) + 16,), i4, 0)
+    ws.buf('hash', (max(N, 1),), i4)
+    ws.buf('tmp_ids', (max(N, 1),), i4)
+    ws.buf('perm', (c.n_pad,), i4, 0)
+    ws.buf('inv_perm', (max(N, 1),), i4)
+    ws.buf('pos_sorted', (c.n_pad, 4), position.dtype, 0)
+    ws.buf('cnt', (c.n_pad,), i4, 0)
+    ws.buf('cnt_lower', (c.n_pad,), i4, 0)
+    ws.buf('offsets', (N + 1,), torch.int64, 0)
+    ws.buf('reference_position', (N, dim), position.dtype)
+    ws.buf('error', (), torch.uint8, 0)
+    ws.buf('state', (_lib.ST_COUNT,), torch.int64, 0)
+    ws.cell_size_host = cell_size
+    ws.use_cells = use_cells
+    return ws
+
+  def allocate_fn(position, extra_capacity: int = 0, **kwargs):
+    """partition.py:1156-1157 -> neighbor_fn with neighbors=None (not jittable:
+    reads occupancies back to the host)."""
+    if 'box' in kwargs:
+      raise ValueError('Neighbor list cannot accept a box keyword argument if '
+                       'fractional_coordinates is not enabled.')
+    position = position.contiguous()
+    ws = _make_workspace(position, extra_capacity)
+    c, N, dim = ws.c, ws.n, ws.dim
+    st, pp = _lib.stream(), _lib.ptr(position)
+    # -- cell capacity (partition.py:243-250, 369-373)
+    c.cell_capacity = 1
+    c.m_int, c.max_occupancy = 1, 1
+    _lib.call('jmd_nbr_bin', ws.ref(), pp, 0, st)
+    cl_capacity = None
+    if ws.use_cells:
+      max_cell = ws.state_host()[_lib.ST_MAX_CELL_OCC]
+      cl_capacity = int(max_cell * capacity_multiplier) + extra_capacity
+      c.cell_capacity = cl_capacity
+      width = 3 ** dim * cl_capacity
+    else:
+      width = N
+    # -- occupancy pass (partition.py:1083-1088)
+    _lib.call('jmd_nbr_build', ws.ref(), pp, 1, 0, st)
+    state = ws.state_host()
+    max_row, total = state[_lib.ST_MAX_ROW], state[_lib.ST_TOTAL]
+    sparse = is_sparse(format)
+    occupancy = total if sparse else max_row
+    full_width = N * width if sparse else width
+    # -- capacity rule (partition.py:1090-1104)
+    _extra = extra_capacity if not sparse else N * extra_capacity
+    max_occupancy = int(occupancy * capacity_multiplier + _extra)
+    if max_occupancy > full_width:
+      max_occupancy = full_width
+    if not sparse:
+      capacity_limit = N - 1 if mask_self else N
+    elif format is Sparse:
+      capacity_limit = N * (N - 1) if mask_self else N ** 2
+    else:
+      capacity_limit = N * (N - 1) // 2
+    if max_occupancy > capacity_limit:
+      max_occupancy = capacity_limit
+    # internal full rows: Dense uses the public capacity; sparse formats get the
+    # Dense-equivalent rule on the longest row ("row capacity").
+    if sparse:
+      m_int = min(int(max_row * capacity_multiplier + extra_capacity), width,
+                  N - 1 if mask_self else N)
+    else:
+      m_int = max_occupancy
+    c.max_occupancy = max_occupancy
+    c.m_int = max(m_int, 1)
+    ws.buf('nl', (c.m_int, c.n_pad), torch.int32)
+    if sparse:
+      idx = ws.buf('idx', (2, max_occupancy), torch.int32, N)
+    else:
+      idx = ws.buf('idx', (N, max_occupancy), torch.int32, N)
+    if idx.numel() == 0:
+      c.idx = None
+    _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 0, st)
+    _lib.call('jmd_nbr_export', ws.ref(), pp, 0, st)
+    return NeighborList(idx, ws.t['reference_position'],
+                        PartitionError(ws.t['error']), cl_capacity,
+                        max_occupancy, format, ws.cell_size_host,
+                        'cell_list' if ws.use_cells else None, update_fn, ws)
+
+  def update_fn(position, neighbors, **kwargs):
+    """partition.py:1159-1160 / 1119-1154.  Never syncs with the host."""
+    if 'box' in kwargs and not disable_cell_list:
+      raise ValueError('Neighbor list cannot accept a box keyword argument if '
+                       'fractional_coordinates is not enabled.')
+    ws = neighbors._ws
+    if ws is None:
+      raise ValueError('This NeighborList was not allocated by jax_md_b200.')
+    if position.shape != (ws.n, ws.dim) or position.dtype != ws.dtype:
+      raise ValueError('position shape/dtype differs from the allocated list')
+    position = position.contiguous()
+    st, pp = _lib.stream(), _lib.ptr(position)
+    if ws.update_mode == 'tail':
+      _lib.call('jmd_nbr_skin_check', ws.ref(), pp, 1, st)
+    else:
+      _lib.call('jmd_nbr_skin_check', ws.ref(), pp, 0, st)
+      _lib.call('jmd_nbr_bin', ws.ref(), pp, 1, st)
+      _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 1, st)
+      _lib.call('jmd_nbr_export', ws.ref(), pp, 1, st)
+    return neighbors
+
+  return NeighborListFns(allocate_fn, update_fn)
+
+
+def neighbor_list_mask(neighbor: NeighborList, mask_self: bool = False):
+  """partition.py:1167-1182."""
+  N = len(neighbor.reference_position)
+  if is_sparse(neighbor.format):
+    mask = neighbor.idx[0] < N
+    if mask_self:
+      mask = mask & (neighbor.idx[0] != neighbor.idx[1])
+    return mask
+  mask = neighbor.idx < len(neighbor.idx)
+  if mask_self:
+    rows = torch.arange(N, dtype=torch.int32, device=neighbor.idx.device)
+    mask = mask & (neighbor.idx != rows[:, None])
+  return mask
+
+
+def to_dense(neighbor: NeighborList):
+  """partition.py:1245-1265 (host-side utility, torch ops)."""
+  if neighbor.format is not Sparse:
+    raise ValueError('Can only convert sparse neighbor lists to dense ones.')
+  receivers, senders = neighbor.idx
+  mask = neighbor_list_mask(neighbor)
+  receivers, senders = receivers[mask].long(), senders[mask].long()
+  N = len(neighbor.reference_position)
+  count = torch.bincount(receivers, minlength=N)
+  max_count = int(count.max())
+  offset = torch.arange(max_count, device=receivers.device).repeat(N)[:len(senders)]
+  hashes = senders * max_count + offset
+  dense_idx = torch.full((N * max_count,), N, dtype=torch.int32,
+                         device=receivers.device)
+  dense_idx[hashes] = receivers.to(torch.int32)
+  return dense_idx.reshape(N, max_count)

@@ -1,0 +1,318 @@
+"""Integrators on the B200 hot path: drop-in for `simulate.nve` and
+`simulate.nvt_nose_hoover` of the reference (jax_md/simulate.py:279-317,
+565-669), with the same `(init_fn, apply_fn)` contract and state field names.
+
+When the energy function is one of this package's fused neighbour-list
+energies and `shift_fn` comes from `jax_md_b200.space`, one MD step is two
+kernels:
+   jmd_nve_kick_drift   p += dt/2 F;  R = shift(R, dt p / m);  refresh the
+                        cell-sorted float4 positions        (simulate.py:238-239)
+   jmd_pair_force       F = -dE/dR over the full neighbour rows, fused with
+                        p += dt/2 F and the KE/|F|^2/|P|^2/F.P reductions
+                                                            (simulate.py:240-241)
+Otherwise the same two integrator kernels bracket a call to the user's force
+function.  No step synchronises with the host.
+"""
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib, dataclasses, quantity, smap, space
+
+f32 = np.float32
+
+SUZUKI_YOSHIDA_WEIGHTS = {
+    1: [1],
+    3: [0.828981543588751, -0.657963087177502, 0.828981543588751],
+    5: [0.2967324292201065, 0.2967324292201065, -0.186929716880426,
+        0.2967324292201065, 0.2967324292201065],
+    7: [0.784513610477560, 0.235573213359357, -1.17767998417887,
+        1.31518632068391, -1.17767998417887, 0.235573213359357,
+        0.784513610477560],
+}
+
+
+def _canonical_mass(mass, R):
+  """simulate.canonicalize_mass (simulate.py:119-138): float stays scalar,
+  [N] becomes [N, 1].  Kernels take the flat view."""
+  if isinstance(mass, torch.Tensor):
+    m = mass.to(device=R.device, dtype=R.dtype)
+    if m.ndim == 1 and m.numel() > 1:
+      m = m.reshape(-1, 1)
+    elif m.ndim == 0:
+      m = m.reshape(1)
+    return m.contiguous()
+  m = np.asarray(mass)
+  if m.ndim == 0:
+    return torch.full((1,), float(m), dtype=R.dtype, device=R.device)
+  t = torch.as_tensor(m, dtype=R.dtype, device=R.device)
+  return t.reshape(-1, 1).contiguous() if t.ndim == 1 else t.contiguous()
+
+
+def _generator(key, device):
+  if isinstance(key, torch.Generator):
+    return key
+  g = torch.Generator(device=device)
+  seed = int(key) if not isinstance(key, torch.Tensor) else int(key.flatten()[0])
+  g.manual_seed(seed)
+  return g
+
+
+def initialize_momenta(R, mass, key, kT):
+  """simulate.py:141-159: Maxwell-Boltzmann, centred when N > 1."""
+  g = _generator(key, R.device)
+  p = torch.sqrt(mass * kT) * torch.randn(R.shape, dtype=R.dtype, device=R.device,
+                                          generator=g)
+  if R.shape[0] > 1:
+    p = p - p.mean(dim=0, keepdim=True)
+  return p
+
+
+@dataclasses.dataclass
+class NVEState:
+  """simulate.py:249-275."""
+  position: Any
+  momentum: Any
+  force: Any
+  mass: Any
+
+  @property
+  def velocity(self):
+    return self.momentum / self.mass
+
+
+class _Stepper:
+  """Shared machinery of nve / nvt / fire: the two-kernel velocity Verlet."""
+
+  def __init__(self, energy_or_force_fn, shift_fn, dt):
+    self.fn = energy_or_force_fn
+    self.fused = getattr(energy_or_force_fn, '_jmd_fused', None)
+    self.force_fn = quantity.canonicalize_force(energy_or_force_fn)
+    self.spec = space.get_spec(shift_fn)
+    self.dt = float(f32(dt))
+    self.dt_2 = float(f32(f32(dt) / 2))
+    self._sp = {}
+    self._red = {}
+
+  def space_struct(self, R):
+    key = (R.shape[1], R.dtype)
+    st = self._sp.get(key)
+    if st is None:
+      st = space.space_struct(self.spec, R.shape[1], R.dtype)
+      self._sp[key] = st
+    return st
+
+  def red(self, R):
+    key = (str(R.device),)
+    r = self._red.get(key)
+    if r is None:
+      r = torch.zeros(_lib.RED_COUNT, dtype=torch.float64, device=R.device)
+      self._red[key] = r
+    return r
+
+  def force(self, R, kwargs):
+    return self.force_fn(R, **kwargs)
+
+  def step(self, R, P, F, mass, kwargs, dt=None, dt_dev=None, scale_dev=None):
+    """One velocity-Verlet step (simulate.py:227-243) -> (R', P', F')."""
+    import ctypes as C
+    _lib.require_cuda()
+    N, dim = R.shape
+    dtc = _lib.dtype_code(R.dtype)
+    dt_h = self.dt if dt is None else float(f32(dt))
+    dt2_h = self.dt_2 if dt is None else float(f32(f32(dt) / 2))
+    neighbor = kwargs.get('neighbor')
+    fused = bool(self.fused) and neighbor is not None and \
+        getattr(neighbor, '_ws', None) is not None and \
+        neighbor.internal_list_is_current
+    sp = self.space_struct(R)
+    R2 = torch.empty_like(R)
+    P2 = torch.empty_like(P)
+    mass_is_array = 1 if mass.numel() > 1 else 0
+    red = self.red(R)
+    st = _lib.stream()
+    nb_ref = None
+    if fused:
+      ws = neighbor._ws
+      if self.fused == 'pair':
+        kw = dict(kwargs)
+        kw.pop('neighbor')
+        _, species, params = self.fn._resolve(neighbor, kw)
+        ws.set_species(self.fn._species_tensor(species, R.device))
+      else:
+        ws.set_species(None)
+      nb_ref = ws.ref()
+    _lib.call('jmd_nve_kick_drift', C.byref(sp), dtc, N, nb_ref, _lib.ptr(R),
+              _lib.ptr(P), _lib.ptr(F), _lib.ptr(mass), mass_is_array, dt_h,
+              _lib.ptr(dt_dev), _lib.ptr(scale_dev), _lib.ptr(R2), _lib.ptr(P2),
+              st)
+    if fused and self.fused == 'pair':
+      out = self.fn.launch(R2, neighbor, species, params, want_energy=False,
+                           momentum=P2, mass=mass, dt_2=dt2_h, dt_dev=dt_dev,
+                           red=red, refresh_positions=False)
+      F2 = out['force']
+    elif fused:
+      out = self.fn.launch(R2, neighbor, momentum=P2, mass=mass, dt_2=dt2_h,
+                           dt_dev=dt_dev, red=red, refresh_positions=False)
+      F2 = out['force']
+    else:
+      F2 = self.force(R2, kwargs).contiguous()
+      partials = smap.Scratch.get(N, R.device)
+      _lib.call('jmd_kick_reduce', dtc, N, dim, _lib.ptr(P2), _lib.ptr(F2),
+                _lib.ptr(mass), mass_is_array, dt2_h, _lib.ptr(dt_dev),
+                _lib.ptr(red), _lib.ptr(partials), st)
+    return R2, P2, F2
+
+
+def nve(energy_or_force_fn, shift_fn, dt=1e-3, **sim_kwargs):
+  """simulate.py:279-317."""
+  stepper = _Stepper(energy_or_force_fn, shift_fn, dt)
+
+  def init_fn(key, R, kT, mass=f32(1.0), momenta=None, **kwargs):
+    R = R.contiguous()
+    force = stepper.force(R, kwargs).contiguous()
+    m = _canonical_mass(mass, R)
+    if momenta is None:
+      P = initialize_momenta(R, m, key, kT)
+    else:
+      P = momenta.to(dtype=R.dtype, device=R.device)
+    return NVEState(R, P.contiguous(), force, m)
+
+  def step_fn(state, **kwargs):
+    _dt = kwargs.pop('dt', None)
+    dt_dev = _dt if isinstance(_dt, torch.Tensor) else None
+    R, P, F = stepper.step(state.position, state.momentum, state.force,
+                           state.mass, kwargs,
+                           dt=None if dt_dev is not None else _dt, dt_dev=dt_dev)
+    return state.set(position=R, momentum=P, force=F)
+
+  step_fn._stepper = stepper
+  return init_fn, step_fn
+
+
+# -- Nose-Hoover chain -----------------------------------------------------------
+
+@dataclasses.dataclass
+class NoseHooverChain:
+  """simulate.py:350-374.  The fields are views into one device buffer laid
+  out [xi | p_xi | Q | KE] that the single-thread chain kernel updates."""
+  position: Any
+  momentum: Any
+  mass: Any
+  tau: Any
+  kinetic_energy: Any
+  degrees_of_freedom: int = dataclasses.static_field()
+  _buf: Any = dataclasses.static_field(default=None)
+
+
+def _make_chain(buf, cl, tau, dof):
+  return NoseHooverChain(buf[0:cl], buf[cl:2 * cl], buf[2 * cl:3 * cl], tau,
+                         buf[3 * cl], dof, buf)
+
+
+@dataclasses.dataclass
+class NVTNoseHooverState:
+  """simulate.py:538-562."""
+  position: Any
+  momentum: Any
+  force: Any
+  mass: Any
+  chain: NoseHooverChain
+
+  @property
+  def velocity(self):
+    return self.momentum / self.mass
+
+
+def nvt_nose_hoover(energy_or_force_fn, shift_fn, dt, kT, chain_length=5,
+                    chain_steps=2, sy_steps=3, tau=None, **sim_kwargs):
+  """simulate.py:565-669."""
+  stepper = _Stepper(energy_or_force_fn, shift_fn, dt)
+  dt_f = f32(dt)
+  if tau is None:
+    tau = dt_f * 100
+  tau = f32(tau)
+  if sy_steps not in SUZUKI_YOSHIDA_WEIGHTS:
+    raise ValueError('sy_steps must be 1, 3, 5 or 7')
+  kT_cache = {}
+
+  def _kT_dev(_kT, R):
+    if isinstance(_kT, torch.Tensor):
+      return _kT.to(device=R.device, dtype=R.dtype).reshape(1)
+    key = (float(_kT), R.dtype, str(R.device))
+    t = kT_cache.get(key)
+    if t is None:
+      t = torch.full((1,), float(_kT), dtype=R.dtype, device=R.device)
+      kT_cache[key] = t
+    return t
+
+  def _half_step(state_chain, kT_t, R, ke_red):
+    dtc = _lib.dtype_code(R.dtype)
+    scale = torch.empty((1,), dtype=R.dtype, device=R.device)
+    _lib.call('jmd_nhc_half_step', dtc, chain_length, chain_steps, sy_steps,
+              float(dt_f), float(tau), int(state_chain.degrees_of_freedom),
+              _lib.ptr(kT_t), _lib.ptr(state_chain._buf),
+              None if ke_red is None else
+              (ke_red.data_ptr() + 8 * _lib.RED_KINETIC),
+              _lib.ptr(scale), _lib.stream())
+    return scale
+
+  def init_fn(key, R, mass=f32(1.0), momenta=None, **kwargs):
+    _kT = kT if 'kT' not in kwargs else kwargs.pop('kT')
+    R = R.contiguous()
+    dof = quantity.count_dof(R)
+    force = stepper.force(R, kwargs).contiguous()
+    m = _canonical_mass(mass, R)
+    if momenta is None:
+      P = initialize_momenta(R, m, key, _kT)
+    else:
+      P = momenta.to(dtype=R.dtype, device=R.device)
+    P = P.contiguous()
+    KE = quantity.kinetic_energy(momentum=P, mass=m)
+    buf = torch.zeros(3 * chain_length + 1, dtype=R.dtype, device=R.device)
+    Q = float(_kT) * float(tau) ** 2                       # simulate.py:440-442
+    buf[2 * chain_length:3 * chain_length] = float(f32(Q))
+    buf[2 * chain_length] = float(f32(f32(Q) * dof))
+    buf[3 * chain_length] = KE
+    return NVTNoseHooverState(R, P, force, m,
+                              _make_chain(buf, chain_length, tau, dof))
+
+  def apply_fn(state, **kwargs):
+    _kT = kT if 'kT' not in kwargs else kwargs.pop('kT')
+    R = state.position
+    kT_t = _kT_dev(_kT, R)
+    chain = state.chain
+    # update_mass + first half step on the carried KE (simulate.py:654-658)
+    s1 = _half_step(chain, kT_t, R, None)
+    R2, P2, F2 = stepper.step(R, state.momentum, state.force, state.mass,
+                              kwargs, scale_dev=s1)
+    # chain.KE = KE(p) from the fused reduction, second half step (:660-665)
+    s2 = _half_step(chain, kT_t, R, stepper.red(R))
+    _lib.call('jmd_scale_momentum', _lib.dtype_code(R.dtype), P2.numel(),
+              _lib.ptr(P2), _lib.ptr(s2), _lib.stream())
+    return state.set(position=R2, momentum=P2, force=F2)
+
+  apply_fn._stepper = stepper
+  return init_fn, apply_fn
+
+
+def nvt_nose_hoover_invariant(energy_fn, state, kT, **kwargs):
+  """simulate.py:672-701."""
+  PE = energy_fn(state.position, **kwargs)
+  KE = quantity.kinetic_energy(momentum=state.momentum, mass=state.mass)
+  DOF = quantity.count_dof(state.position)
+  E = PE + KE
+  c = state.chain
+  E = E + c.momentum[0] ** 2 / (2 * c.mass[0]) + DOF * kT * c.position[0]
+  for r, p, m in zip(c.position[1:], c.momentum[1:], c.mass[1:]):
+    E = E + p ** 2 / (2 * m) + kT * r
+  return E
+
+
+def kinetic_energy(state):
+  return quantity.kinetic_energy(momentum=state.momentum, mass=state.mass)
+
+
+def temperature(state):
+  return quantity.temperature(momentum=state.momentum, mass=state.mass)

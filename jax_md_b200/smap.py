@@ -1,0 +1,263 @@
+"""`smap.pair_neighbor_list`: drop-in for jax_md/smap.py:856-979 for the pair
+potentials of this package (Lennard-Jones, soft sphere, Morse, optionally
+wrapped in `energy.multiplicative_isotropic_cutoff`).
+
+The mapped function has the reference signature
+`fn_mapped(R, neighbor, **dynamic_kwargs)` and returns the total energy (or
+per-atom energies with `reduce_axis=(1,)`).  Instead of gather + vmap + sum it
+launches the fused CUDA kernel over the neighbour list's internal full rows.
+Gradients with respect to positions and to `sigma` / `epsilon` are served by a
+custom backward (the reference's `jax.custom_vjp` role is played by
+`torch.autograd.Function`): the forward kernel already produced
+F = -dE/dR, dE/dsigma and dE/depsilon.  Higher-order derivatives are out of
+scope.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, partition, space
+
+_DEFAULTS = {
+    _lib.POT_LJ: {'sigma': 1.0, 'epsilon': 1.0, 'alpha': 1.0},
+    _lib.POT_SOFT_SPHERE: {'sigma': 1.0, 'epsilon': 1.0, 'alpha': 2.0},
+    _lib.POT_MORSE: {'sigma': 1.0, 'epsilon': 5.0, 'alpha': 5.0},
+}
+_PARAM_ORDER = ('sigma', 'epsilon', 'alpha')
+
+
+class Scratch:
+  """Per-(device, n) reduction scratch shared by the force kernels."""
+  _cache = {}
+
+  @classmethod
+  def get(cls, n, device):
+    key = (int(n), str(device))
+    s = cls._cache.get(key)
+    if s is None:
+      nd = _lib.load().jmd_red_scratch_doubles(int(n))
+      s = torch.zeros(nd, dtype=torch.float64, device=device)
+      cls._cache[key] = s
+    return s
+
+
+def _merge(static, dynamic, ignore_unused):
+  """util.merge_dicts (util.py:57-79)."""
+  if not ignore_unused:
+    return {**static, **dynamic}
+  merged = dict(static)
+  for k in static:
+    if dynamic.get(k) is not None:
+      merged[k] = dynamic[k]
+  return merged
+
+
+class PairNeighborListFn:
+  """Callable returned by `pair_neighbor_list`."""
+  _jmd_fused = 'pair'
+
+  def __init__(self, pot, displacement_or_metric, species, reduce_axis,
+               ignore_unused_parameters, kwargs):
+    self.pot = pot                      # dict(kind, r_onset, r_cutoff)
+    self.spec = space.get_spec(displacement_or_metric)
+    self.species = species
+    self.reduce_axis = reduce_axis
+    self.ignore_unused = ignore_unused_parameters
+    self.kwargs = dict(kwargs)
+    self.kwargs.pop('fractional_coordinates', None)   # energy.py:240,340,443
+    self._conv = {}
+    if reduce_axis is not None:
+      if len(reduce_axis) == 0:
+        raise NotImplementedError('reduce_axis=() (per-edge output) is not '
+                                  'provided by the fused kernel.')
+      if 0 in reduce_axis and 1 not in reduce_axis:
+        raise ValueError()
+
+  # -- parameter canonicalisation (smap.py:697-846) ---------------------------
+  def _tensor(self, x, dtype, device):
+    key = (id(x), dtype)
+    hit = self._conv.get(key)
+    if hit is not None and hit[0] is x:
+      return hit[1]
+    if isinstance(x, torch.Tensor):
+      t = x.detach().to(device=device, dtype=dtype).contiguous()
+    else:
+      t = torch.as_tensor(np.asarray(x), dtype=dtype, device=device).contiguous()
+    if len(self._conv) > 64:
+      self._conv.clear()
+    self._conv[key] = (x, t)
+    return t
+
+  def _pair_struct(self, R, species, params, sparse=False):
+    pt = _lib.PairT()
+    pt.transposed = 1 if sparse else 0
+    keep = []
+    kind = self.pot['kind']
+    pt.kind = kind
+    pt.has_cutoff = 1 if self.pot.get('r_cutoff') is not None else 0
+    if pt.has_cutoff:
+      pt.r_onset = float(self.pot['r_onset'])
+      pt.r_cutoff = float(self.pot['r_cutoff'])
+    pt.n_species = 0
+    modes = []
+    for k, name in enumerate(_PARAM_ORDER):
+      v = params.get(name, _DEFAULTS[kind][name])
+      ndim = v.ndim if isinstance(v, (torch.Tensor, np.ndarray)) else 0
+      if ndim == 0:
+        pt.mode[k] = _lib.PARAM_SCALAR
+        pt.scalar[k] = float(v)
+      elif species is None or ndim == 1:
+        if ndim == 1:
+          pt.mode[k] = _lib.PARAM_PER_ATOM
+        elif ndim == 2:
+          pt.mode[k] = _lib.PARAM_MATRIX
+          pt.n_species = int(v.shape[0])
+        else:
+          raise ValueError('Parameter array must be either a scalar, a vector, '
+                           f'or a matrix. Found ndim={ndim}.')
+        t = self._tensor(v, R.dtype, R.device)
+        keep.append(t)
+        pt.array[k] = t.data_ptr()
+      else:
+        if ndim != 2:
+          raise ValueError('Params must be a scalar or a 2d array if using a '
+                           'species lookup.')
+        pt.mode[k] = _lib.PARAM_SPECIES
+        pt.n_species = int(v.shape[0])
+        t = self._tensor(v, R.dtype, R.device)
+        keep.append(t)
+        pt.array[k] = t.data_ptr()
+      modes.append(pt.mode[k])
+    return pt, keep, modes
+
+  def _resolve(self, neighbor, dynamic_kwargs):
+    if neighbor is None:
+      neighbor = dynamic_kwargs.pop('neighbor', None)
+    if neighbor is None:
+      raise TypeError('energy_fn(R, neighbor=...) needs a NeighborList')
+    if neighbor._ws is None or not neighbor.internal_list_is_current:
+      raise NotImplementedError(
+          'The fused kernels read the internal rows of a NeighborList built by '
+          'jax_md_b200.partition; this list has a foreign `idx`.')
+    species = dynamic_kwargs.pop('species', self.species)
+    params = _merge(self.kwargs, dynamic_kwargs, self.ignore_unused)
+    return neighbor, species, params
+
+  def _species_tensor(self, species, device):
+    if species is None:
+      return None
+    if isinstance(species, torch.Tensor) and species.dtype == torch.int32 \
+        and species.is_cuda and species.is_contiguous():
+      return species
+    return self._tensor(species, torch.int32, device)
+
+  # -- kernels ------------------------------------------------------------------
+  def launch(self, R, neighbor, species, params, want_energy, per_atom=False,
+             momentum=None, mass=None, dt_2=0.0, dt_dev=None, red=None,
+             refresh_positions=True):
+    """Runs the fused kernel.  Returns dict(force, red, e_atom, dparam, modes)."""
+    ws = neighbor._ws
+    dev, N, dim = R.device, ws.n, ws.dim
+    ws.set_species(self._species_tensor(species, dev))
+    if refresh_positions:
+      _lib.call('jmd_nbr_pack', ws.ref(), _lib.ptr(R.contiguous()), _lib.stream())
+    pt, keep, modes = self._pair_struct(
+        R, species, params, partition.is_sparse(neighbor.format))
+    force = torch.empty((N, dim), dtype=R.dtype, device=dev)
+    if red is None:
+      red = torch.zeros(_lib.RED_COUNT, dtype=torch.float64, device=dev)
+    partials = Scratch.get(N, dev)
+    e_atom = torch.empty((N,), dtype=R.dtype, device=dev) if per_atom else None
+    dparam = None
+    if want_energy and any(m in (_lib.PARAM_SPECIES, _lib.PARAM_PER_ATOM)
+                           for m in modes[:2]):
+      size = 2 * N if _lib.PARAM_PER_ATOM in modes[:2] else 2 * pt.n_species ** 2
+      size = max(size, 2 * pt.n_species ** 2)
+      dparam = torch.zeros(size, dtype=torch.float64, device=dev)
+    mass_is_array = 0
+    if momentum is not None:
+      mass_is_array = 1 if mass.numel() > 1 else 0
+    _lib.call('jmd_pair_force', ws.ref(), C.byref(pt), _lib.ptr(force),
+              _lib.ptr(e_atom), _lib.ptr(red), _lib.ptr(dparam),
+              _lib.ptr(partials), _lib.ptr(momentum), _lib.ptr(mass),
+              mass_is_array, float(dt_2), _lib.ptr(dt_dev),
+              1 if want_energy else 0, _lib.stream())
+    return dict(force=force, red=red, e_atom=e_atom, dparam=dparam, modes=modes,
+                n_species=pt.n_species, keep=keep)
+
+  def force(self, R, neighbor=None, **dynamic_kwargs):
+    """-dE/dR straight from the kernel (quantity.force fast path)."""
+    neighbor, species, params = self._resolve(neighbor, dict(dynamic_kwargs))
+    return self.launch(R, neighbor, species, params, want_energy=False)['force']
+
+  def __call__(self, R, neighbor=None, **dynamic_kwargs):
+    neighbor, species, params = self._resolve(neighbor, dict(dynamic_kwargs))
+    per_atom = self.reduce_axis is not None
+    if per_atom and neighbor.format is partition.OrderedSparse:
+      raise ValueError('Cannot report per-particle values with a neighbor list '
+                       'whose format is `OrderedSparse`. Please use either '
+                       '`Dense` or `Sparse`.')
+    grad_params = [(n, params[n]) for n in ('sigma', 'epsilon')
+                   if isinstance(params.get(n), torch.Tensor)
+                   and params[n].requires_grad]
+    needs_grad = torch.is_grad_enabled() and (R.requires_grad or grad_params)
+    if not needs_grad:
+      out = self.launch(R, neighbor, species, params, True, per_atom)
+      if per_atom:
+        return out['e_atom']
+      return out['red'][_lib.RED_ENERGY].to(R.dtype)
+    if per_atom:
+      raise NotImplementedError('gradients of per-particle energies')
+    fn = self
+
+    class _Energy(torch.autograd.Function):
+      @staticmethod
+      def forward(ctx, Rin, *ptensors):
+        out = fn.launch(Rin.detach(), neighbor, species, params, True, False)
+        ctx.out = out
+        ctx.shapes = [p.shape for p in ptensors]
+        return out['red'][_lib.RED_ENERGY].to(Rin.dtype)
+
+      @staticmethod
+      def backward(ctx, g):
+        out = ctx.out
+        grads = [-(g * out['force'])]
+        for (name, p), k in zip(grad_params, range(len(grad_params))):
+          slot = 0 if name == 'sigma' else 1
+          mode = out['modes'][slot]
+          if mode == _lib.PARAM_SCALAR:
+            r = out['red'][_lib.RED_DSIGMA + slot]
+            grads.append((g * r).to(p.dtype).reshape(p.shape))
+          elif mode == _lib.PARAM_SPECIES:
+            S = out['n_species']
+            tbl = out['dparam'][slot * S * S:(slot + 1) * S * S].reshape(S, S)
+            grads.append((g * tbl).to(p.dtype))
+          elif mode == _lib.PARAM_PER_ATOM:
+            N = Rin_n[0]
+            grads.append((g * out['dparam'][slot * N:(slot + 1) * N]).to(p.dtype))
+          else:
+            raise NotImplementedError('gradient of [N, N] matrix parameters')
+        return tuple(grads)
+
+    Rin_n = [R.shape[0]]
+    return _Energy.apply(R, *[p for _, p in grad_params])
+
+
+def pair_neighbor_list(fn, displacement_or_metric, species=None,
+                       reduce_axis=None, ignore_unused_parameters=False,
+                       **kwargs):
+  """smap.py:856-979.  `fn` must be one of this package's pair potentials
+  (`energy.lennard_jones`, `energy.soft_sphere`, `energy.morse`), optionally
+  wrapped by `energy.multiplicative_isotropic_cutoff`."""
+  pot = getattr(fn, '_jmd_potential', None)
+  if pot is None:
+    raise NotImplementedError(
+        'pair_neighbor_list over an arbitrary Python `fn` is row 1 of '
+        'SURVEY.md 8(f) ("next"); the fused path covers lennard_jones, '
+        'soft_sphere and morse.')
+  for k in kwargs:
+    if callable(kwargs[k]) and not isinstance(kwargs[k], torch.Tensor):
+      raise NotImplementedError('custom parameter combinators')
+  return PairNeighborListFn(pot, displacement_or_metric, species, reduce_axis,
+                            ignore_unused_parameters, kwargs)

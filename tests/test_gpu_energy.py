@@ -1,0 +1,359 @@
+"""GPU parity: fused force/energy kernels and integrators vs the CPU oracle.
+
+Tolerances are the north star's: rtol 1e-5 in f32, 1e-10 in f64 (the reference
+tests use 2e-5 / 1e-10, tests/energy_test.py:63).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import energy as oenergy
+from oracle import partition as opart
+from oracle import simulate as osim
+from oracle import space as ospace
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+FORMATS = ['Dense', 'Sparse', 'OrderedSparse']
+with open(os.path.join(util.GOLDEN, 'goldens.json')) as f:
+  G = json.load(f)
+
+
+def _jmd():
+  import jax_md_b200 as jmd
+  return jmd
+
+
+def _dev(x):
+  return torch.as_tensor(x, device='cuda')
+
+
+def _tol(dtype):
+  return dict(rtol=1e-5, atol=1e-5) if dtype == np.float32 else dict(rtol=1e-10, atol=1e-10)
+
+
+def _ftol(dtype, F):
+  scale = float(np.abs(F).max())
+  if dtype == np.float32:
+    return dict(rtol=1e-5, atol=1e-5 * scale)
+  return dict(rtol=1e-10, atol=1e-10 * scale)
+
+
+def _pair_setup(kind, dtype, fmt, n=6, species=False):
+  jmd = _jmd()
+  R, L = util.fcc(n, rho=0.8442, dtype=dtype)
+  R = util.jitter(R, L, 0.06)
+  N = len(R)
+  d_o, s_o = ospace.periodic(L)
+  d_g, s_g = jmd.space.periodic(L)
+  F = jmd.partition.NeighborListFormat[fmt]
+  sp = None
+  kw_o, kw_g = {}, {}
+  if species:
+    sp = (np.arange(N) % 2).astype(np.int32)
+  if kind == 'lj':
+    sigma = np.array([[1.0, 1.05], [1.05, 1.1]], np.float32) if species else np.float32(1.0)
+    eps = np.array([[1.0, 0.8], [0.8, 0.6]], np.float32) if species else np.float32(1.0)
+    nf_g, e_g = jmd.energy.lennard_jones_neighbor_list(
+        d_g, L, species=None if sp is None else _dev(sp), sigma=sigma,
+        epsilon=eps, dr_threshold=0.3, format=F)
+    smax = np.float32(np.max(sigma))
+    pot = oenergy.PairPotential('lj', np.float32(2.0) * smax, np.float32(2.5) * smax)
+    nf_o = opart.neighbor_list(d_o, L, np.float32(2.5) * smax, np.float32(0.3),
+                               format=opart.Format[fmt])
+    params = dict(sigma=sigma, epsilon=eps)
+  elif kind == 'morse':
+    nf_g, e_g = jmd.energy.morse_neighbor_list(d_g, L, sigma=1.1, epsilon=2.0,
+                                               alpha=4.0, dr_threshold=0.3, format=F)
+    pot = oenergy.PairPotential('morse', np.float32(2.0), np.float32(2.5))
+    nf_o = opart.neighbor_list(d_o, L, np.float32(2.5), np.float32(0.3),
+                               format=opart.Format[fmt])
+    params = dict(sigma=np.float32(1.1), epsilon=np.float32(2.0), alpha=np.float32(4.0))
+  else:
+    sigma = np.array([[1.0, 1.2], [1.2, 1.4]], np.float32) if species else np.float32(1.3)
+    nf_g, e_g = jmd.energy.soft_sphere_neighbor_list(
+        d_g, L, species=None if sp is None else _dev(sp), sigma=sigma,
+        dr_threshold=0.2, format=F)
+    pot = oenergy.PairPotential('soft_sphere')
+    nf_o = opart.neighbor_list(d_o, L, np.float32(np.max(sigma)), np.float32(0.2),
+                               format=opart.Format[fmt])
+    params = dict(sigma=sigma, epsilon=np.float32(1.0), alpha=np.float32(2.0))
+  return dict(R=R, L=L, d_o=d_o, s_o=s_o, s_g=s_g, nf_o=nf_o, nf_g=nf_g, e_g=e_g,
+              pot=pot, params=params, species=sp)
+
+
+@pytest.mark.parametrize('kind', ['lj', 'soft_sphere', 'morse'])
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_pair_energy_force_param_grads(kind, fmt, dtype):
+  jmd = _jmd()
+  s = _pair_setup(kind, dtype, fmt)
+  R = s['R']
+  nb_o = s['nf_o'].allocate(R)
+  Rd = _dev(R)
+  nb_g = s['nf_g'].allocate(Rd)
+  np.testing.assert_array_equal(nb_g.idx.cpu().numpy(), nb_o.idx)
+  E_o, F_o, dp_o = oenergy.pair_neighbor_list_energy(
+      s['pot'], s['d_o'], R.astype(np.float64), nb_o, want_grads=True,
+      **{k: np.float64(v) for k, v in s['params'].items()})
+  E_g = s['e_g'](Rd, neighbor=nb_g)
+  assert E_g.dtype == Rd.dtype and E_g.ndim == 0
+  np.testing.assert_allclose(float(E_g), E_o, **_tol(dtype))
+  F_g = jmd.quantity.force(s['e_g'])(Rd, neighbor=nb_g)
+  np.testing.assert_allclose(F_g.cpu().numpy(), F_o, **_ftol(dtype, F_o))
+  # autograd route == jax.grad(energy_fn): positions and (sigma, epsilon)
+  Rg = Rd.clone().requires_grad_(True)
+  sig = torch.tensor(float(s['params']['sigma']), dtype=Rd.dtype, device='cuda',
+                     requires_grad=True)
+  eps = torch.tensor(float(s['params']['epsilon']), dtype=Rd.dtype, device='cuda',
+                     requires_grad=True)
+  E = s['e_g'](Rg, neighbor=nb_g, sigma=sig, epsilon=eps)
+  E.backward()
+  np.testing.assert_allclose((-Rg.grad).cpu().numpy(), F_o, **_ftol(dtype, F_o))
+  t = dict(rtol=2e-5, atol=1e-4) if dtype == np.float32 else dict(rtol=1e-9, atol=1e-9)
+  np.testing.assert_allclose(float(sig.grad), dp_o['sigma'], **t)
+  np.testing.assert_allclose(float(eps.grad), dp_o['epsilon'], **t)
+
+
+@pytest.mark.parametrize('kind', ['lj', 'soft_sphere'])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_species_tables_and_per_particle(kind, dtype):
+  jmd = _jmd()
+  s = _pair_setup(kind, dtype, 'Sparse', species=True)
+  R = s['R']
+  nb_o = s['nf_o'].allocate(R)
+  Rd = _dev(R)
+  nb_g = s['nf_g'].allocate(Rd)
+  p64 = {k: np.asarray(v, np.float64) for k, v in s['params'].items()}
+  E_o, F_o, dp_o = oenergy.pair_neighbor_list_energy(
+      s['pot'], s['d_o'], R.astype(np.float64), nb_o, species=s['species'],
+      want_grads=True, **p64)
+  E_g = s['e_g'](Rd, nb_g)          # positional neighbor, as tests/energy_test.py:596
+  np.testing.assert_allclose(float(E_g), E_o, **_tol(dtype))
+  F_g = jmd.quantity.force(s['e_g'])(Rd, neighbor=nb_g)
+  np.testing.assert_allclose(F_g.cpu().numpy(), F_o, **_ftol(dtype, F_o))
+  # table gradients
+  sig = _dev(np.asarray(s['params']['sigma'], dtype)).requires_grad_(True)
+  E = s['e_g'](Rd, neighbor=nb_g, sigma=sig)
+  E.backward()
+  t = dict(rtol=5e-5, atol=1e-3) if dtype == np.float32 else dict(rtol=1e-9, atol=1e-9)
+  np.testing.assert_allclose(sig.grad.cpu().numpy(), dp_o['sigma'], **t)
+  # per-particle energies (reduce_axis=(1,), smap.py:958-977)
+  if kind == 'lj':
+    d_g, _ = jmd.space.periodic(s['L'])
+    _, e_pp = jmd.energy.lennard_jones_neighbor_list(
+        d_g, s['L'], species=_dev(s['species']), sigma=s['params']['sigma'],
+        epsilon=s['params']['epsilon'], dr_threshold=0.3, per_particle=True,
+        format=jmd.partition.Sparse)
+    Ea_o = oenergy.pair_neighbor_list_energy(
+        s['pot'], s['d_o'], R.astype(np.float64), nb_o, species=s['species'],
+        per_particle=True, **p64)
+    Ea_g = e_pp(Rd, neighbor=nb_g)
+    np.testing.assert_allclose(Ea_g.cpu().numpy(), Ea_o,
+                               rtol=1e-5 if dtype == np.float32 else 1e-10,
+                               atol=1e-5 if dtype == np.float32 else 1e-10)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+def test_jammed_soft_sphere_golden(fmt):
+  """tests/data/simulation_test_state.npy: E = 0.45247561922261154 (2-D, f64)."""
+  jmd = _jmd()
+  s = np.load(os.path.join(util.GOLDEN, 'jammed_state.npz'))
+  R = _dev(s['real_position'])
+  L = float(s['box'][0, 0])
+  d, _ = jmd.space.periodic(L)
+  nf, efn = jmd.energy.soft_sphere_neighbor_list(
+      d, L, species=_dev(s['species']), sigma=s['sigma'],
+      format=jmd.partition.NeighborListFormat[fmt])
+  nbrs = nf.allocate(R)
+  np.testing.assert_allclose(float(efn(R, neighbor=nbrs)), G['jammed_energy'],
+                             rtol=1e-10)
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('n', [3, 4])
+def test_stillinger_weber_golden_and_forces(dtype, n):
+  """tests/energy_test.py:429-466: -4.336503155764325 eV/atom on diamond Si;
+  forces on a perturbed lattice vs the oracle."""
+  jmd = _jmd()
+  R, L = util.diamond(n, a=G['sw_lattice_constant'], dtype=dtype)
+  d_g, _ = jmd.space.periodic(L)
+  nf, efn = jmd.energy.stillinger_weber_neighbor_list(d_g, L)
+  Rd = _dev(R)
+  nbrs = nf.allocate(Rd)
+  E = float(efn(Rd, neighbor=nbrs)) / len(R)
+  np.testing.assert_allclose(E, G['sw_diamond_energy_per_atom'],
+                             rtol=2e-5 if dtype == np.float32 else 1e-10)
+  Rp = util.jitter(R, L, 0.08, seed=2)
+  d_o, _ = ospace.periodic(L)
+  nf_o = opart.neighbor_list(d_o, L, 3.77118, 0.5, format=opart.Dense)
+  nb_o = nf_o.allocate(Rp)
+  E_o, F_o = oenergy.stillinger_weber_energy(d_o, Rp.astype(np.float64), nb_o,
+                                             want_force=True)
+  Rpd = _dev(Rp)
+  nbrs = nf.allocate(Rpd)
+  np.testing.assert_array_equal(nbrs.idx.cpu().numpy(), nb_o.idx)
+  E_g = float(efn(Rpd, neighbor=nbrs))
+  np.testing.assert_allclose(E_g, E_o, rtol=2e-5 if dtype == np.float32 else 1e-10)
+  F_g = jmd.quantity.force(efn)(Rpd, neighbor=nbrs)
+  np.testing.assert_allclose(F_g.cpu().numpy(), F_o, **_ftol(dtype, F_o))
+
+
+# -- integrators -----------------------------------------------------------------
+
+def _oracle_force(s, nbrs_holder):
+  def f(Rx):
+    nb = nbrs_holder['nb'].update(Rx)
+    nbrs_holder['nb'] = nb
+    return oenergy.pair_neighbor_list_energy(
+        s['pot'], s['d_o'], Rx, nb, want_grads=True, **s['params'])[1]
+  return f
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('fmt', ['Dense', 'OrderedSparse'])
+def test_nve_trajectory_matches_oracle(dtype, fmt):
+  """tests/simulate_test.py:203-247 analogue: NL trajectory vs the oracle's."""
+  jmd = _jmd()
+  s = _pair_setup('lj', dtype, fmt, n=5)
+  R = s['R']
+  P = util.momenta(len(R), 3, kT=1.0, dtype=dtype)
+  holder = {'nb': s['nf_o'].allocate(R)}
+  init_o, step_o = osim.nve(_oracle_force(s, holder), s['s_o'], 1e-3)
+  st_o = init_o(R, P, mass=dtype(1.0))
+  init_g, step_g = jmd.simulate.nve(s['e_g'], s['s_g'], 1e-3)
+  Rd = _dev(R)
+  nbrs = s['nf_g'].allocate(Rd)
+  st_g = init_g(0, Rd, kT=1.0, momenta=_dev(P), neighbor=nbrs)
+  np.testing.assert_allclose(st_g.force.cpu().numpy(), st_o.force,
+                             **_ftol(dtype, st_o.force))
+  steps = 200
+  for _ in range(steps):
+    st_o = step_o(st_o)
+    nbrs = nbrs.update(st_g.position)
+    st_g = step_g(st_g, neighbor=nbrs)
+  assert not bool(nbrs.did_buffer_overflow)
+  tol = 5e-3 if dtype == np.float32 else 5e-9      # simulate_test.py:243-246 uses 5e-3 / 5e-12 over 2000
+  dR = st_g.position.cpu().numpy() - st_o.position
+  dR -= np.round(dR / s['L']) * s['L']
+  assert np.abs(dR).max() < tol
+  np.testing.assert_allclose(st_g.momentum.cpu().numpy(), st_o.momentum, atol=tol * 10, rtol=0)
+  assert st_g.position.dtype == Rd.dtype
+
+
+def test_nve_energy_conservation_and_rebuilds():
+  """NVE drift over 2000 steps at T*=1 with rebuilds through the tail-launch
+  path (f32): |dE|/N below 2e-4 (stated bound), no overflow."""
+  jmd = _jmd()
+  R, L = util.fcc(10, dtype=np.float32)
+  d, s = jmd.space.periodic(L)
+  nf, efn = jmd.energy.lennard_jones_neighbor_list(d, L, dr_threshold=0.3)
+  Rd = _dev(R)
+  nbrs = nf.allocate(Rd)
+  init, step = jmd.simulate.nve(efn, s, 5e-3)
+  st = init(0, Rd, kT=1.0, momenta=_dev(util.momenta(len(R), 3, 1.0)), neighbor=nbrs)
+  KE = lambda st: float(jmd.quantity.kinetic_energy(momentum=st.momentum, mass=st.mass))
+  E0 = float(efn(st.position, neighbor=nbrs)) + KE(st)
+  b0 = nbrs._ws.state_host()[4]
+  for _ in range(2000):
+    nbrs = nbrs.update(st.position)
+    st = step(st, neighbor=nbrs)
+  E1 = float(efn(st.position, neighbor=nbrs)) + KE(st)
+  assert not bool(nbrs.did_buffer_overflow)
+  assert nbrs._ws.state_host()[4] - b0 > 20          # it did rebuild
+  assert abs(E1 - E0) / len(R) < 2e-4
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('sy', [1, 3, 5, 7])
+def test_nvt_nose_hoover_matches_oracle(dtype, sy):
+  """tests/simulate_test.py:264-350: chain variables and momenta vs the oracle,
+  and the NHC invariant is conserved."""
+  jmd = _jmd()
+  s = _pair_setup('lj', dtype, 'Dense', n=5)
+  R = s['R']
+  kT = 0.9
+  P = util.momenta(len(R), 3, kT=kT, dtype=dtype)
+  holder = {'nb': s['nf_o'].allocate(R)}
+  init_o, step_o = osim.nvt_nose_hoover(_oracle_force(s, holder), s['s_o'], 1e-3,
+                                        kT, chain_length=3, sy_steps=sy)
+  st_o = init_o(R, P, mass=dtype(1.0))
+  init_g, step_g = jmd.simulate.nvt_nose_hoover(s['e_g'], s['s_g'], 1e-3, kT,
+                                                chain_length=3, sy_steps=sy)
+  Rd = _dev(R)
+  nbrs = s['nf_g'].allocate(Rd)
+  st_g = init_g(0, Rd, momenta=_dev(P), neighbor=nbrs)
+  H0 = float(jmd.simulate.nvt_nose_hoover_invariant(s['e_g'], st_g, kT, neighbor=nbrs))
+  for _ in range(100):
+    st_o = step_o(st_o)
+    nbrs = nbrs.update(st_g.position)
+    st_g = step_g(st_g, neighbor=nbrs)
+  H1 = float(jmd.simulate.nvt_nose_hoover_invariant(s['e_g'], st_g, kT, neighbor=nbrs))
+  rt = 2e-3 if dtype == np.float32 else 1e-7
+  np.testing.assert_allclose(st_g.chain.momentum.cpu().numpy(), st_o.chain.momentum,
+                             rtol=rt, atol=rt)
+  np.testing.assert_allclose(st_g.chain.position.cpu().numpy(), st_o.chain.position,
+                             rtol=rt, atol=rt)
+  np.testing.assert_allclose(float(st_g.chain.kinetic_energy),
+                             float(st_o.chain.kinetic_energy), rtol=rt)
+  np.testing.assert_allclose(st_g.momentum.cpu().numpy(), st_o.momentum, atol=rt, rtol=0)
+  assert abs(H1 - H0) < (5e-4 if dtype == np.float32 else 1e-6) * abs(H0)
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_fire_descent_matches_oracle(dtype):
+  """tests/minimize_test.py:111 + step-by-step schedule parity with the oracle."""
+  jmd = _jmd()
+  s = _pair_setup('soft_sphere', dtype, 'OrderedSparse', n=5, species=True)
+  R = s['R']
+
+  def f_o(Rx):
+    nb = holder['nb'].update(Rx)
+    holder['nb'] = nb
+    return oenergy.pair_neighbor_list_energy(
+        s['pot'], s['d_o'], Rx, nb, species=s['species'], want_grads=True,
+        **s['params'])[1]
+  holder = {'nb': s['nf_o'].allocate(R)}
+  init_o, step_o = osim.fire_descent(f_o, s['s_o'])
+  st_o = init_o(R, mass=dtype(1.0))
+  init_g, step_g = jmd.minimize.fire_descent(s['e_g'], s['s_g'])
+  Rd = _dev(R)
+  nbrs = s['nf_g'].allocate(Rd)
+  st_g = init_g(Rd, neighbor=nbrs)
+  f0 = float(st_g.force.abs().max())
+  for i in range(120):
+    st_o = step_o(st_o)
+    nbrs = nbrs.update(st_g.position)
+    st_g = step_g(st_g, neighbor=nbrs)
+    if i == 30:
+      assert int(st_g.n_pos) == st_o.n_pos
+      np.testing.assert_allclose(float(st_g.dt), st_o.dt, rtol=1e-5)
+      np.testing.assert_allclose(float(st_g.alpha), st_o.alpha, rtol=1e-5)
+  assert float(st_g.force.abs().max()) < 0.05 * f0
+  if dtype == np.float64:
+    np.testing.assert_allclose(float(st_g.dt), st_o.dt, rtol=1e-9)
+    dR = st_g.position.cpu().numpy() - st_o.position
+    dR -= np.round(dR / s['L']) * s['L']
+    assert np.abs(dR).max() < 1e-7
+
+
+def test_generic_force_fn_path():
+  """simulate.nve over a user force function (not fused): the integrator
+  kernels bracket a Python callable (quantity.canonicalize_force)."""
+  jmd = _jmd()
+  _, s = jmd.space.periodic(10.0)
+  k = 2.0
+  R = _dev(np.random.default_rng(0).random((256, 3)).astype(np.float64) * 2 + 4)
+  efn = lambda Rx, **kw: 0.5 * k * ((Rx - 5.0) ** 2).sum()
+  init, step = jmd.simulate.nve(efn, s, 1e-2)
+  st = init(1, R, kT=0.0, momenta=torch.zeros_like(R))
+  E0 = float(efn(st.position))
+  for _ in range(100):
+    st = step(st)
+  E1 = float(efn(st.position)) + float(jmd.quantity.kinetic_energy(
+      momentum=st.momentum, mass=st.mass))
+  assert abs(E1 - E0) < 1e-3 * E0

@@ -1,0 +1,248 @@
+"""GPU parity: neighbour lists built by libjmd_b200.so vs the CPU oracle.
+
+Bar: bit-exact -- the public `idx` arrays are compared element by element
+(same neighbours in the same order as the reference's candidate order), plus
+occupancies, capacities and error flags.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import partition as opart
+from oracle import space as ospace
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+FORMATS = ['Dense', 'Sparse', 'OrderedSparse']
+
+
+def _mods():
+  import jax_md_b200 as jmd
+  return jmd
+
+
+def _dev(x):
+  return torch.as_tensor(x, device='cuda')
+
+
+def _build_both(R, box, r_cut, skin, fmt, periodic=True, **kw):
+  jmd = _mods()
+  if periodic:
+    d_o, _ = ospace.periodic(box)
+    d_g, _ = jmd.space.periodic(box)
+  else:
+    d_o, _ = ospace.free()
+    d_g, _ = jmd.space.free()
+  nf_o = opart.neighbor_list(d_o, box, r_cut, skin, format=opart.Format[fmt], **kw)
+  nf_g = jmd.partition.neighbor_list(
+      d_g, box, r_cut, skin, format=jmd.partition.NeighborListFormat[fmt], **kw)
+  return nf_o, nf_g
+
+
+def _assert_same(nb_o, nb_g, exact_order=True):
+  assert nb_g.max_occupancy == nb_o.max_occupancy
+  assert nb_g.cell_list_capacity == nb_o.cell_list_capacity
+  assert int(nb_g.error.code) == int(nb_o.error)
+  idx_g = nb_g.idx.cpu().numpy()
+  assert idx_g.shape == nb_o.idx.shape
+  assert idx_g.dtype == np.int32
+  if exact_order:
+    np.testing.assert_array_equal(idx_g, nb_o.idx)
+  else:
+    N = len(nb_o.reference_position)
+    if nb_o.format is opart.Dense:
+      np.testing.assert_array_equal(np.sort(idx_g, -1), np.sort(nb_o.idx, -1))
+    else:
+      np.testing.assert_array_equal(util.sparse_pairs(idx_g, N),
+                                    util.sparse_pairs(nb_o.idx, N))
+  np.testing.assert_array_equal(nb_g.reference_position.cpu().numpy(),
+                                nb_o.reference_position)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('dim', [2, 3])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_random_rectangular_box(fmt, dim, dtype):
+  """reference tests/partition_test.py:203-301 configuration."""
+  rng = np.random.default_rng(0)
+  box = np.array([9.0, 4.0, 7.25][:dim], np.float32)
+  N = 1000
+  R = (rng.random((N, dim)) * box).astype(dtype)
+  nf_o, nf_g = _build_both(R, box, 1.23, 0.0, fmt, capacity_multiplier=1.1)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  assert nb_o.use_cell_list
+  _assert_same(nb_o, nb_g)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_fcc_lj_config(fmt, dtype):
+  """BASELINE config: LJ fcc, rho=0.8442, rc=2.5, skin 0.3 (N=4*12^3=6912)."""
+  R, L = util.fcc(12, dtype=dtype)
+  R = util.jitter(R, L, 0.05)
+  nf_o, nf_g = _build_both(R, L, np.float32(2.5), np.float32(0.3), fmt)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  _assert_same(nb_o, nb_g)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('mask_self', [True, False])
+def test_all_pairs_path(fmt, mask_self):
+  """cutoff >= box/3 -> no cell list (partition.py:1052), candidates = all."""
+  rng = np.random.default_rng(3)
+  box = np.float32(5.0)
+  R = (rng.random((64, 3)) * box).astype(np.float32)
+  nf_o, nf_g = _build_both(R, box, 1.8, 0.2, fmt, mask_self=mask_self)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  assert not nb_o.use_cell_list
+  _assert_same(nb_o, nb_g)
+
+
+@pytest.mark.parametrize('case', [(0.12, True, 1.5), (0.25, False, 1.5),
+                                  (0.31, False, 1.5), (0.31, False, 1.0)])
+@pytest.mark.parametrize('mask_self', [False, True])
+@pytest.mark.parametrize('fmt', FORMATS)
+def test_issue191_capacity_goldens(case, mask_self, fmt):
+  """reference tests/partition_test.py:488-546 (shape goldens)."""
+  r_cut, disable, cm = case
+  box = np.ones(3)
+  R = np.ones((20, 3)) * 0.5
+  want = {'Dense': (20, 19) if mask_self else (20, 20),
+          'Sparse': (2, 380) if mask_self else (2, 400),
+          'OrderedSparse': (2, 190)}[fmt]
+  nf_o, nf_g = _build_both(R, box, r_cut, 0.1 * r_cut, fmt,
+                           capacity_multiplier=cm, disable_cell_list=disable,
+                           mask_self=mask_self)
+  nb_g = nf_g.allocate(_dev(R))
+  assert not bool(nb_g.did_buffer_overflow)
+  assert tuple(nb_g.idx.shape) == want
+  nb_o = nf_o.allocate(R)
+  _assert_same(nb_o, nb_g)
+  nb_g2 = nb_g.update(_dev(R + 0.1))
+  assert not bool(nb_g2.did_buffer_overflow)
+  assert tuple(nb_g2.idx.shape) == want
+  nb_o2 = nb_o.update(R + 0.1)
+  _assert_same(nb_o2, nb_g2)
+
+
+def test_cell_list_overflow_flag():
+  """reference tests/partition_test.py:363-401 (free space + cell list)."""
+  R = np.array([[20., 20.], [30., 30.], [40., 40.], [50., 50.]], np.float32)
+  nf_o, nf_g = _build_both(R, 100.0, 3.0, 0.0, 'Dense', periodic=False)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  _assert_same(nb_o, nb_g)
+  R2 = np.array([[20., 20.], [20., 20.], [40., 40.], [50., 50.]], np.float32)
+  nb_g = nb_g.update(_dev(R2))
+  nb_o = nb_o.update(R2)
+  assert bool(nb_g.did_buffer_overflow)
+  assert int(nb_g.error.code) == int(nb_o.error)
+  assert nb_g.idx.dtype == torch.int32
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('mode', ['tail', 'gated'])
+def test_update_semantics(fmt, mode):
+  """partition.py:1119-1154: no rebuild below the skin threshold, rebuild above
+  it (strict >), sticky error bits; device tail-launch and gated modes agree."""
+  R, L = util.fcc(8, dtype=np.float32)
+  R = util.jitter(R, L, 0.03)
+  nf_o, nf_g = _build_both(R, L, np.float32(2.5), np.float32(0.3), fmt)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  nb_g._ws.update_mode = mode
+  builds0 = nb_g._ws.state_host()[4]
+  rng = np.random.default_rng(5)
+  # (a) tiny move: below threshold -> identical list, no rebuild
+  Ra = np.mod(R + rng.normal(0, 0.01, R.shape).astype(np.float32), L).astype(np.float32)
+  nb_o = nb_o.update(Ra)
+  nb_g = nb_g.update(_dev(Ra))
+  assert not nb_o.did_rebuild
+  assert nb_g._ws.state_host()[4] == builds0
+  _assert_same(nb_o, nb_g)
+  # (b) one atom jumps past skin/2 -> rebuild
+  Rb = Ra.copy()
+  Rb[17, 0] = np.mod(Rb[17, 0] + 0.2, L)
+  nb_o = nb_o.update(Rb)
+  nb_g = nb_g.update(_dev(Rb))
+  assert nb_o.did_rebuild
+  assert nb_g._ws.state_host()[4] == builds0 + 1
+  _assert_same(nb_o, nb_g)
+  # (c) crush a region: cell (and row) capacity overflow.  With a cell overflow
+  # the reference loses atoms in an unspecified way, so only the cell bit and
+  # the truthiness of did_buffer_overflow are defined; they must match + stick.
+  Rc = Rb.copy()
+  Rc[:200] = np.mod(Rb[100] + rng.normal(0, 0.4, (200, 3)).astype(np.float32), L)
+  nb_o = nb_o.update(Rc)
+  nb_g = nb_g.update(_dev(Rc))
+  assert int(nb_g.error.code) & 2 == int(nb_o.error) & 2 == 2
+  assert bool(nb_g.did_buffer_overflow) and bool(nb_o.did_buffer_overflow)
+  nb_g = nb_g.update(_dev(Rb))
+  assert int(nb_g.error.code) & 2 == 2                  # sticky
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+def test_neighbor_overflow_flag_all_pairs(fmt):
+  """NEIGHBOR_LIST_OVERFLOW alone (no cell list involved): identical flag,
+  identical truncated idx."""
+  rng = np.random.default_rng(11)
+  box = np.float32(6.0)
+  R = (rng.random((96, 3)) * box).astype(np.float32)
+  nf_o, nf_g = _build_both(R, box, 1.9, 0.2, fmt, capacity_multiplier=1.0)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  _assert_same(nb_o, nb_g)
+  R2 = (R * np.float32(0.8)).astype(np.float32)        # denser -> more neighbours
+  nb_o = nb_o.update(R2)
+  nb_g = nb_g.update(_dev(R2))
+  assert int(nb_o.error) == 1
+  assert int(nb_g.error.code) == 1
+  if fmt == 'Dense':
+    np.testing.assert_array_equal(nb_g.idx.cpu().numpy(), nb_o.idx)
+
+
+def test_large_random_sets_bit_exact():
+  """SURVEY 7 hard-part 1 at scale: 100k random atoms, every row compared."""
+  rng = np.random.default_rng(1)
+  N = 100_000
+  L = np.float32((N / 0.8442) ** (1 / 3))
+  R = (rng.random((N, 3), np.float32) * L).astype(np.float32)
+  nf_o, nf_g = _build_both(R, L, np.float32(2.5), np.float32(0.3), 'Dense')
+  nb_g = nf_g.allocate(_dev(R))
+  nb_o = nf_o.allocate(R)
+  _assert_same(nb_o, nb_g)
+
+
+def test_always_rebuild_when_skin_zero():
+  R, L = util.fcc(6, dtype=np.float32)
+  nf_o, nf_g = _build_both(R, L, 2.0, 0.0, 'Dense')
+  nb_g = nf_g.allocate(_dev(R))
+  b0 = nb_g._ws.state_host()[4]
+  nb_g = nb_g.update(_dev(R))
+  assert nb_g._ws.state_host()[4] == b0 + 1
+
+
+def test_update_is_graph_capturable():
+  """update() must not sync: capture it in a CUDA graph and replay."""
+  R, L = util.fcc(8, dtype=np.float32)
+  nf_o, nf_g = _build_both(R, L, np.float32(2.5), np.float32(0.3), 'Dense')
+  Rd = _dev(R)
+  nb_g = nf_g.allocate(Rd)
+  nb_g._ws.update_mode = 'gated'
+  s = torch.cuda.Stream()
+  s.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(s):
+    nb_g.update(Rd)
+  torch.cuda.current_stream().wait_stream(s)
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    nb_g.update(Rd)
+  b0 = nb_g._ws.state_host()[4]
+  Rd.add_(0.2)          # every atom moved by > skin/2 -> replay must rebuild
+  g.replay()
+  torch.cuda.synchronize()
+  assert nb_g._ws.state_host()[4] == b0 + 1
