@@ -196,6 +196,7 @@ def run_b200(args):
   Rd = R_pin.to(dev, non_blocking=True)
   Pd = P_pin.to(dev, non_blocking=True)
   nbrs = nf.allocate(Rd)
+  nbrs._ws.update_mode = args.update_mode
   state = init_fn(0, Rd, kT=KT, momenta=Pd, neighbor=nbrs)
 
   def md_steps(state, nbrs, k):
@@ -212,6 +213,7 @@ def run_b200(args):
   barrier()
   if bool(nbrs.did_buffer_overflow):
     nbrs = nf.allocate(state.position)
+    nbrs._ws.update_mode = args.update_mode
   builds0 = nbrs._ws.state_host()[_lib.ST_BUILDS]
 
   # ---- timed region: exactly K steps, device timed ------------------------------
@@ -286,6 +288,7 @@ def run_b200(args):
   Rd = R_pin.to(dev, non_blocking=True)
   Pd = P_pin.to(dev, non_blocking=True)
   nb2 = nf.allocate(Rd)
+  nb2._ws.update_mode = args.update_mode
   st2 = init_fn(0, Rd, kT=KT, momenta=Pd, neighbor=nb2)
   d2h = 0
   for _ in range(n_blocks):
@@ -344,8 +347,10 @@ def main():
   ap.add_argument('--block', type=int, default=100)
   ap.add_argument('--kernel-reps', type=int, default=20)
   ap.add_argument('--cpu-cells', type=int, default=20)
-  ap.add_argument('--cpu-steps', type=int, default=3)
+  ap.add_argument('--cpu-steps', type=int, default=20)
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--update-mode', default='tail', choices=['tail', 'gated'],
+                  help="how update()'s lax.cond is realised: device tail launch or gated kernels")
   args = ap.parse_args()
   if args.impl == 'reference':
     return run_reference(args)

@@ -154,6 +154,8 @@ typedef struct {
   double scalar[3];        /* sigma, epsilon, alpha when SCALAR */
   const void* array[3];    /* device arrays (position dtype) otherwise */
   double r_onset, r_cutoff;
+  double r_onset2, r_cutoff2; /* r ** f32(2) in the reference's dtype, energy.py:558-559 */
+  double switch_denom;        /* (r_c2 - r_o2) ** 3 in that same dtype, energy.py:566 */
 } jmd_pair_t;
 
 /* Slots of the double reduction block written by the force kernels. */

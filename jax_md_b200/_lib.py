@@ -53,7 +53,9 @@ class PairT(C.Structure):
               ('mode', C.c_int32 * 3), ('n_species', C.c_int32),
               ('transposed', C.c_int32), ('_pad', C.c_int32),
               ('scalar', C.c_double * 3), ('array', C.c_void_p * 3),
-              ('r_onset', C.c_double), ('r_cutoff', C.c_double)]
+              ('r_onset', C.c_double), ('r_cutoff', C.c_double),
+              ('r_onset2', C.c_double), ('r_cutoff2', C.c_double),
+              ('switch_denom', C.c_double)]
 
 
 class SwT(C.Structure):

@@ -111,7 +111,7 @@ __global__ void k_nhc_half_step(int cl, int chain_steps, int sy_steps, T dt, T t
   T* KEp = chain + 3 * cl;
   const T kT = *kT_dev;
   // update_mass (simulate.py:509-515): Q = kT tau^2 ones(f32); Q[0] *= dof
-  for (int m = 0; m < cl; ++m) Q[m] = (T)((float)kT * (float)tau * (float)tau);
+  for (int m = 0; m < cl; ++m) Q[m] = (T)((float)kT * ((float)tau * (float)tau));
   Q[0] = (T)((float)Q[0] * (float)dof);
   T KE = ke_red ? (T)(*ke_red) : *KEp;
   const T DOF = (T)dof;
@@ -124,7 +124,10 @@ __global__ void k_nhc_half_step(int cl, int chain_steps, int sy_steps, T dt, T t
       delta = dt;
     } else {
       double w = sy_steps == 1 ? 1.0 : (sy_steps == 3 ? SY3[it % 3] : (sy_steps == 5 ? SY5[it % 5] : SY7[it % 7]));
-      delta = (T)(float)((double)(dt / (T)chain_steps) * w);     // simulate.py:500: f32(delta * ws[i])
+      // simulate.py:497-500: delta = dt / chain_steps (f32); d = f32(delta * ws[i]) with
+      // ws f32 unless x64 is on (then the product is formed in f64 first)
+      const float delta_f = (float)dt / (float)chain_steps;
+      delta = sizeof(T) == 4 ? (T)(delta_f * (float)w) : (T)(float)((double)delta_f * w);
     }
     const T d2 = delta / T(2), d4 = d2 / T(2), d8 = d4 / T(2);
     // simulate.py:456-466 backward sweep (uses the OLD p_xi[m-1])

@@ -24,6 +24,9 @@ enum { ST_REBUILD = JMD_ST_REBUILD, ST_MAX_CELL = JMD_ST_MAX_CELL_OCC,
        ST_BUILDS = JMD_ST_BUILDS, ST_TICKET = JMD_ST_SCAN_TICKET,
        ST_PENDING = 6 };
 
+#ifndef JMD_BUILD_WARP_PER_CELL
+#define JMD_BUILD_WARP_PER_CELL 0
+#endif
 constexpr int SCAN_TILE = 2048;   // 256 threads x 8
 constexpr int BUILD_WARPS = 4;
 constexpr int BUILD_CAP = 1024;   // candidates staged per warp per chunk
@@ -85,11 +88,14 @@ __global__ void k_zero(NbrP<T, DIM> P, int gated) {
     P.cell_count[c] = 0;
     if (c < P.n_cells) P.cell_cursor[c] = 0;
   }
-  if (i == 0) {
-    P.state[ST_MAX_CELL] = 0;
-    P.state[ST_MAX_ROW] = 0;
-    P.state[ST_TOTAL] = 0;
-  }
+  if (i == 0) P.state[ST_MAX_CELL] = 0;
+}
+
+template <typename T, int DIM>
+__global__ void k_build_reset(NbrP<T, DIM> P, int gated) {
+  GATE(P, gated);
+  P.state[ST_MAX_ROW] = 0;
+  P.state[ST_TOTAL] = 0;
 }
 
 // partition.py:421-423: int32(R / cell_size) (truncation), mod cells_per_side,
@@ -262,11 +268,7 @@ __global__ void k_identity_sort(NbrP<T, DIM> P, int gated) {
     P.inv_perm[i] = i;
     P.pos_sorted[i] = load_atom(P, i);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    P.state[ST_MAX_CELL] = 0;
-    P.state[ST_MAX_ROW] = 0;
-    P.state[ST_TOTAL] = 0;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.state[ST_MAX_CELL] = 0;
 }
 
 template <typename T, int DIM>
@@ -426,6 +428,86 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) k_build_cells(NbrP<T, DIM> P
   if (lane == 0) {
     if (wmax > 0) atomicMax((unsigned long long*)&P.state[ST_MAX_ROW], (unsigned long long)wmax);
     if (wtotal > 0) atomicAdd((unsigned long long*)&P.state[ST_TOTAL], (unsigned long long)wtotal);
+  }
+}
+
+// Thread-per-atom stencil scan (the default).  Thread t owns sorted slot t and
+// walks the 3^d stencil cells of its own cell in reference order; candidates
+// of a cell are a contiguous range of the cell-sorted float4 array, so the 32
+// lanes of a warp (2-3 adjacent cells) issue loads that hit 2-3 distinct
+// addresses (L1 broadcast).  Every row is appended in candidate order by its
+// own thread: no ballots, no atomics, order == reference order.  Row k of the
+// transposed list is written by neighbouring lanes at neighbouring addresses.
+constexpr int TPA_BLOCK = 128;
+
+template <typename T, int DIM, bool ORDERED>
+__global__ void __launch_bounds__(TPA_BLOCK) k_build_cells_tpa(NbrP<T, DIM> P, int gated) {
+  GATE(P, gated);
+  using V4 = typename Vec4<T>::type;
+  constexpr int NS = DIM == 3 ? 27 : 9;
+  const int slot = blockIdx.x * TPA_BLOCK + threadIdx.x;
+  long long my_k = 0, my_tot = 0;
+  if (slot < P.n) {
+    const V4 hv = P.pos_sorted[slot];
+    const T hp[3] = {hv.x, hv.y, hv.z};
+    const int hid = P.perm[slot];
+    // own cell from the stored hash of this atom
+    const int c = P.hash[hid];
+    const int cx_n = P.cps[0], cy_n = P.cps[1];
+    int cc[3];
+    cc[0] = c % cx_n;
+    cc[1] = (c / cx_n) % cy_n;
+    cc[2] = DIM == 3 ? c / (cx_n * cy_n) : 0;
+    const int cap = P.cell_capacity > 0 ? P.cell_capacity : 1;
+    int k = 0, kl = 0;
+    int* out = P.nl + slot;
+    for (int s = 0; s < NS; ++s) {
+      int sh[3];
+      if (DIM == 3) { sh[0] = s / 9 - 1; sh[1] = (s / 3) % 3 - 1; sh[2] = s % 3 - 1; }
+      else { sh[0] = s / 3 - 1; sh[1] = s % 3 - 1; sh[2] = 0; }
+      int h = 0, mult = 1;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        int v = cc[d] + sh[d];
+        v = v < 0 ? v + P.cps[d] : (v >= P.cps[d] ? v - P.cps[d] : v);
+        h += v * mult;
+        mult *= P.cps[d];
+      }
+      const int start = __ldg(&P.cell_start[h]);
+      const int count = __ldg(&P.cell_start[h + 1]) - start;
+      // slot = sorted_rank mod capacity (partition.py:441): rotated arrival order
+      const int room = cap - start % cap;
+      int r = count < room ? count : room;       // first rank offset in slot order
+      if (r == count) r = 0;
+      for (int q = 0; q < count; ++q) {
+        const int rank = start + r;
+        r = r + 1 == count ? 0 : r + 1;
+        const V4 cv = P.pos_sorted[rank];
+        const T cp[3] = {cv.x, cv.y, cv.z};
+        bool keep = candidate_test<T, DIM>(P, hp, cp);
+        if (P.mask_self && rank == slot) keep = false;
+        if (keep) {
+          if (!P.count_only && k < P.m_int) out[(size_t)k * P.n_pad] = rank;
+          ++k;
+          if (ORDERED) kl += (__ldg(&P.perm[rank]) < hid);
+        }
+      }
+    }
+    P.cnt[slot] = k;
+    P.cnt_lower[slot] = kl;
+    my_k = k;
+    my_tot = ORDERED ? kl : k;
+  }
+  // block max / total -> one atomic each per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    long long y = __shfl_xor_sync(0xffffffffu, my_k, o);
+    my_k = y > my_k ? y : my_k;
+    my_tot += __shfl_xor_sync(0xffffffffu, my_tot, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (my_k > 0) atomicMax((unsigned long long*)&P.state[ST_MAX_ROW], (unsigned long long)my_k);
+    if (my_tot > 0) atomicAdd((unsigned long long*)&P.state[ST_TOTAL], (unsigned long long)my_tot);
   }
 }
 
@@ -598,9 +680,19 @@ __host__ __device__ void launch_bin(const NbrP<T, DIM>& P, int gated, cudaStream
 
 template <typename T, int DIM>
 __host__ __device__ void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+  k_build_reset<T, DIM><<<1, 1, 0, JMD_STREAM>>>(P, gated);
   if (P.use_cells) {
+#if JMD_BUILD_WARP_PER_CELL
     int g = grid_for(P.n_cells, BUILD_WARPS, JMD_SM_COUNT * 16);
     k_build_cells<T, DIM><<<g, BUILD_WARPS * 32, build_smem_bytes<T, DIM>(), JMD_STREAM>>>(P, gated);
+#else
+    int g = (P.n + TPA_BLOCK - 1) / TPA_BLOCK;
+    if (g < 1) g = 1;
+    if (P.format == JMD_ORDERED_SPARSE)
+      k_build_cells_tpa<T, DIM, true><<<g, TPA_BLOCK, 0, JMD_STREAM>>>(P, gated);
+    else
+      k_build_cells_tpa<T, DIM, false><<<g, TPA_BLOCK, 0, JMD_STREAM>>>(P, gated);
+#endif
   } else {
     k_build_all_pairs<T, DIM><<<grid_for((long long)P.n * 32, 128, JMD_SM_COUNT * 16), 128, 0, JMD_STREAM>>>(P, gated);
   }
@@ -613,7 +705,7 @@ __host__ __device__ void launch_export(const NbrP<T, DIM>& P, int gated, cudaStr
   if (P.format != JMD_DENSE) {
     int tiles = (int)(((long long)P.n + SCAN_TILE - 1) / SCAN_TILE);
     k_sparse_counts<T, DIM><<<grid_for(P.n, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
-    long long* tile_sums = (long long*)P.cell_cursor;   // reuse: >= tiles*2 ints (host checks)
+    long long* tile_sums = (long long*)P.scan_tmp;   // free again here; host sizes it for n/2048 int64
     k_scan_tiles<int, long long><<<tiles, 256, 0, JMD_STREAM>>>(P.tmp_ids, P.n, tile_sums, nullptr, gate);
     k_scan_top<long long><<<1, 256, 0, JMD_STREAM>>>(tile_sums, tiles, gate);
     k_scan_apply<int, long long><<<tiles, 256, 0, JMD_STREAM>>>(P.tmp_ids, P.n, tile_sums, P.offsets, gate);

@@ -302,9 +302,9 @@ int launch_pair(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, void* e_
   }
   T ro = (T)pp->r_onset, rc = (T)pp->r_cutoff;
   Q.r_onset = ro; Q.r_cutoff = rc;
-  Q.r_onset2 = ro * ro; Q.r_cutoff2 = rc * rc;
-  T den = Q.r_cutoff2 - Q.r_onset2;
-  Q.inv_denom = pp->has_cutoff ? T(1) / (den * den * den) : T(0);
+  Q.r_onset2 = (T)pp->r_onset2; Q.r_cutoff2 = (T)pp->r_cutoff2;
+  T den3 = (T)pp->switch_denom;
+  Q.inv_denom = pp->has_cutoff ? T(1) / den3 : T(0);
   Q.force = (T*)force; Q.e_atom = (T*)e_atom; Q.red = red; Q.dparam = dparam; Q.partials = partials;
   Q.momentum = (T*)momentum; Q.mass = (const T*)mass; Q.mass_is_array = mass_is_array; Q.dt_2 = (T)dt_2;
   Q.dt_dev = (const T*)dt_dev;

@@ -63,8 +63,8 @@ morse._jmd_potential = dict(kind=_lib.POT_MORSE, r_onset=None, r_cutoff=None)
 
 def multiplicative_isotropic_cutoff(fn, r_onset, r_cutoff):
   """energy.py:534-580."""
-  r_c = float(r_cutoff) ** 2
-  r_o = float(r_onset) ** 2
+  r_c = float(r_cutoff ** f32(2))
+  r_o = float(r_onset ** f32(2))
 
   def smooth_fn(dr):
     r = dr ** 2

@@ -271,9 +271,9 @@ def nvt_nose_hoover(energy_or_force_fn, shift_fn, dt, kT, chain_length=5,
     P = P.contiguous()
     KE = quantity.kinetic_energy(momentum=P, mass=m)
     buf = torch.zeros(3 * chain_length + 1, dtype=R.dtype, device=R.device)
-    Q = float(_kT) * float(tau) ** 2                       # simulate.py:440-442
-    buf[2 * chain_length:3 * chain_length] = float(f32(Q))
-    buf[2 * chain_length] = float(f32(f32(Q) * dof))
+    Q = f32(_kT) * (tau ** f32(2))                         # simulate.py:440-442
+    buf[2 * chain_length:3 * chain_length] = float(Q)
+    buf[2 * chain_length] = float(f32(Q * f32(dof)))
     buf[3 * chain_length] = KE
     return NVTNoseHooverState(R, P, force, m,
                               _make_chain(buf, chain_length, tau, dof))

@@ -99,6 +99,13 @@ class PairNeighborListFn:
     if pt.has_cutoff:
       pt.r_onset = float(self.pot['r_onset'])
       pt.r_cutoff = float(self.pot['r_cutoff'])
+      # energy.py:558-559: r_c = r_cutoff ** f32(2), r_o = r_onset ** f32(2),
+      # evaluated in the dtype the factory left them in (f32 unless f64 arrays)
+      r_o = self.pot['r_onset'] ** np.float32(2)
+      r_c = self.pot['r_cutoff'] ** np.float32(2)
+      pt.r_onset2 = float(r_o)
+      pt.r_cutoff2 = float(r_c)
+      pt.switch_denom = float((r_c - r_o) ** 3)
     pt.n_species = 0
     modes = []
     for k, name in enumerate(_PARAM_ORDER):

@@ -107,8 +107,10 @@ def nhc_half_step(P, chain, kT, dt, chain_length, chain_steps, sy_steps):
     return nhc_substep(dt, P, chain, kT, chain_length)
   delta = dt / chain_steps
   ws = SUZUKI_YOSHIDA_WEIGHTS[sy_steps]
+  x64 = P.dtype == np.float64     # jnp.array(weights) is f64 only when x64 is on
   for i in range(chain_steps * sy_steps):
-    d = f32(delta * ws[i % sy_steps])
+    w = ws[i % sy_steps]
+    d = f32(np.float64(delta) * w) if x64 else f32(delta * f32(w))
     P, chain = nhc_substep(d, P, chain, kT, chain_length)
   return P, chain
 

@@ -34,7 +34,7 @@ def test_struct_layout_matches_header():
   from jax_md_b200 import _lib
   assert ctypes.sizeof(_lib.SpaceT) == 16 + 48
   assert ctypes.sizeof(_lib.SwT) == 64
-  assert ctypes.sizeof(_lib.PairT) == 8 + 12 + 4 + 8 + 24 + 24 + 16
+  assert ctypes.sizeof(_lib.PairT) == 8 + 12 + 4 + 8 + 24 + 24 + 40
   n = _lib.NbrT
   assert n.n_pad.offset % 8 == 0 and n.space.offset % 8 == 0
   assert n.cell_count.offset == n.space.offset + ctypes.sizeof(_lib.SpaceT)
