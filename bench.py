@@ -349,8 +349,8 @@ def main():
   ap.add_argument('--cpu-cells', type=int, default=20)
   ap.add_argument('--cpu-steps', type=int, default=20)
   ap.add_argument('--no-cpu', action='store_true')
-  ap.add_argument('--update-mode', default='tail', choices=['tail', 'gated'],
-                  help="how update()'s lax.cond is realised: device tail launch or gated kernels")
+  ap.add_argument('--update-mode', default='fused', choices=['fused', 'gated'],
+                  help="how update()'s lax.cond is realised: one cooperative kernel or gated kernels")
   args = ap.parse_args()
   if args.impl == 'reference':
     return run_reference(args)

@@ -108,15 +108,18 @@ typedef struct {
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */
 
-/* Skin predicate of NeighborList.update (partition.py:1146-1154): sets
- * state[REBUILD] = any_i |d(R_i, ref_i)|^2 > threshold_sq (or 1 when
- * always_rebuild).  tail_launch != 0: when the predicate is true the kernel
- * itself enqueues bin + build + export on the device (CUDA dynamic parallelism,
- * tail-launch stream), so the steady-state step issues no launches for the
- * lax.cond of partition.py:1146; the host then must NOT call the gated
- * bin/build/export for this update. */
-int jmd_nbr_skin_check(const jmd_nbr_t* nb, const void* position,
-                       int tail_launch, void* stream);
+/* NeighborList.update (partition.py:1119-1154) as ONE cooperative kernel:
+ * skin predicate any_i |d(R_i, ref_i)|^2 > threshold_sq (or always_rebuild);
+ * when it is false every block returns, otherwise the same kernel bins, scans
+ * the stencil, exports idx in nb->format, ORs the error bits and stores the new
+ * reference positions, with grid-wide barriers between phases.  This is the
+ * lax.cond of partition.py:1146 without a host round trip.  Leaves
+ * state[REBUILD] = decision. */
+int jmd_nbr_update(const jmd_nbr_t* nb, const void* position, void* stream);
+
+/* The skin predicate alone: state[REBUILD] = decision.  Used with the gated
+ * bin/build/export below as a fallback to jmd_nbr_update. */
+int jmd_nbr_skin_check(const jmd_nbr_t* nb, const void* position, void* stream);
 
 /* Bin atoms into cells and sort them (partition.py:421-460).  gated != 0:
  * kernels exit early unless state[REBUILD] is set (the lax.cond of

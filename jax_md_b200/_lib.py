@@ -67,7 +67,8 @@ class SwT(C.Structure):
 _P, _I, _D, _L = C.c_void_p, C.c_int, C.c_double, C.c_int64
 # name -> argtypes; every function returns int (0 == ok) unless noted.
 _SIGNATURES = {
-    'jmd_nbr_skin_check': [C.POINTER(NbrT), _P, _I, _P],
+    'jmd_nbr_update': [C.POINTER(NbrT), _P, _P],
+    'jmd_nbr_skin_check': [C.POINTER(NbrT), _P, _P],
     'jmd_nbr_bin': [C.POINTER(NbrT), _P, _I, _P],
     'jmd_nbr_build': [C.POINTER(NbrT), _P, _I, _I, _P],
     'jmd_nbr_export': [C.POINTER(NbrT), _P, _I, _P],

@@ -2,10 +2,8 @@
 
     python -m jax_md_b200.build [--force] [--verbose]
 
-The neighbour-list translation unit uses CUDA dynamic parallelism (the skin
-predicate tail-launches the rebuild from the device), so it is compiled with
--rdc=true and device-linked against cudadevrt; the other units are ordinary
-whole-program compiles.
+Every unit is an ordinary whole-program compile (no -rdc); the neighbour-list
+update kernel uses cooperative-groups grid synchronisation, which needs none.
 """
 import hashlib
 import os
@@ -22,8 +20,8 @@ ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
           '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
           '--expt-relaxed-constexpr', '-Xptxas', '-v']
-RDC_UNITS = ['jmd_neighbor.cu']
-UNITS = ['jmd_pair.cu', 'jmd_integrate.cu', 'jmd_sw.cu', 'jmd_domain.cu']
+RDC_UNITS = []
+UNITS = ['jmd_neighbor.cu', 'jmd_pair.cu', 'jmd_integrate.cu', 'jmd_sw.cu', 'jmd_domain.cu']
 
 
 def _sources():
@@ -86,12 +84,7 @@ def build(force=False, verbose=False):
         failed = u
     if failed:
       raise RuntimeError('nvcc failed on ' + failed)
-    rdc_objs = [os.path.join(OBJ, u.replace('.cu', '.o')) for u in RDC_UNITS]
-    dlink = os.path.join(OBJ, 'dlink.o')
-    _run([NVCC] + ARCH + ['-dlink', '-Xcompiler', '-fPIC'] + rdc_objs +
-         ['-o', dlink, '-lcudadevrt'], verbose, log)
-    _run([NVCC, '-shared', '-o', OUT] + objs + [dlink, '-lcudadevrt',
-                                                 '-lcudart'], verbose, log)
+    _run([NVCC, '-shared', '-o', OUT] + objs + ['-lcudart'], verbose, log)
   with open(stamp, 'w') as f:
     f.write(digest)
   return OUT

@@ -41,36 +41,54 @@ __device__ __forceinline__ T mod_pos(T t, T L) {
   return m;
 }
 
+// round-to-nearest-integer by the magic-constant trick (2 full-rate adds, no
+// branch): valid for |x| < 2^22 (f32) / 2^51 (f64).
+__device__ __forceinline__ float rint_magic(float x) {
+  return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f);
+}
+__device__ __forceinline__ double rint_magic(double x) {
+  return __dadd_rn(__dadd_rn(x, 6755399441055744.0), -6755399441055744.0);
+}
+
 template <typename T, int DIM>
 struct Space {
   T side[DIM];
   T half[DIM];
+  T quarter[DIM];    // half / 2: |d| <= quarter takes the exact fast path
+  T inv_side[DIM];   // 1 / side, or 0 for free space (then disp_fast is a no-op)
+  T side_f[DIM];     // side, or 0 for free space
   int periodic;
   int wrapped;
   __host__ void init(const jmd_space_t& s) {
-    for (int k = 0; k < DIM; ++k) { side[k] = (T)s.side[k]; half[k] = (T)s.half[k]; }
     periodic = s.kind == JMD_SPACE_PERIODIC;
     wrapped = s.wrapped;
+    for (int k = 0; k < DIM; ++k) {
+      side[k] = (T)s.side[k];
+      half[k] = (T)s.half[k];
+      quarter[k] = periodic ? (T)(s.half[k] * 0.5) : (T)0;
+      inv_side[k] = periodic && s.side[k] != 0 ? (T)(1.0 / s.side[k]) : (T)0;
+      side_f[k] = periodic ? (T)s.side[k] : (T)0;
+    }
   }
-  // Exact displacement component d(a, b)_k (space.py:213-224).
+  // Exact displacement component d(a, b)_k (space.py:213-224):
+  //   mod(fl(a - b) + h, L) - h.
+  // For |a - b| <= h/2 the sum t = fl(d + h) lies in [h/2, 3h/2], strictly inside
+  // (0, L), so jnp.mod returns t itself and the result is fl(t - h): two adds.
   __device__ __forceinline__ T disp(T a, T b, int k) const {
     T d = sub_rn(a, b);
     if (periodic) {
       T t = add_rn(d, half[k]);
+      if (fabs(d) <= quarter[k]) return sub_rn(t, half[k]);
       d = sub_rn(mod_pos(t, side[k]), half[k]);
     }
     return d;
   }
-  // Fast minimum image for the force kernels (tolerance-level, not bit-level):
-  // positions may be unwrapped, so use rint.
+  // Branch-free minimum image for the force kernels (tolerance-level, not
+  // bit-level; handles unwrapped positions): d - L * rint(d / L).
   __device__ __forceinline__ T disp_fast(T a, T b, int k) const {
     T d = a - b;
-    if (periodic) {
-      T h = half[k];
-      if (d >= h) { d -= side[k]; if (d >= h) d -= side[k] * rint(d / side[k]); }
-      else if (d < -h) { d += side[k]; if (d < -h) d -= side[k] * rint(d / side[k]); }
-    }
-    return d;
+    T r = rint_magic(d * inv_side[k]);
+    return d - side_f[k] * r;
   }
   // shift_fn (space.py:250-252 / 268-270)
   __device__ __forceinline__ T shift(T r, T dr, int k) const {

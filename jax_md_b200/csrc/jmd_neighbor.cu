@@ -2,19 +2,26 @@
 //
 // Replaces the reference pipeline partition.py:349-471 (cell list by argsort +
 // scatter) and partition.py:911-1154 (candidate gather, distance mask, cumsum
-// compaction, skin predicate under lax.cond) with:
-//   k_skin        max-displacement predicate, last block latches the decision
-//                 and (tail_launch mode) launches the rebuild from the device,
-//                 so the steady-state step pays no launches for the lax.cond.
-//   k_zero/k_hash/k_scan*/k_scatter/k_rank_sort
-//                 counting sort of cell hashes -> cell-ordered float4 positions
-//   k_build_*     stencil scan, one warp per home cell, candidates staged in
-//                 shared memory once per cell, warp-ballot compaction into
-//                 capacity-bounded transposed rows (order == reference order)
-//   k_export / k_finalize
-//                 public idx (Dense / Sparse / OrderedSparse), error bits.
+// compaction, skin predicate under lax.cond).  Every stage is a grid-stride
+// "phase" (a __device__ function); the phases are used two ways:
+//
+//   k_update   ONE persistent cooperative kernel per NeighborList.update():
+//              phase 0 is the skin predicate (max displacement vs threshold);
+//              if no atom moved past skin/2 every block returns, otherwise the
+//              same kernel runs the whole rebuild with grid-wide barriers
+//              between phases.  This is the lax.cond of partition.py:1146 with
+//              no host round trip and no extra launches on the common path.
+//   k_phase<>  one ordinary kernel per phase for the host-driven allocate path
+//              (which needs occupancies on the host between stages) and for the
+//              "gated" fallback update mode.
+//
+// Phases:  zero / hash+histogram / 3-pass exclusive scan / scatter / in-cell
+// order (reference slot order) / stencil scan with exact reference arithmetic /
+// sparse offsets / tile-transposed export to Dense|Sparse|OrderedSparse / error
+// bits + reference positions.
 #include <cuda_runtime.h>
-#include <stdio.h>
+#include <math.h>
+#include <type_traits>
 #include "jmd_common.cuh"
 
 namespace {
@@ -22,21 +29,18 @@ namespace {
 enum { ST_REBUILD = JMD_ST_REBUILD, ST_MAX_CELL = JMD_ST_MAX_CELL_OCC,
        ST_MAX_ROW = JMD_ST_MAX_ROW, ST_TOTAL = JMD_ST_TOTAL,
        ST_BUILDS = JMD_ST_BUILDS, ST_TICKET = JMD_ST_SCAN_TICKET,
-       ST_PENDING = 6 };
+       ST_PENDING = 6, ST_BARRIER = 7 };
 
-#ifndef JMD_BUILD_WARP_PER_CELL
-#define JMD_BUILD_WARP_PER_CELL 0
-#endif
-constexpr int SCAN_TILE = 2048;   // 256 threads x 8
-constexpr int BUILD_WARPS = 4;
-constexpr int BUILD_CAP = 1024;   // candidates staged per warp per chunk
+constexpr int NB = 256;           // threads per block, every kernel here
+constexpr int NWARP = NB / 32;
+constexpr int SCAN_TILE = NB * 8;
 constexpr int RANK_LIMIT = 4096;  // cells above this keep arrival order
 
 template <typename T, int DIM>
 struct NbrP {
   int n, format, use_cells, mask_self, always_rebuild, n_cells, cell_capacity, m_int;
   int cps[3];
-  int count_only, tail_launch, two_sided, rev_only;
+  int count_only, two_sided, rev_only;
   long long n_pad, max_occupancy;
   T cell_size[DIM];
   T cutoff_sq, threshold_sq, band, far;
@@ -55,7 +59,43 @@ struct NbrP {
   const T* position;
 };
 
-#define GATE(P, gated) if ((gated) && (P).state[ST_REBUILD] == 0) return
+struct Smem {
+  int tile[NWARP][32][33];   // export: one padded 32x32 tile per warp
+  long long scan[NWARP];
+};
+
+__device__ __forceinline__ int gtid() { return blockIdx.x * NB + threadIdx.x; }
+__device__ __forceinline__ int gthreads() { return gridDim.x * NB; }
+
+// Grid-wide barrier for the persistent update kernels.  They are launched with
+// exactly one co-resident wave of blocks (occupancy API x SM count) as ORDINARY
+// launches: cudaLaunchCooperativeKernel costs ~35 us of device time per launch
+// on B200 (measured), which is more than the skin predicate itself.  `bar` is a
+// pair of zero-initialised counters {arrivals, exits}; the last block to leave
+// the kernel (grid_exit) zeroes them for the next launch.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(&bar[0], 1u);
+    while (*((volatile unsigned int*)&bar[0]) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void grid_exit(unsigned int* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&bar[1], 1u) == gridDim.x - 1) {
+      bar[0] = 0u;
+      bar[1] = 0u;
+      __threadfence();
+    }
+  }
+}
 
 template <typename T>
 __device__ __forceinline__ typename Vec4<T>::type make_v4(T x, T y, T z, T w);
@@ -77,34 +117,39 @@ __device__ __forceinline__ typename Vec4<T>::type load_atom(const NbrP<T, DIM>& 
   return make_v4<T>(r[0], r[1], z, w);
 }
 
-// ---- binning -------------------------------------------------------------------
-
+// ---- phase: skin predicate (partition.py:1146-1154) ------------------------------
 template <typename T, int DIM>
-__global__ void k_zero(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int stride = gridDim.x * blockDim.x;
-  for (int c = i; c <= P.n_cells; c += stride) {
+__device__ bool ph_skin(const NbrP<T, DIM>& P) {
+  bool moved = false;
+  if (P.always_rebuild) return true;
+  for (int i = gtid(); i < P.n; i += gthreads()) {
+    T a[DIM], b[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      a[k] = P.position[(size_t)i * DIM + k];
+      b[k] = P.ref[(size_t)i * DIM + k];
+    }
+    T d2 = dist2_exact<T, DIM>(P.sp, a, b);
+    moved = moved || (d2 > P.threshold_sq);      // strict >, min-image metric
+  }
+  return moved;
+}
+
+// ---- phases: binning -----------------------------------------------------------------
+template <typename T, int DIM>
+__device__ void ph_zero(const NbrP<T, DIM>& P) {
+  for (int c = gtid(); c <= P.n_cells; c += gthreads()) {
     P.cell_count[c] = 0;
     if (c < P.n_cells) P.cell_cursor[c] = 0;
   }
-  if (i == 0) P.state[ST_MAX_CELL] = 0;
-}
-
-template <typename T, int DIM>
-__global__ void k_build_reset(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  P.state[ST_MAX_ROW] = 0;
-  P.state[ST_TOTAL] = 0;
+  if (gtid() == 0) P.state[ST_MAX_CELL] = 0;
 }
 
 // partition.py:421-423: int32(R / cell_size) (truncation), mod cells_per_side,
 // hash = x + y*cx + z*cx*cy.
 template <typename T, int DIM>
-__global__ void k_hash(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+__device__ void ph_hash(const NbrP<T, DIM>& P) {
+  for (int i = gtid(); i < P.n; i += gthreads()) {
     const T* r = P.position + (size_t)i * DIM;
     int h = 0, mult = 1;
 #pragma unroll
@@ -120,20 +165,9 @@ __global__ void k_hash(NbrP<T, DIM> P, int gated) {
   }
 }
 
-// three-pass exclusive scan: tile sums, scan of tile sums, apply.
-template <typename TIn, typename TOut>
-__device__ __forceinline__ void scan_tile_load(const TIn* in, long long n, long long base,
-                                               TOut (&v)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    long long i = base + (long long)threadIdx.x * 8 + j;
-    v[j] = i < n ? (TOut)in[i] : TOut(0);
-  }
-}
-
+// exclusive scan of one value per thread across the block
 template <typename TOut>
-__device__ __forceinline__ TOut block_excl_scan_256(TOut x, TOut* total, TOut* smem /*[8]*/) {
-  // exclusive scan of one value per thread across 256 threads
+__device__ __forceinline__ TOut block_excl_scan(TOut x, TOut* total, long long* smem /*[NWARP]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   TOut incl = x;
 #pragma unroll
@@ -141,12 +175,12 @@ __device__ __forceinline__ TOut block_excl_scan_256(TOut x, TOut* total, TOut* s
     TOut y = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += y;
   }
-  if (lane == 31) smem[warp] = incl;
+  if (lane == 31) smem[warp] = (long long)incl;
   __syncthreads();
   TOut wbase = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    TOut s = smem[w];
+  for (int w = 0; w < NWARP; ++w) {
+    TOut s = (TOut)smem[w];
     if (w < warp) wbase += s;
     tot += s;
   }
@@ -156,70 +190,80 @@ __device__ __forceinline__ TOut block_excl_scan_256(TOut x, TOut* total, TOut* s
 }
 
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) k_scan_tiles(const TIn* in, long long n, TOut* tile_sums,
-                                                    long long* max_out, const long long* gate) {
-  if (gate && *gate == 0) return;
-  __shared__ TOut sm[8];
-  TOut v[8];
-  scan_tile_load<TIn, TOut>(in, n, (long long)blockIdx.x * SCAN_TILE, v);
-  TOut s = 0, mx = 0;
+__device__ __forceinline__ void scan_tile_load(const TIn* in, long long n, long long base, TOut (&v)[8]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s += v[j]; mx = v[j] > mx ? v[j] : mx; }
-  TOut tot;
-  block_excl_scan_256<TOut>(s, &tot, sm);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-  if (max_out) {
+  for (int j = 0; j < 8; ++j) {
+    long long i = base + (long long)threadIdx.x * 8 + j;
+    v[j] = i < n ? (TOut)in[i] : TOut(0);
+  }
+}
+
+// three-pass exclusive scan of in[0..n) -> out[0..n]; tile_sums scratch
+template <typename TIn, typename TOut>
+__device__ void ph_scan_tiles(const TIn* in, long long n, TOut* tile_sums, long long* max_out, Smem& sm) {
+  const long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    TOut v[8];
+    scan_tile_load<TIn, TOut>(in, n, t * SCAN_TILE, v);
+    TOut s = 0, mx = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      TOut y = __shfl_xor_sync(0xffffffffu, mx, o);
-      mx = y > mx ? y : mx;
+    for (int j = 0; j < 8; ++j) { s += v[j]; mx = v[j] > mx ? v[j] : mx; }
+    TOut tot;
+    block_excl_scan<TOut>(s, &tot, sm.scan);
+    if (threadIdx.x == 0) tile_sums[t] = tot;
+    if (max_out) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        TOut y = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = y > mx ? y : mx;
+      }
+      if ((threadIdx.x & 31) == 0 && mx > 0)
+        atomicMax((unsigned long long*)max_out, (unsigned long long)mx);
     }
-    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax((unsigned long long*)max_out, (unsigned long long)mx);
   }
 }
 
 template <typename TOut>
-__global__ void __launch_bounds__(256) k_scan_top(TOut* tile_sums, int n_tiles, const long long* gate) {
-  if (gate && *gate == 0) return;
-  __shared__ TOut sm[8];
+__device__ void ph_scan_top(TOut* tile_sums, long long n, Smem& sm) {
+  if (blockIdx.x != 0) return;
+  const int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   TOut carry = 0;
-  for (int base = 0; base < n_tiles; base += 256) {
+  for (int base = 0; base < tiles; base += NB) {
     int i = base + threadIdx.x;
-    TOut x = i < n_tiles ? tile_sums[i] : TOut(0);
+    TOut x = i < tiles ? tile_sums[i] : TOut(0);
     TOut tot;
-    TOut e = block_excl_scan_256<TOut>(x, &tot, sm);
-    if (i < n_tiles) tile_sums[i] = carry + e;
+    TOut e = block_excl_scan<TOut>(x, &tot, sm.scan);
+    if (i < tiles) tile_sums[i] = carry + e;
     carry += tot;
   }
 }
 
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) k_scan_apply(const TIn* in, long long n, const TOut* tile_sums,
-                                                    TOut* out /*[n+1]*/, const long long* gate) {
-  if (gate && *gate == 0) return;
-  __shared__ TOut sm[8];
-  TOut v[8];
-  long long base = (long long)blockIdx.x * SCAN_TILE;
-  scan_tile_load<TIn, TOut>(in, n, base, v);
-  TOut s = 0;
+__device__ void ph_scan_apply(const TIn* in, long long n, const TOut* tile_sums, TOut* out, Smem& sm) {
+  const long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    TOut v[8];
+    const long long base = t * SCAN_TILE;
+    scan_tile_load<TIn, TOut>(in, n, base, v);
+    TOut s = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s += v[j];
-  TOut tot;
-  TOut e = block_excl_scan_256<TOut>(s, &tot, sm) + tile_sums[blockIdx.x];
+    for (int j = 0; j < 8; ++j) s += v[j];
+    TOut tot;
+    TOut e = block_excl_scan<TOut>(s, &tot, sm.scan) + tile_sums[t];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    long long i = base + (long long)threadIdx.x * 8 + j;
-    if (i < n) out[i] = e;
-    e += v[j];
-    if (i == n - 1) out[n] = e;
+    for (int j = 0; j < 8; ++j) {
+      long long i = base + (long long)threadIdx.x * 8 + j;
+      if (i < n) out[i] = e;
+      e += v[j];
+      if (i == n - 1) out[n] = e;
+    }
   }
+  if (n == 0 && gtid() == 0) out[0] = 0;
 }
 
 template <typename T, int DIM>
-__global__ void k_scatter(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+__device__ void ph_scatter(const NbrP<T, DIM>& P) {
+  for (int i = gtid(); i < P.n; i += gthreads()) {
     int h = P.hash[i];
     int pos = P.cell_start[h] + atomicAdd(&P.cell_cursor[h], 1);
     P.tmp_ids[pos] = i;
@@ -227,13 +271,16 @@ __global__ void k_scatter(NbrP<T, DIM> P, int gated) {
   }
 }
 
-// Stable order inside a cell (== stable argsort of hashes, partition.py:432):
-// rank = #atoms of the same cell with a smaller id.
+// Order inside a cell.  The reference sorts atoms by hash with a stable argsort
+// (partition.py:432: arrival order == id order) and then places sorted rank r
+// in slot `r mod cell_capacity` (partition.py:441), so reading a cell in slot
+// order yields the arrival order ROTATED by r0 = cap - start % cap (when that
+// is < count).  We store each cell directly in that slot order, so the stencil
+// scan walks plain contiguous ranges and emits candidates in reference order.
 template <typename T, int DIM>
-__global__ void k_rank_sort(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+__device__ void ph_rank_sort(const NbrP<T, DIM>& P) {
+  const int cap = P.cell_capacity > 0 ? P.cell_capacity : 1;
+  for (int i = gtid(); i < P.n; i += gthreads()) {
     int h = P.hash[i];
     int s = P.cell_start[h];
     int c = P.cell_start[h + 1] - s;
@@ -244,41 +291,47 @@ __global__ void k_rank_sort(NbrP<T, DIM> P, int gated) {
     } else {
       rank = P.inv_perm[i] - s;
     }
-    int dst = s + rank;
+    const int room = cap - s % cap;
+    const int r0 = room < c ? room : 0;
+    int q = rank - r0;
+    q = q < 0 ? q + c : q;
+    int dst = s + q;
     P.perm[dst] = i;
     P.pos_sorted[dst] = load_atom(P, i);
   }
 }
 
-// inv_perm is read by k_rank_sort (arrival position) so it is rewritten after.
+// inv_perm held the arrival position for ph_rank_sort; now the final slot.
 template <typename T, int DIM>
-__global__ void k_inv_perm(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  int stride = gridDim.x * blockDim.x;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P.n; t += stride) P.inv_perm[P.perm[t]] = t;
+__device__ void ph_inv_perm(const NbrP<T, DIM>& P) {
+  for (int t = gtid(); t < P.n; t += gthreads()) P.inv_perm[P.perm[t]] = t;
+}
+
+template <typename T, int DIM>
+__device__ void ph_build_reset(const NbrP<T, DIM>& P) {
+  if (gtid() == 0) {
+    P.state[ST_MAX_ROW] = 0;
+    P.state[ST_TOTAL] = 0;
+  }
 }
 
 // all-pairs path: identity order.
 template <typename T, int DIM>
-__global__ void k_identity_sort(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+__device__ void ph_identity_sort(const NbrP<T, DIM>& P) {
+  for (int i = gtid(); i < P.n; i += gthreads()) {
     P.perm[i] = i;
     P.inv_perm[i] = i;
     P.pos_sorted[i] = load_atom(P, i);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) P.state[ST_MAX_CELL] = 0;
+  if (gtid() == 0) P.state[ST_MAX_CELL] = 0;
 }
 
 template <typename T, int DIM>
-__global__ void k_pack(NbrP<T, DIM> P) {
-  int stride = gridDim.x * blockDim.x;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P.n; t += stride)
-    P.pos_sorted[t] = load_atom(P, P.perm[t]);
+__device__ void ph_pack(const NbrP<T, DIM>& P) {
+  for (int t = gtid(); t < P.n; t += gthreads()) P.pos_sorted[t] = load_atom(P, P.perm[t]);
 }
 
-// ---- candidate test -------------------------------------------------------------
+// ---- candidate test -------------------------------------------------------------------
 // Reference semantics (oracle/partition.py): the cell path tests
 // d2(R_i, R_c) < cutoff^2 (partition.py:945-951); Dense then re-tests with the
 // opposite orientation d2(R_c, R_i) (prune_neighbor_list_dense via map_neighbor,
@@ -302,203 +355,7 @@ __device__ __forceinline__ bool candidate_test(const NbrP<T, DIM>& P, const T* h
   return keep;
 }
 
-template <typename T, int DIM>
-__device__ __forceinline__ void append_rows(const NbrP<T, DIM>& P, int slot, int hid, bool keep,
-                                            int cslot, int cid, int& k, int& kl) {
-  const unsigned lane = threadIdx.x & 31;
-  unsigned b = __ballot_sync(0xffffffffu, keep);
-  if (keep && !P.count_only) {
-    int pos = k + __popc(b & ((1u << lane) - 1u));
-    if (pos < P.m_int) P.nl[(size_t)pos * P.n_pad + slot] = cslot;
-  }
-  k += __popc(b);
-  kl += __popc(__ballot_sync(0xffffffffu, keep && cid < hid));
-}
-
-template <typename T, int DIM>
-__global__ void __launch_bounds__(BUILD_WARPS * 32) k_build_cells(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  using V4 = typename Vec4<T>::type;
-  constexpr int NS = DIM == 3 ? 27 : 9;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  V4* cand_pos = reinterpret_cast<V4*>(smem_raw) + (size_t)wib * BUILD_CAP;
-  int* ibase = reinterpret_cast<int*>(smem_raw + sizeof(V4) * BUILD_CAP * BUILD_WARPS);
-  int* cand_slot = ibase + (size_t)wib * (2 * BUILD_CAP + 4 * 32);
-  int* cand_id = cand_slot + BUILD_CAP;
-  int* st_start = cand_id + BUILD_CAP;
-  int* st_count = st_start + 32;
-  int* st_rot = st_count + 32;
-  int* st_off = st_rot + 32;
-
-  const int nwarps = gridDim.x * BUILD_WARPS;
-  long long wmax = 0, wtotal = 0;
-  const int cx_n = P.cps[0], cy_n = P.cps[1];
-  for (int c = blockIdx.x * BUILD_WARPS + wib; c < P.n_cells; c += nwarps) {
-    const int hs = P.cell_start[c];
-    const int hn = P.cell_start[c + 1] - hs;
-    if (hn == 0) continue;
-    int cc[3];
-    cc[0] = c % cx_n;
-    cc[1] = (c / cx_n) % cy_n;
-    cc[2] = DIM == 3 ? c / (cx_n * cy_n) : 0;
-    // stencil, reference order: first coordinate slowest (partition.py:232-240)
-    int my_start = 0, my_cnt = 0, my_rot = 0;
-    if (lane < NS) {
-      int sh[3];
-      if (DIM == 3) { sh[0] = lane / 9 - 1; sh[1] = (lane / 3) % 3 - 1; sh[2] = lane % 3 - 1; }
-      else { sh[0] = lane / 3 - 1; sh[1] = lane % 3 - 1; sh[2] = 0; }
-      int h = 0, mult = 1;
-#pragma unroll
-      for (int k = 0; k < DIM; ++k) {
-        int v = cc[k] + sh[k];
-        v = v < 0 ? v + P.cps[k] : (v >= P.cps[k] ? v - P.cps[k] : v);
-        h += v * mult;
-        mult *= P.cps[k];
-      }
-      my_start = P.cell_start[h];
-      my_cnt = P.cell_start[h + 1] - my_start;
-      // slot = sorted_rank mod capacity (partition.py:441): slot order inside a
-      // cell is arrival order rotated by `rot`.
-      int cap = P.cell_capacity > 0 ? P.cell_capacity : 1;
-      int room = cap - my_start % cap;
-      my_rot = my_cnt < room ? my_cnt : room;
-    }
-    int incl = my_cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    __syncwarp();
-    st_start[lane] = my_start;
-    st_count[lane] = my_cnt;
-    st_rot[lane] = my_rot;
-    st_off[lane] = incl - my_cnt;
-    __syncwarp();
-
-    for (int chunk = 0; chunk < total; chunk += BUILD_CAP) {
-      const int nchunk = min(BUILD_CAP, total - chunk);
-      for (int q = lane; q < nchunk; q += 32) {
-        int ci = chunk + q;
-        int s = 0;
-        while (s + 1 < NS && st_off[s + 1] <= ci) ++s;
-        int within = ci - st_off[s];
-        int cntc = st_count[s];
-        int r = within + st_rot[s];
-        r = r >= cntc ? r - cntc : r;
-        int rank = st_start[s] + r;
-        cand_pos[q] = P.pos_sorted[rank];
-        cand_slot[q] = rank;
-        cand_id[q] = P.perm[rank];
-      }
-      __syncwarp();
-      const bool last_chunk = chunk + BUILD_CAP >= total;
-      for (int h = 0; h < hn; ++h) {
-        const int slot = hs + h;
-        const V4 hv = P.pos_sorted[slot];
-        const T hp[3] = {hv.x, hv.y, hv.z};
-        const int hid = P.perm[slot];
-        int k = 0, kl = 0;
-        if (chunk != 0) { k = P.cnt[slot]; kl = P.cnt_lower[slot]; }
-        for (int q0 = 0; q0 < nchunk; q0 += 32) {
-          const int q = q0 + lane;
-          bool keep = false;
-          int cslot = 0, cid = 0;
-          if (q < nchunk) {
-            const V4 cv = cand_pos[q];
-            const T cp[3] = {cv.x, cv.y, cv.z};
-            cslot = cand_slot[q];
-            cid = cand_id[q];
-            keep = candidate_test<T, DIM>(P, hp, cp);
-            if (P.mask_self && cslot == slot) keep = false;
-          }
-          append_rows<T, DIM>(P, slot, hid, keep, cslot, cid, k, kl);
-        }
-        if (lane == 0) { P.cnt[slot] = k; P.cnt_lower[slot] = kl; }
-        if (last_chunk) {
-          wmax = k > wmax ? k : wmax;
-          wtotal += (P.format == JMD_ORDERED_SPARSE) ? kl : k;
-        }
-      }
-      __syncwarp();
-    }
-  }
-  if (lane == 0) {
-    if (wmax > 0) atomicMax((unsigned long long*)&P.state[ST_MAX_ROW], (unsigned long long)wmax);
-    if (wtotal > 0) atomicAdd((unsigned long long*)&P.state[ST_TOTAL], (unsigned long long)wtotal);
-  }
-}
-
-// Thread-per-atom stencil scan (the default).  Thread t owns sorted slot t and
-// walks the 3^d stencil cells of its own cell in reference order; candidates
-// of a cell are a contiguous range of the cell-sorted float4 array, so the 32
-// lanes of a warp (2-3 adjacent cells) issue loads that hit 2-3 distinct
-// addresses (L1 broadcast).  Every row is appended in candidate order by its
-// own thread: no ballots, no atomics, order == reference order.  Row k of the
-// transposed list is written by neighbouring lanes at neighbouring addresses.
-constexpr int TPA_BLOCK = 128;
-
-template <typename T, int DIM, bool ORDERED>
-__global__ void __launch_bounds__(TPA_BLOCK) k_build_cells_tpa(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  using V4 = typename Vec4<T>::type;
-  constexpr int NS = DIM == 3 ? 27 : 9;
-  const int slot = blockIdx.x * TPA_BLOCK + threadIdx.x;
-  long long my_k = 0, my_tot = 0;
-  if (slot < P.n) {
-    const V4 hv = P.pos_sorted[slot];
-    const T hp[3] = {hv.x, hv.y, hv.z};
-    const int hid = P.perm[slot];
-    // own cell from the stored hash of this atom
-    const int c = P.hash[hid];
-    const int cx_n = P.cps[0], cy_n = P.cps[1];
-    int cc[3];
-    cc[0] = c % cx_n;
-    cc[1] = (c / cx_n) % cy_n;
-    cc[2] = DIM == 3 ? c / (cx_n * cy_n) : 0;
-    const int cap = P.cell_capacity > 0 ? P.cell_capacity : 1;
-    int k = 0, kl = 0;
-    int* out = P.nl + slot;
-    for (int s = 0; s < NS; ++s) {
-      int sh[3];
-      if (DIM == 3) { sh[0] = s / 9 - 1; sh[1] = (s / 3) % 3 - 1; sh[2] = s % 3 - 1; }
-      else { sh[0] = s / 3 - 1; sh[1] = s % 3 - 1; sh[2] = 0; }
-      int h = 0, mult = 1;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        int v = cc[d] + sh[d];
-        v = v < 0 ? v + P.cps[d] : (v >= P.cps[d] ? v - P.cps[d] : v);
-        h += v * mult;
-        mult *= P.cps[d];
-      }
-      const int start = __ldg(&P.cell_start[h]);
-      const int count = __ldg(&P.cell_start[h + 1]) - start;
-      // slot = sorted_rank mod capacity (partition.py:441): rotated arrival order
-      const int room = cap - start % cap;
-      int r = count < room ? count : room;       // first rank offset in slot order
-      if (r == count) r = 0;
-      for (int q = 0; q < count; ++q) {
-        const int rank = start + r;
-        r = r + 1 == count ? 0 : r + 1;
-        const V4 cv = P.pos_sorted[rank];
-        const T cp[3] = {cv.x, cv.y, cv.z};
-        bool keep = candidate_test<T, DIM>(P, hp, cp);
-        if (P.mask_self && rank == slot) keep = false;
-        if (keep) {
-          if (!P.count_only && k < P.m_int) out[(size_t)k * P.n_pad] = rank;
-          ++k;
-          if (ORDERED) kl += (__ldg(&P.perm[rank]) < hid);
-        }
-      }
-    }
-    P.cnt[slot] = k;
-    P.cnt_lower[slot] = kl;
-    my_k = k;
-    my_tot = ORDERED ? kl : k;
-  }
-  // block max / total -> one atomic each per warp
+__device__ __forceinline__ void publish_counts(long long* state, long long my_k, long long my_tot) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     long long y = __shfl_xor_sync(0xffffffffu, my_k, o);
@@ -506,20 +363,126 @@ __global__ void __launch_bounds__(TPA_BLOCK) k_build_cells_tpa(NbrP<T, DIM> P, i
     my_tot += __shfl_xor_sync(0xffffffffu, my_tot, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    if (my_k > 0) atomicMax((unsigned long long*)&P.state[ST_MAX_ROW], (unsigned long long)my_k);
-    if (my_tot > 0) atomicAdd((unsigned long long*)&P.state[ST_TOTAL], (unsigned long long)my_tot);
+    if (my_k > 0) atomicMax((unsigned long long*)&state[ST_MAX_ROW], (unsigned long long)my_k);
+    if (my_tot > 0) atomicAdd((unsigned long long*)&state[ST_TOTAL], (unsigned long long)my_tot);
+  }
+}
+
+// Thread-per-atom stencil scan.  A thread owns sorted slot `slot` and walks the
+// 3^d stencil cells of its own cell in reference order (first coordinate
+// slowest, partition.py:232-240); the candidates of a cell are a contiguous
+// range of the cell-sorted float4 array stored in reference slot order, so the
+// 32 lanes of a warp (2-3 adjacent cells) issue loads that hit 2-3 distinct
+// addresses (L1 broadcast).  Every row is appended in candidate order by its
+// own thread: no ballots, no atomics, order == reference order.  Row k of the
+// transposed list is written by neighbouring lanes at neighbouring addresses.
+// MODE: 0 = forward test only (Sparse formats), 1 = forward + reverse inside
+// the rounding band (Dense).
+template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC>
+__device__ void ph_build_cells(const NbrP<T, DIM>& P) {
+  using V4 = typename Vec4<T>::type;
+  constexpr int NS = DIM == 3 ? 27 : 9;
+  const int lane = threadIdx.x & 31;
+  const int self_on = P.mask_self;
+  const T c2 = P.cutoff_sq;
+  constexpr bool periodic = PERIODIC;
+  const int kmax = P.count_only ? 0 : P.m_int;
+  T hh[3], qq[3];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { hh[d] = P.sp.half[d]; qq[d] = P.sp.quarter[d]; }
+  for (int wbase = gtid() - lane; wbase < P.n; wbase += gthreads()) {
+    const int slot = wbase + lane;
+    long long my_k = 0, my_tot = 0;
+    if (slot < P.n) {
+      const V4 hv = P.pos_sorted[slot];
+      const T hp[3] = {hv.x, hv.y, hv.z};
+      const int hid = P.perm[slot];
+      const int c = P.hash[hid];              // own cell (hash of this atom)
+      const int cx_n = P.cps[0], cy_n = P.cps[1];
+      int cc[3];
+      cc[0] = c % cx_n;
+      cc[1] = (c / cx_n) % cy_n;
+      cc[2] = DIM == 3 ? c / (cx_n * cy_n) : 0;
+      const int self = self_on ? slot : -1;
+      int k = 0, kl = 0;
+      int* out = P.nl + slot;
+      for (int s = 0; s < NS; ++s) {
+        int sh[3];
+        if (DIM == 3) { sh[0] = s / 9 - 1; sh[1] = (s / 3) % 3 - 1; sh[2] = s % 3 - 1; }
+        else { sh[0] = s / 3 - 1; sh[1] = s % 3 - 1; sh[2] = 0; }
+        int h = 0, mult = 1;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          int v = cc[d] + sh[d];
+          v = v < 0 ? v + P.cps[d] : (v >= P.cps[d] ? v - P.cps[d] : v);
+          h += v * mult;
+          mult *= P.cps[d];
+        }
+        const int start = __ldg(&P.cell_start[h]);
+        const int end = __ldg(&P.cell_start[h + 1]);
+        const V4* cptr = P.pos_sorted + start;
+        for (int rank = start; rank < end; ++rank, ++cptr) {
+          const V4 cv = *cptr;
+          // forward displacement d(R_i, R_c), exact (space.py:213-235)
+          T dd[3];
+          dd[0] = sub_rn(hp[0], cv.x);
+          dd[1] = sub_rn(hp[1], cv.y);
+          dd[2] = DIM == 3 ? sub_rn(hp[2], cv.z) : T(0);
+          T d2;
+          bool slow = false;
+          if (!periodic) {
+            d2 = mul_rn(dd[0], dd[0]);
+#pragma unroll
+            for (int d = 1; d < DIM; ++d) d2 = add_rn(d2, mul_rn(dd[d], dd[d]));
+          } else {
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) slow = slow || !(fabs(dd[d]) <= qq[d]);
+            if (!slow) {
+              // |d| <= L/4: mod() is the identity on fl(d + h) (see Space::disp)
+              T m0 = sub_rn(add_rn(dd[0], hh[0]), hh[0]);
+              d2 = mul_rn(m0, m0);
+#pragma unroll
+              for (int d = 1; d < DIM; ++d) {
+                T m = sub_rn(add_rn(dd[d], hh[d]), hh[d]);
+                d2 = add_rn(d2, mul_rn(m, m));
+              }
+            } else {
+              const T cp[3] = {cv.x, cv.y, cv.z};
+              d2 = dist2_exact<T, DIM>(P.sp, hp, cp);
+            }
+          }
+          bool keep = d2 < c2;
+          if (MODE == 1 && periodic) {
+            if (slow || (fabs(d2 - c2) <= P.band)) {
+              const T cp[3] = {cv.x, cv.y, cv.z};
+              keep = keep && (dist2_exact<T, DIM>(P.sp, cp, hp) < c2);
+            }
+          }
+          keep = keep && (rank != self);
+          if (keep) {
+            if (k < kmax) { *out = rank; out += P.n_pad; }
+            ++k;
+            if (ORDERED) kl += (__ldg(&P.perm[rank]) < hid);
+          }
+        }
+      }
+      P.cnt[slot] = k;
+      P.cnt_lower[slot] = kl;
+      my_k = k;
+      my_tot = ORDERED ? kl : k;
+    }
+    publish_counts(P.state, my_k, my_tot);
   }
 }
 
 // all-pairs candidates (partition.py:904-909): one warp per atom, candidates in
-// id order.
+// id order, warp-ballot compaction.
 template <typename T, int DIM>
-__global__ void __launch_bounds__(128) k_build_all_pairs(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
+__device__ void ph_build_all_pairs(const NbrP<T, DIM>& P) {
   using V4 = typename Vec4<T>::type;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  const int warp = gtid() >> 5;
+  const int nwarps = gthreads() >> 5;
   long long wmax = 0, wtotal = 0;
   for (int i = warp; i < P.n; i += nwarps) {
     const V4 hv = P.pos_sorted[i];
@@ -534,7 +497,13 @@ __global__ void __launch_bounds__(128) k_build_all_pairs(NbrP<T, DIM> P, int gat
         keep = candidate_test<T, DIM>(P, hp, cp);
         if (P.mask_self && j == i) keep = false;
       }
-      append_rows<T, DIM>(P, i, i, keep, j, j, k, kl);
+      unsigned b = __ballot_sync(0xffffffffu, keep);
+      if (keep && !P.count_only) {
+        int pos = k + __popc(b & ((1u << lane) - 1u));
+        if (pos < P.m_int) P.nl[(size_t)pos * P.n_pad + i] = j;
+      }
+      k += __popc(b);
+      kl += __popc(__ballot_sync(0xffffffffu, keep && j < i));
     }
     if (lane == 0) { P.cnt[i] = k; P.cnt_lower[i] = kl; }
     wmax = k > wmax ? k : wmax;
@@ -546,59 +515,93 @@ __global__ void __launch_bounds__(128) k_build_all_pairs(NbrP<T, DIM> P, int gat
   }
 }
 
-// ---- export to the public formats ---------------------------------------------------
+template <typename T, int DIM>
+__device__ void ph_build(const NbrP<T, DIM>& P) {
+  if (!P.use_cells) { ph_build_all_pairs<T, DIM>(P); return; }
+  if (P.sp.periodic) {
+    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, true>(P);
+    else if (P.format == JMD_SPARSE) ph_build_cells<T, DIM, 0, false, true>(P);
+    else ph_build_cells<T, DIM, 1, false, true>(P);
+  } else {
+    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, false>(P);
+    else ph_build_cells<T, DIM, 0, false, false>(P);
+  }
+}
+
+// ---- phases: export to the public formats ------------------------------------------------
 
 // per-atom (user order) number of public sparse entries
 template <typename T, int DIM>
-__global__ void k_sparse_counts(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  int stride = gridDim.x * blockDim.x;
-  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < P.n; a += stride) {
+__device__ void ph_sparse_counts(const NbrP<T, DIM>& P) {
+  for (int a = gtid(); a < P.n; a += gthreads()) {
     int t = P.inv_perm[a];
-    // rows longer than m_int are truncated; lower-count is then recomputed on export
-    int c = P.format == JMD_ORDERED_SPARSE ? P.cnt_lower[t] : min(P.cnt[t], P.m_int);
-    P.tmp_ids[a] = c;
+    P.tmp_ids[a] = P.format == JMD_ORDERED_SPARSE ? P.cnt_lower[t] : min(P.cnt[t], P.m_int);
   }
 }
 
 // Dense: idx[a, k] (partition.py:960-980, 1105); Sparse: idx[0]=receivers,
 // idx[1]=senders ordered by sender then candidate order (partition.py:1010-1032).
+// The internal list is transposed ([k][slot]).  Each WARP moves 32 slots x 32 k
+// through its own padded shared-memory tile: 32 independent coalesced row loads
+// in flight, then 32 independent perm gathers, then coalesced writes along k.
+// No block barriers.
 template <typename T, int DIM>
-__global__ void __launch_bounds__(128) k_export(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+__device__ void ph_export(const NbrP<T, DIM>& P, Smem& sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int (*tile)[33] = sm.tile[w];
   const long long cap = P.max_occupancy;
-  for (int t = warp; t < P.n; t += nwarps) {
-    const int a = P.perm[t];
-    const int c = min(P.cnt[t], P.m_int);
-    if (P.format == JMD_DENSE) {
-      int* row = P.idx + (size_t)a * cap;
-      for (int k = lane; k < cap; k += 32) {
-        int v = P.n;
-        if (k < c) v = P.perm[P.nl[(size_t)k * P.n_pad + t]];
-        row[k] = v;
+  const bool dense = P.format == JMD_DENSE;
+  const bool ordered = P.format == JMD_ORDERED_SPARSE;
+  const int nwarps = gthreads() >> 5;
+  const int ntiles = (P.n + 31) / 32;
+  for (int tI = gtid() >> 5; tI < ntiles; tI += nwarps) {
+    const int t0 = tI * 32;
+    // lane r keeps the state of slot t0 + r
+    const int slot = t0 + lane;
+    int a_l = -1, c_l = 0, kk_l = 0;
+    long long off_l = 0;
+    if (slot < P.n) {
+      a_l = P.perm[slot];
+      c_l = min(P.cnt[slot], P.m_int);
+      if (!dense) off_l = P.offsets[a_l];
+    }
+    int cmax = c_l;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    const long long kend = dense ? cap : (long long)cmax;
+    for (int k0 = 0; k0 < kend; k0 += 32) {
+      const int rows = min(32, cmax - k0);       // rows of this tile that hold data
+      __syncwarp();
+      if (slot < P.n) {
+        const int* src = P.nl + (size_t)k0 * P.n_pad + slot;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          if (r < rows) tile[r][lane] = __ldcs(src + (size_t)r * P.n_pad);
+        }
       }
-    } else {
-      long long off = P.offsets[a];
-      int* recv = P.idx;
-      int* send = P.idx + cap;
-      int kk = 0;
-      for (int k0 = 0; k0 < c; k0 += 32) {
-        const int k = k0 + lane;
+      __syncwarp();
+      const int k = k0 + lane;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int a = __shfl_sync(0xffffffffu, a_l, r);
+        if (a < 0) break;                            // slots beyond n (uniform)
+        const int c = __shfl_sync(0xffffffffu, c_l, r);
+        const bool in_row = k < c;
         int v = P.n;
-        bool keep = false;
-        if (k < c) {
-          v = P.perm[P.nl[(size_t)k * P.n_pad + t]];
-          keep = P.format == JMD_SPARSE || v < a;
+        if (in_row) v = __ldg(&P.perm[tile[lane][r]]);
+        if (dense) {
+          if (k < cap) P.idx[(size_t)a * cap + k] = v;
+        } else {
+          const bool keep = in_row && (!ordered || v < a);
+          const unsigned b = __ballot_sync(0xffffffffu, keep);
+          const long long off = __shfl_sync(0xffffffffu, off_l, r);
+          const int kk = __shfl_sync(0xffffffffu, kk_l, r);
+          if (keep) {
+            const long long pos = off + kk + __popc(b & ((1u << lane) - 1u));
+            if (pos < cap) { P.idx[pos] = v; P.idx[cap + pos] = a; }
+          }
+          if (lane == r) kk_l += __popc(b);
         }
-        unsigned b = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          long long pos = off + kk + __popc(b & ((1u << lane) - 1u));
-          if (pos < cap) { recv[pos] = v; send[pos] = a; }
-        }
-        kk += __popc(b);
       }
     }
   }
@@ -606,25 +609,20 @@ __global__ void __launch_bounds__(128) k_export(NbrP<T, DIM> P, int gated) {
 
 // pad the tail of the sparse arrays with N (partition.py:1024 `N * ones`)
 template <typename T, int DIM>
-__global__ void k_sparse_pad(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
+__device__ void ph_sparse_pad(const NbrP<T, DIM>& P) {
   const long long cap = P.max_occupancy;
-  long long start = P.offsets[P.n];
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long p = start + blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cap; p += stride) {
+  const long long start = P.offsets[P.n];
+  for (long long p = start + gtid(); p < cap; p += gthreads()) {
     P.idx[p] = P.n;
     P.idx[cap + p] = P.n;
   }
 }
 
 template <typename T, int DIM>
-__global__ void k_finalize(NbrP<T, DIM> P, int gated) {
-  GATE(P, gated);
-  long long stride = (long long)gridDim.x * blockDim.x;
-  long long total = (long long)P.n * DIM;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride)
-    P.ref[i] = P.position[i];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+__device__ void ph_finalize(const NbrP<T, DIM>& P) {
+  const long long total = (long long)P.n * DIM;
+  for (long long i = gtid(); i < total; i += gthreads()) P.ref[i] = P.position[i];
+  if (gtid() == 0) {
     unsigned e = *P.error;
     // partition.py:1066 CELL_LIST_OVERFLOW, :1110 NEIGHBOR_LIST_OVERFLOW
     if (P.use_cells && P.state[ST_MAX_CELL] > P.cell_capacity) e |= JMD_ERR_CELL_LIST_OVERFLOW;
@@ -637,103 +635,108 @@ __global__ void k_finalize(NbrP<T, DIM> P, int gated) {
   }
 }
 
-// ---- launch plan (host or device) ----------------------------------------------------
+// ---- one ordinary kernel per phase (allocate path / gated fallback) -----------------------
+enum Phase { PH_ZERO, PH_HASH, PH_SCAN1, PH_SCAN2, PH_SCAN3, PH_SCATTER, PH_RANK, PH_INVPERM,
+             PH_IDENTITY, PH_PACK, PH_BUILD_RESET, PH_BUILD, PH_SP_COUNTS, PH_SP_SCAN1,
+             PH_SP_SCAN2, PH_SP_SCAN3, PH_EXPORT, PH_SP_PAD, PH_FINALIZE };
 
-template <typename T, int DIM>
-__host__ __device__ inline size_t build_smem_bytes() {
-  return (sizeof(typename Vec4<T>::type) * BUILD_CAP + sizeof(int) * (2 * BUILD_CAP + 4 * 32)) * BUILD_WARPS;
+template <typename T, int DIM, int PHASE>
+__global__ void __launch_bounds__(NB, 3) k_phase(NbrP<T, DIM> P, int gated) {
+  if (gated && P.state[ST_REBUILD] == 0) return;
+  __shared__ Smem sm;
+  long long* sp_sums = (long long*)P.scan_tmp;
+  switch (PHASE) {
+    case PH_ZERO: ph_zero(P); break;
+    case PH_HASH: ph_hash(P); break;
+    case PH_SCAN1: ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, &P.state[ST_MAX_CELL], sm); break;
+    case PH_SCAN2: ph_scan_top<int>(P.scan_tmp, P.n_cells, sm); break;
+    case PH_SCAN3: ph_scan_apply<int, int>(P.cell_count, P.n_cells, P.scan_tmp, P.cell_start, sm); break;
+    case PH_SCATTER: ph_scatter(P); break;
+    case PH_RANK: ph_rank_sort(P); break;
+    case PH_INVPERM: ph_inv_perm(P); break;
+    case PH_IDENTITY: ph_identity_sort(P); break;
+    case PH_PACK: ph_pack(P); break;
+    case PH_BUILD_RESET: ph_build_reset(P); break;
+    case PH_BUILD: ph_build(P); break;
+    case PH_SP_COUNTS: ph_sparse_counts(P); break;
+    case PH_SP_SCAN1: ph_scan_tiles<int, long long>(P.tmp_ids, P.n, sp_sums, nullptr, sm); break;
+    case PH_SP_SCAN2: ph_scan_top<long long>(sp_sums, P.n, sm); break;
+    case PH_SP_SCAN3: ph_scan_apply<int, long long>(P.tmp_ids, P.n, sp_sums, P.offsets, sm); break;
+    case PH_EXPORT: ph_export(P, sm); break;
+    case PH_SP_PAD: ph_sparse_pad(P); break;
+    case PH_FINALIZE: ph_finalize(P); break;
+  }
 }
 
-__host__ __device__ inline int grid_for(long long n, int block, int cap_blocks) {
-  long long g = (n + block - 1) / block;
+inline int grid_for(long long work_items, int per_block, int cap_blocks) {
+  long long g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;
   if (g > cap_blocks) g = cap_blocks;
   return (int)g;
 }
 
-#ifdef __CUDA_ARCH__
-#define JMD_STREAM cudaStreamTailLaunch
-#else
-#define JMD_STREAM stream
-#endif
+// The two heavy phases get their own kernel names so profiles are readable.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(NB, 3) k_nbr_stencil_scan(NbrP<T, DIM> P, int gated) {
+  if (gated && P.state[ST_REBUILD] == 0) return;
+  ph_build(P);
+}
 
 template <typename T, int DIM>
-__host__ __device__ void launch_bin(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+__global__ void __launch_bounds__(NB, 3) k_nbr_export(NbrP<T, DIM> P, int gated) {
+  if (gated && P.state[ST_REBUILD] == 0) return;
+  __shared__ Smem sm;
+  ph_export(P, sm);
+}
+
+#define LAUNCH(PH, grid) k_phase<T, DIM, PH><<<(grid), NB, 0, stream>>>(P, gated)
+#define LAUNCH_SCAN(grid) k_nbr_stencil_scan<T, DIM><<<(grid), NB, 0, stream>>>(P, gated)
+
+template <typename T, int DIM>
+void launch_bin(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   const int G = JMD_SM_COUNT * 8;
   if (!P.use_cells) {
-    k_identity_sort<T, DIM><<<grid_for(P.n, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
+    LAUNCH(PH_IDENTITY, grid_for(P.n, NB, G));
     return;
   }
-  const long long* gate = gated ? &P.state[ST_REBUILD] : nullptr;
-  int tiles = (int)((P.n_cells + SCAN_TILE - 1) / SCAN_TILE);
-  k_zero<T, DIM><<<grid_for(P.n_cells + 1, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
-  k_hash<T, DIM><<<grid_for(P.n, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
-  k_scan_tiles<int, int><<<tiles, 256, 0, JMD_STREAM>>>(P.cell_count, P.n_cells, P.scan_tmp,
-                                                        &P.state[ST_MAX_CELL], gate);
-  k_scan_top<int><<<1, 256, 0, JMD_STREAM>>>(P.scan_tmp, tiles, gate);
-  k_scan_apply<int, int><<<tiles, 256, 0, JMD_STREAM>>>(P.cell_count, P.n_cells, P.scan_tmp,
-                                                        P.cell_start, gate);
-  k_scatter<T, DIM><<<grid_for(P.n, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
-  k_rank_sort<T, DIM><<<grid_for(P.n, 128, G * 2), 128, 0, JMD_STREAM>>>(P, gated);
-  k_inv_perm<T, DIM><<<grid_for(P.n, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
+  const int tiles = grid_for(P.n_cells, SCAN_TILE, G);
+  LAUNCH(PH_ZERO, grid_for(P.n_cells + 1, NB, G));
+  LAUNCH(PH_HASH, grid_for(P.n, NB, G));
+  LAUNCH(PH_SCAN1, tiles);
+  LAUNCH(PH_SCAN2, 1);
+  LAUNCH(PH_SCAN3, tiles);
+  LAUNCH(PH_SCATTER, grid_for(P.n, NB, G));
+  LAUNCH(PH_RANK, grid_for(P.n, NB, G * 2));
+  LAUNCH(PH_INVPERM, grid_for(P.n, NB, G));
 }
 
 template <typename T, int DIM>
-__host__ __device__ void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
-  k_build_reset<T, DIM><<<1, 1, 0, JMD_STREAM>>>(P, gated);
-  if (P.use_cells) {
-#if JMD_BUILD_WARP_PER_CELL
-    int g = grid_for(P.n_cells, BUILD_WARPS, JMD_SM_COUNT * 16);
-    k_build_cells<T, DIM><<<g, BUILD_WARPS * 32, build_smem_bytes<T, DIM>(), JMD_STREAM>>>(P, gated);
-#else
-    int g = (P.n + TPA_BLOCK - 1) / TPA_BLOCK;
-    if (g < 1) g = 1;
-    if (P.format == JMD_ORDERED_SPARSE)
-      k_build_cells_tpa<T, DIM, true><<<g, TPA_BLOCK, 0, JMD_STREAM>>>(P, gated);
-    else
-      k_build_cells_tpa<T, DIM, false><<<g, TPA_BLOCK, 0, JMD_STREAM>>>(P, gated);
-#endif
-  } else {
-    k_build_all_pairs<T, DIM><<<grid_for((long long)P.n * 32, 128, JMD_SM_COUNT * 16), 128, 0, JMD_STREAM>>>(P, gated);
-  }
+void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+  LAUNCH(PH_BUILD_RESET, 1);
+  if (P.use_cells) LAUNCH_SCAN(grid_for(P.n, NB, 1 << 30));
+  else LAUNCH_SCAN(grid_for((long long)P.n * 32, NB, JMD_SM_COUNT * 16));
 }
 
 template <typename T, int DIM>
-__host__ __device__ void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   const int G = JMD_SM_COUNT * 8;
-  const long long* gate = gated ? &P.state[ST_REBUILD] : nullptr;
   if (P.format != JMD_DENSE) {
-    int tiles = (int)(((long long)P.n + SCAN_TILE - 1) / SCAN_TILE);
-    k_sparse_counts<T, DIM><<<grid_for(P.n, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
-    long long* tile_sums = (long long*)P.scan_tmp;   // free again here; host sizes it for n/2048 int64
-    k_scan_tiles<int, long long><<<tiles, 256, 0, JMD_STREAM>>>(P.tmp_ids, P.n, tile_sums, nullptr, gate);
-    k_scan_top<long long><<<1, 256, 0, JMD_STREAM>>>(tile_sums, tiles, gate);
-    k_scan_apply<int, long long><<<tiles, 256, 0, JMD_STREAM>>>(P.tmp_ids, P.n, tile_sums, P.offsets, gate);
+    const int tiles = grid_for(P.n, SCAN_TILE, G);
+    LAUNCH(PH_SP_COUNTS, grid_for(P.n, NB, G));
+    LAUNCH(PH_SP_SCAN1, tiles);
+    LAUNCH(PH_SP_SCAN2, 1);
+    LAUNCH(PH_SP_SCAN3, tiles);
   }
-  k_export<T, DIM><<<grid_for((long long)P.n * 32, 128, JMD_SM_COUNT * 16), 128, 0, JMD_STREAM>>>(P, gated);
-  if (P.format != JMD_DENSE)
-    k_sparse_pad<T, DIM><<<grid_for(P.max_occupancy / 4 + 1, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
-  k_finalize<T, DIM><<<grid_for((long long)P.n * DIM, 256, G), 256, 0, JMD_STREAM>>>(P, gated);
+  k_nbr_export<T, DIM><<<grid_for((long long)P.n, NB, 1 << 30), NB, 0, stream>>>(P, gated);
+  if (P.format != JMD_DENSE) LAUNCH(PH_SP_PAD, grid_for(P.max_occupancy / 4 + 1, NB, G));
+  LAUNCH(PH_FINALIZE, grid_for((long long)P.n * DIM, NB, G));
 }
 
-// Skin predicate (partition.py:1146-1154).  The last block to finish latches
-// the decision into state[REBUILD]; in tail_launch mode it also enqueues the
-// whole rebuild from the device (CUDA dynamic parallelism, tail-launch stream),
-// which runs before the next kernel of the host stream starts.
+// Skin predicate alone (gated mode): the last block latches the decision.
 template <typename T, int DIM>
-__global__ void __launch_bounds__(256) k_skin(NbrP<T, DIM> P) {
-  bool moved = false;
-  int stride = gridDim.x * blockDim.x;
-  if (!P.always_rebuild) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-      T a[DIM], b[DIM];
-#pragma unroll
-      for (int k = 0; k < DIM; ++k) { a[k] = P.position[(size_t)i * DIM + k]; b[k] = P.ref[(size_t)i * DIM + k]; }
-      T d2 = dist2_exact<T, DIM>(P.sp, a, b);
-      moved = moved || (d2 > P.threshold_sq);
-    }
-  }
-  int any = __syncthreads_or(moved ? 1 : 0);
+__global__ void __launch_bounds__(NB) k_skin(NbrP<T, DIM> P) {
+  const bool moved = ph_skin(P);
+  const int any = __syncthreads_or(moved ? 1 : 0);
   if (threadIdx.x == 0) {
     if (any) atomicOr((unsigned long long*)&P.state[ST_PENDING], 1ull);
     __threadfence();
@@ -743,16 +746,84 @@ __global__ void __launch_bounds__(256) k_skin(NbrP<T, DIM> P) {
       long long reb = (atomicExch((unsigned long long*)&P.state[ST_PENDING], 0ull) != 0ull) || P.always_rebuild;
       P.state[ST_REBUILD] = reb;
       P.state[ST_TICKET] = 0;
-      if (reb && P.tail_launch) {
-        launch_bin<T, DIM>(P, 0, 0);
-        launch_build<T, DIM>(P, 0, 0);
-        launch_export<T, DIM>(P, 0, 0);
-      }
     }
   }
 }
 
-// ---- host side ---------------------------------------------------------------------
+// NeighborList.update(), part A (cooperative, persistent): skin predicate; when
+// it fires the same kernel bins and sorts the atoms with grid-wide barriers
+// between the phases.  Part B is the stencil scan as an ordinary (gated) launch
+// so it runs at one thread per atom and full occupancy; part C (k_update_c)
+// exports.  On the common no-rebuild step A returns after the predicate and B,
+// C are two empty launches.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(NB, 4) k_update(NbrP<T, DIM> P) {
+  __shared__ Smem sm;
+  unsigned int* bar = reinterpret_cast<unsigned int*>(&P.state[ST_BARRIER]);
+  unsigned int target = 0;
+  const bool moved = ph_skin(P);
+  const int any = __syncthreads_or(moved ? 1 : 0);
+  if (threadIdx.x == 0 && any) atomicOr((unsigned long long*)&P.state[ST_PENDING], 1ull);
+  grid_sync(bar, target);
+  const bool rebuild = __ldcg(&P.state[ST_PENDING]) != 0 || P.always_rebuild;
+  if (gtid() == 0) P.state[ST_REBUILD] = rebuild ? 1 : 0;
+  if (!rebuild) { grid_exit(bar); return; }       // uniform over the whole grid
+  if (P.use_cells) {
+    ph_zero(P);
+    grid_sync(bar, target);
+    if (gtid() == 0) P.state[ST_PENDING] = 0;    // everyone has read it
+    ph_hash(P);
+    grid_sync(bar, target);
+    ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, &P.state[ST_MAX_CELL], sm);
+    grid_sync(bar, target);
+    ph_scan_top<int>(P.scan_tmp, P.n_cells, sm);
+    grid_sync(bar, target);
+    ph_scan_apply<int, int>(P.cell_count, P.n_cells, P.scan_tmp, P.cell_start, sm);
+    grid_sync(bar, target);
+    ph_scatter(P);
+    grid_sync(bar, target);
+    ph_rank_sort(P);
+    ph_build_reset(P);
+    grid_sync(bar, target);
+    ph_inv_perm(P);
+  } else {
+    grid_sync(bar, target);
+    if (gtid() == 0) P.state[ST_PENDING] = 0;
+    ph_identity_sort(P);
+    ph_build_reset(P);
+  }
+  grid_exit(bar);
+}
+
+// part C: sparse offsets (needs a scan, hence barriers) + export + error bits.
+// Dense needs no barrier and is launched with one thread per atom instead.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(NB, 4) k_update_c(NbrP<T, DIM> P) {
+  if (P.state[ST_REBUILD] == 0) return;
+  __shared__ Smem sm;
+  if (P.format != JMD_DENSE) {
+    unsigned int* bar = reinterpret_cast<unsigned int*>(&P.state[ST_BARRIER]);
+    unsigned int target = 0;
+    long long* sp_sums = (long long*)P.scan_tmp;
+    ph_sparse_counts(P);
+    grid_sync(bar, target);
+    ph_scan_tiles<int, long long>(P.tmp_ids, P.n, sp_sums, nullptr, sm);
+    grid_sync(bar, target);
+    ph_scan_top<long long>(sp_sums, P.n, sm);
+    grid_sync(bar, target);
+    ph_scan_apply<int, long long>(P.tmp_ids, P.n, sp_sums, P.offsets, sm);
+    grid_sync(bar, target);
+    ph_export(P, sm);
+    ph_sparse_pad(P);
+    ph_finalize(P);
+    grid_exit(bar);
+  } else {
+    ph_export(P, sm);
+    ph_finalize(P);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------
 
 template <typename T, int DIM>
 int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
@@ -761,7 +832,7 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   P.always_rebuild = nb->always_rebuild; P.n_cells = nb->n_cells; P.cell_capacity = nb->cell_capacity;
   P.m_int = nb->m_int;
   for (int k = 0; k < 3; ++k) P.cps[k] = nb->cps[k] > 0 ? nb->cps[k] : 1;
-  P.count_only = 0; P.tail_launch = 0;
+  P.count_only = 0;
   P.n_pad = nb->n_pad; P.max_occupancy = nb->max_occupancy;
   for (int k = 0; k < DIM; ++k) P.cell_size[k] = (T)nb->cell_size[k];
   P.cutoff_sq = (T)nb->cutoff_sq; P.threshold_sq = (T)nb->threshold_sq;
@@ -801,15 +872,40 @@ int dispatch(const jmd_nbr_t* nb, F&& f) {
   return JMD_EINVAL;
 }
 
+// one co-resident wave of blocks of a persistent kernel on the current device
+template <typename K>
+int coop_grid(K kernel, int* cached /*[64]*/, int* grid) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 64 && cached[dev] > 0) { *grid = cached[dev]; return 0; }
+  int per_sm = 0, sms = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NB, 0);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (per_sm < 1) return JMD_EINVAL;
+  *grid = per_sm * sms;
+  if (dev < 64) cached[dev] = *grid;
+  return 0;
+}
+
 template <typename T, int DIM>
-int ensure_smem() {
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(k_build_cells<T, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)build_smem_bytes<T, DIM>());
-    if (e != cudaSuccess) return (int)e;
-    done = true;
+int launch_update(NbrP<T, DIM>& P, cudaStream_t stream) {
+  static int cache_a[64] = {0}, cache_c[64] = {0};
+  int grid = 0, rc;
+  if ((rc = coop_grid(k_update<T, DIM>, cache_a, &grid))) return rc;
+  k_update<T, DIM><<<grid, NB, 0, stream>>>(P);
+  const int gated = 1;
+  if (P.use_cells) LAUNCH_SCAN(grid_for(P.n, NB, 1 << 30));
+  else LAUNCH_SCAN(grid_for((long long)P.n * 32, NB, JMD_SM_COUNT * 16));
+  if (P.format == JMD_DENSE) {
+    k_update_c<T, DIM><<<grid_for(P.n, NB, 1 << 30), NB, 0, stream>>>(P);
+  } else {
+    if ((rc = coop_grid(k_update_c<T, DIM>, cache_c, &grid))) return rc;
+    k_update_c<T, DIM><<<grid, NB, 0, stream>>>(P);
   }
+  JMD_LAUNCH_CHECK();
   return 0;
 }
 
@@ -817,81 +913,89 @@ int ensure_smem() {
 
 extern "C" {
 
-int jmd_nbr_skin_check(const jmd_nbr_t* nb, const void* position, int tail_launch, void* stream) {
+int jmd_nbr_update(const jmd_nbr_t* nb, const void* position, void* stream) {
   return dispatch(nb, [&](auto t, auto d) -> int {
     using T = decltype(t);
     constexpr int DIM = decltype(d)::value;
     NbrP<T, DIM> P;
     int rc = fill(P, nb, position);
     if (rc) return rc;
-    P.tail_launch = tail_launch;
-    if (tail_launch && (rc = ensure_smem<T, DIM>())) return rc;
-    k_skin<T, DIM><<<grid_for(P.n, 256, JMD_SM_COUNT * 4), 256, 0, (cudaStream_t)stream>>>(P);
+    return launch_update<T, DIM>(P, (cudaStream_t)stream);
+  });
+}
+
+int jmd_nbr_skin_check(const jmd_nbr_t* nb, const void* position, void* stream) {
+  return dispatch(nb, [&](auto t, auto d) -> int {
+    using T = decltype(t);
+    constexpr int DIM = decltype(d)::value;
+    NbrP<T, DIM> P;
+    int rc = fill(P, nb, position);
+    if (rc) return rc;
+    k_skin<T, DIM><<<grid_for(P.n, NB, JMD_SM_COUNT * 4), NB, 0, (cudaStream_t)stream>>>(P);
     JMD_LAUNCH_CHECK();
     return 0;
   });
 }
 
-int jmd_nbr_bin(const jmd_nbr_t* nb, const void* position, int gated, void* stream) {
+int jmd_nbr_bin(const jmd_nbr_t* nb, const void* position, int gated, void* stream_) {
   return dispatch(nb, [&](auto t, auto d) -> int {
     using T = decltype(t);
     constexpr int DIM = decltype(d)::value;
     NbrP<T, DIM> P;
     int rc = fill(P, nb, position);
     if (rc) return rc;
-    launch_bin<T, DIM>(P, gated, (cudaStream_t)stream);
+    launch_bin<T, DIM>(P, gated, (cudaStream_t)stream_);
     JMD_LAUNCH_CHECK();
     return 0;
   });
 }
 
-int jmd_nbr_build(const jmd_nbr_t* nb, const void* position, int count_only, int gated, void* stream) {
+int jmd_nbr_build(const jmd_nbr_t* nb, const void* position, int count_only, int gated, void* stream_) {
   return dispatch(nb, [&](auto t, auto d) -> int {
     using T = decltype(t);
     constexpr int DIM = decltype(d)::value;
     NbrP<T, DIM> P;
     int rc = fill(P, nb, position);
     if (rc) return rc;
-    if ((rc = ensure_smem<T, DIM>())) return rc;
     P.count_only = count_only;
-    launch_build<T, DIM>(P, gated, (cudaStream_t)stream);
+    launch_build<T, DIM>(P, gated, (cudaStream_t)stream_);
     JMD_LAUNCH_CHECK();
     return 0;
   });
 }
 
-int jmd_nbr_export(const jmd_nbr_t* nb, const void* position, int gated, void* stream) {
+int jmd_nbr_export(const jmd_nbr_t* nb, const void* position, int gated, void* stream_) {
   return dispatch(nb, [&](auto t, auto d) -> int {
     using T = decltype(t);
     constexpr int DIM = decltype(d)::value;
     NbrP<T, DIM> P;
     int rc = fill(P, nb, position);
     if (rc) return rc;
-    launch_export<T, DIM>(P, gated, (cudaStream_t)stream);
+    launch_export<T, DIM>(P, gated, (cudaStream_t)stream_);
     JMD_LAUNCH_CHECK();
     return 0;
   });
 }
 
-int jmd_nbr_pack(const jmd_nbr_t* nb, const void* position, void* stream) {
+int jmd_nbr_pack(const jmd_nbr_t* nb, const void* position, void* stream_) {
   return dispatch(nb, [&](auto t, auto d) -> int {
     using T = decltype(t);
     constexpr int DIM = decltype(d)::value;
     NbrP<T, DIM> P;
     int rc = fill(P, nb, position);
     if (rc) return rc;
-    k_pack<T, DIM><<<grid_for(P.n, 256, JMD_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(P);
+    k_phase<T, DIM, PH_PACK><<<grid_for(P.n, NB, JMD_SM_COUNT * 8), NB, 0, (cudaStream_t)stream_>>>(P, 0);
     JMD_LAUNCH_CHECK();
     return 0;
   });
 }
 
-int jmd_nbr_state_host(const jmd_nbr_t* nb, int64_t* out, void* stream) {
+int jmd_nbr_state_host(const jmd_nbr_t* nb, int64_t* out, void* stream_) {
   if (!nb || !out) return JMD_EINVAL;
   cudaError_t e = cudaMemcpyAsync(out, nb->state, sizeof(int64_t) * JMD_ST_COUNT, cudaMemcpyDeviceToHost,
-                                  (cudaStream_t)stream);
+                                  (cudaStream_t)stream_);
   if (e != cudaSuccess) return (int)e;
-  e = cudaStreamSynchronize((cudaStream_t)stream);
+  e = cudaStreamSynchronize((cudaStream_t)stream_);
   return (int)e;
 }
 

@@ -55,71 +55,99 @@ struct PairP {
   const int* species;
 };
 
-template <typename T>
-__device__ __forceinline__ T fast_rcp(T x) { return T(1) / x; }
+// read-only (non-coherent) 16/32-byte position gathers
+__device__ __forceinline__ float4 ld_pos(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ double4 ld_pos(const double4* p) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// 1/x: MUFU.RCP + one Newton step in f32 (~1 ulp, branch-free); IEEE in f64.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * (2.0f - x * y);
+}
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * (1.5f - 0.5f * x * y * y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
 
 // U, (dU/dr)/r, dU/dsigma, dU/depsilon of the (switched) potential at r2.
+// Written select-style (no data-dependent branches on the Lennard-Jones path)
+// so the unrolled neighbour loop stays one basic block and its loads pipeline.
 template <typename T, int POT, bool WANT_E>
 __device__ __forceinline__ void pair_eval(int has_cutoff, T r2, T sigma, T eps, T alpha, T ro2, T rc2,
                                           T inv_denom, T& u, T& du_r, T& dus, T& due) {
-  u = T(0); du_r = T(0); dus = T(0); due = T(0);
-  if (!(r2 > T(0))) {
-    // reference: distance() has zero gradient at 0 (util.safe_mask, space.py:246);
-    // LJ / Morse energies go through nan_to_num.
-    if (POT == JMD_POT_SOFT_SPHERE && WANT_E) { u = eps / alpha; due = T(1) / alpha; }
-    if (POT == JMD_POT_MORSE && WANT_E) {
-      T m = exp(alpha * sigma);
-      u = eps * (T(1) - m) * (T(1) - m) - eps;
-      due = (T(1) - m) * (T(1) - m) - T(1);
-    }
-    return;
-  }
+  dus = T(0); due = T(0);
+  // reference: distance() has zero gradient at r = 0 (util.safe_mask, space.py:246)
+  const bool pos = r2 > T(0);
+  bool live = pos;
   if (POT == JMD_POT_LJ) {
-    if (has_cutoff && !(r2 < rc2)) return;
-    T ir2 = T(1) / r2;
-    T x2 = sigma * sigma * ir2;
-    T x6 = x2 * x2 * x2;
-    T x12 = x6 * x6;
-    u = T(4) * eps * (x12 - x6);
-    du_r = T(-24) * eps * (T(2) * x12 - x6) * ir2;
+    if (has_cutoff) live = live && (r2 < rc2);
+    const T ir2 = fast_rcp(r2);
+    const T x2 = sigma * sigma * ir2;
+    const T x6 = x2 * x2 * x2;
+    const T x12 = x6 * x6;
+    const T e4 = T(4) * eps;
+    u = e4 * (x12 - x6);
+    du_r = T(-6) * e4 * (T(2) * x12 - x6) * ir2;
     if (WANT_E) {
-      dus = T(4) * eps * (T(12) * x12 - T(6) * x6) / sigma;
+      dus = e4 * (T(12) * x12 - T(6) * x6) / sigma;
       due = T(4) * (x12 - x6);
     }
   } else if (POT == JMD_POT_SOFT_SPHERE) {
-    T r = sqrt(r2);
-    T x = r / sigma;
-    if (!(x < T(1))) return;
-    T b = T(1) - x;
-    T bm1 = (alpha == T(2)) ? b : ((alpha == T(2.5)) ? b * sqrt(b) : pow(b, alpha - T(1)));
+    const T ir = fast_rsqrt(r2);
+    const T r = r2 * ir;
+    const T x = r / sigma;
+    live = live && (x < T(1));
+    const T b = live ? T(1) - x : T(0);
+    const T bm1 = (alpha == T(2)) ? b : ((alpha == T(2.5)) ? b * sqrt(b) : pow(b, alpha - T(1)));
     u = eps / alpha * bm1 * b;
-    du_r = -(eps / sigma) * bm1 / r;
+    du_r = -(eps / sigma) * bm1 * ir;
     if (WANT_E) {
       dus = eps * bm1 * r / (sigma * sigma);
       due = bm1 * b / alpha;
+      if (!pos) { u = eps / alpha; due = T(1) / alpha; dus = T(0); }   // r = 0: U = eps/alpha
     }
   } else {
-    if (has_cutoff && !(r2 < rc2)) return;
-    T r = sqrt(r2);
-    T m = exp(-alpha * (r - sigma));
-    T om = T(1) - m;
+    if (has_cutoff) live = live && (r2 < rc2);
+    const T ir = fast_rsqrt(r2);
+    const T r = pos ? r2 * ir : T(0);
+    const T m = exp(-alpha * (r - sigma));
+    const T om = T(1) - m;
     u = eps * om * om - eps;
-    T dudr = T(2) * eps * alpha * m * om;
-    du_r = dudr / r;
+    const T dudr = T(2) * eps * alpha * m * om;
+    du_r = dudr * ir;
     if (WANT_E) {
       dus = -dudr;
       due = om * om - T(1);
     }
   }
-  if (has_cutoff && r2 >= ro2) {
-    // energy.py:562-574: S = (rc2-r2)^2 (rc2 + 2 r2 - 3 ro2) / (rc2-ro2)^3
-    T a = rc2 - r2;
-    T S = a * a * (rc2 + T(2) * r2 - T(3) * ro2) * inv_denom;
-    T dS_r = T(12) * a * (ro2 - r2) * inv_denom;        // (dS/dr)/r
+  if (has_cutoff) {
+    // energy.py:562-574: S = (rc2-r2)^2 (rc2 + 2 r2 - 3 ro2) / (rc2-ro2)^3 on [ro, rc)
+    const bool sw = r2 >= ro2;
+    const T a = rc2 - r2;
+    const T S = sw ? a * a * (rc2 + T(2) * r2 - T(3) * ro2) * inv_denom : T(1);
+    const T dS_r = sw ? T(12) * a * (ro2 - r2) * inv_denom : T(0);        // (dS/dr)/r
     du_r = dS_r * u + S * du_r;
     u = S * u;
     dus = S * dus;
     due = S * due;
+  }
+  du_r = live ? du_r : T(0);
+  if (POT == JMD_POT_LJ) {
+    u = live ? u : T(0); dus = live ? dus : T(0); due = live ? due : T(0);
+  } else if (POT == JMD_POT_SOFT_SPHERE) {
+    if (pos && !live) { u = T(0); dus = T(0); due = T(0); }
+  } else {
+    // Morse at r = 0 keeps its (finite) energy; beyond the cutoff everything is 0
+    if (has_cutoff && !(r2 < rc2)) { u = T(0); dus = T(0); due = T(0); }
+    if (!pos) dus = T(0);
   }
 }
 
@@ -160,8 +188,8 @@ __global__ void __launch_bounds__(PAIR_BLOCK) k_pair_force(PairP<T, DIM> Q) {
     const T sig0 = Q.scalar[0], eps0 = Q.scalar[1], alp0 = Q.scalar[2];
 #pragma unroll 4
     for (int k = 0; k < cnt; ++k) {
-      const int j = __ldg(col + (size_t)k * Q.n_pad);
-      const V4 pj = Q.pos_sorted[j];
+      const int j = __ldcs(col + (size_t)k * Q.n_pad);   // streamed once: keep it out of L1
+      const V4 pj = ld_pos(&Q.pos_sorted[j]);
       T d[3];
       d[0] = Q.sp.disp_fast(pi.x, pj.x, 0);
       d[1] = Q.sp.disp_fast(pi.y, pj.y, 1);

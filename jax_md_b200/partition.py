@@ -97,7 +97,7 @@ class Workspace:
     self.c = _lib.NbrT()
     self.t = {}          # name -> tensor (keeps buffers alive)
     self.species = None
-    self.update_mode = 'tail'   # 'tail' | 'gated'
+    self.update_mode = 'fused'   # 'fused' (one cooperative kernel) | 'gated'
 
   def buf(self, name, shape, dtype, fill=None):
     if fill is None:
@@ -334,6 +334,9 @@ def neighbor_list(displacement_or_metric,
       cl_capacity = int(max_cell * capacity_multiplier) + extra_capacity
       c.cell_capacity = cl_capacity
       width = 3 ** dim * cl_capacity
+      # cells are stored in the reference's slot order, which depends on the
+      # capacity (slot = rank mod capacity, partition.py:441): bin again.
+      _lib.call('jmd_nbr_bin', ws.ref(), pp, 0, st)
     else:
       width = N
     # -- occupancy pass (partition.py:1083-1088)
@@ -391,10 +394,10 @@ def neighbor_list(displacement_or_metric,
       raise ValueError('position shape/dtype differs from the allocated list')
     position = position.contiguous()
     st, pp = _lib.stream(), _lib.ptr(position)
-    if ws.update_mode == 'tail':
-      _lib.call('jmd_nbr_skin_check', ws.ref(), pp, 1, st)
+    if ws.update_mode == 'fused':
+      _lib.call('jmd_nbr_update', ws.ref(), pp, st)
     else:
-      _lib.call('jmd_nbr_skin_check', ws.ref(), pp, 0, st)
+      _lib.call('jmd_nbr_skin_check', ws.ref(), pp, st)
       _lib.call('jmd_nbr_bin', ws.ref(), pp, 1, st)
       _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 1, st)
       _lib.call('jmd_nbr_export', ws.ref(), pp, 1, st)

@@ -246,7 +246,7 @@ def test_nve_trajectory_matches_oracle(dtype, fmt):
 
 
 def test_nve_energy_conservation_and_rebuilds():
-  """NVE drift over 2000 steps at T*=1 with rebuilds through the tail-launch
+  """NVE drift over 2000 steps at T*=1 with rebuilds through the fused update
   path (f32): |dE|/N below 2e-4 (stated bound), no overflow."""
   jmd = _jmd()
   R, L = util.fcc(10, dtype=np.float32)

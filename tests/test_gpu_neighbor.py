@@ -145,10 +145,10 @@ def test_cell_list_overflow_flag():
 
 
 @pytest.mark.parametrize('fmt', FORMATS)
-@pytest.mark.parametrize('mode', ['tail', 'gated'])
+@pytest.mark.parametrize('mode', ['fused', 'gated'])
 def test_update_semantics(fmt, mode):
   """partition.py:1119-1154: no rebuild below the skin threshold, rebuild above
-  it (strict >), sticky error bits; device tail-launch and gated modes agree."""
+  it (strict >), sticky error bits; fused cooperative kernel and gated modes agree."""
   R, L = util.fcc(8, dtype=np.float32)
   R = util.jitter(R, L, 0.03)
   nf_o, nf_g = _build_both(R, L, np.float32(2.5), np.float32(0.3), fmt)
