@@ -5,12 +5,15 @@
 // compaction, skin predicate under lax.cond).  Every stage is a grid-stride
 // "phase" (a __device__ function); the phases are used two ways:
 //
-//   k_update   ONE persistent cooperative kernel per NeighborList.update():
-//              phase 0 is the skin predicate (max displacement vs threshold);
-//              if no atom moved past skin/2 every block returns, otherwise the
-//              same kernel runs the whole rebuild with grid-wide barriers
-//              between phases.  This is the lax.cond of partition.py:1146 with
-//              no host round trip and no extra launches on the common path.
+//   k_update   a persistent kernel (one co-resident wave, hand-rolled grid
+//              barrier) per NeighborList.update(): phase 0 is the skin
+//              predicate (max displacement vs threshold); if no atom moved past
+//              skin/2 every block returns, otherwise the same kernel bins and
+//              sorts the atoms with grid-wide barriers between phases.  The
+//              stencil scan (k_nbr_stencil_scan) and the export (k_update_c)
+//              follow as gated launches that are empty on non-rebuild steps.
+//              This is the lax.cond of partition.py:1146 with no host round
+//              trip.
 //   k_phase<>  one ordinary kernel per phase for the host-driven allocate path
 //              (which needs occupancies on the host between stages) and for the
 //              "gated" fallback update mode.
