@@ -79,6 +79,10 @@ typedef struct {
   int32_t n_cells;
   int32_t cell_capacity;   /* reference cell_list_capacity (slot rotation, flag) */
   int32_t m_int;           /* internal row capacity (rows of `nl`) */
+  int32_t n_rows;          /* atoms [0, n_rows) own rows / forces / skin checks; the rest
+                              (ghosts of a domain decomposition) are candidates only.
+                              0 means n. */
+  int32_t no_public_idx;   /* skip the export of `idx` (distributed driver) */
   int64_t n_pad;           /* row stride of `nl` (n rounded up to 32) */
   int64_t max_occupancy;   /* public capacity: per row (Dense) / total (Sparse) */
   double cell_size[3];     /* f32 cell size, partition.py:162-163 */
@@ -143,6 +147,11 @@ int jmd_nbr_state_host(const jmd_nbr_t* nb, int64_t* out, void* stream);
 
 /* Refresh pos_sorted from user-order positions (no rebuild). */
 int jmd_nbr_pack(const jmd_nbr_t* nb, const void* position, void* stream);
+
+/* Same for atoms [first, first + count) only (ghost positions after a halo
+ * exchange). */
+int jmd_nbr_pack_range(const jmd_nbr_t* nb, const void* position, int first,
+                       int count, void* stream);
 
 /* ---- pair potentials (replaces smap.py:922-979 + energy.py:125-371,534-580) */
 
@@ -240,6 +249,22 @@ int jmd_fire_mix(int dtype, int64_t count, void* momentum, const void* force,
                  const int32_t* npos_in, int32_t* npos_out, double dt_max,
                  double n_min, double f_inc, double f_dec, double alpha_start,
                  double f_alpha, void* stream);
+
+/* ---- slab domain decomposition helpers (no reference equivalent) */
+
+/* For atoms i < n: d = (pos[i, axis] - lo) wrapped into [-L/2, L/2).  Appends i to
+ * list_a when d < thr_a and to list_b when d >= thr_b (unordered; counters[0..1]
+ * must be zeroed by the caller; entries beyond `cap` are counted, not stored).
+ * Migration uses thr_a = 0, thr_b = width; ghost selection thr_a = ghost_width,
+ * thr_b = width - ghost_width. */
+int jmd_dd_select(int dtype, int dim, int n, const void* position, int axis,
+                  double lo, double L, double thr_a, double thr_b,
+                  int32_t* list_a, int32_t* list_b, int32_t* counters, int cap,
+                  void* stream);
+
+/* dst[i, :] = src[idx[i], :] for rows of `ncomp` elements (halo / migration pack). */
+int jmd_dd_pack(int dtype, int ncomp, int n_idx, const int32_t* idx,
+                const void* src, void* dst, void* stream);
 
 const char* jmd_version(void);
 

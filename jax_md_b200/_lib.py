@@ -36,7 +36,8 @@ class NbrT(C.Structure):
       ('use_cells', C.c_int32), ('mask_self', C.c_int32),
       ('always_rebuild', C.c_int32), ('cps', C.c_int32 * 3),
       ('n_cells', C.c_int32), ('cell_capacity', C.c_int32),
-      ('m_int', C.c_int32), ('n_pad', C.c_int64), ('max_occupancy', C.c_int64),
+      ('m_int', C.c_int32), ('n_rows', C.c_int32), ('no_public_idx', C.c_int32),
+      ('n_pad', C.c_int64), ('max_occupancy', C.c_int64),
       ('cell_size', C.c_double * 3), ('cutoff_sq', C.c_double),
       ('threshold_sq', C.c_double), ('space', SpaceT),
       ('cell_count', C.c_void_p), ('cell_start', C.c_void_p),
@@ -74,6 +75,9 @@ _SIGNATURES = {
     'jmd_nbr_export': [C.POINTER(NbrT), _P, _I, _P],
     'jmd_nbr_state_host': [C.POINTER(NbrT), C.POINTER(C.c_int64), _P],
     'jmd_nbr_pack': [C.POINTER(NbrT), _P, _P],
+    'jmd_nbr_pack_range': [C.POINTER(NbrT), _P, _I, _I, _P],
+    'jmd_dd_select': [_I, _I, _I, _P, _I, _D, _D, _D, _D, _P, _P, _P, _I, _P],
+    'jmd_dd_pack': [_I, _I, _I, _P, _P, _P, _P],
     'jmd_pair_force': [C.POINTER(NbrT), C.POINTER(PairT), _P, _P, _P, _P, _P,
                        _P, _P, _I, _D, _P, _I, _P],
     'jmd_sw_force': [C.POINTER(NbrT), C.POINTER(SwT), _P, _P, _P, _P, _P, _I,

@@ -43,7 +43,7 @@ template <typename T, int DIM>
 struct NbrP {
   int n, format, use_cells, mask_self, always_rebuild, n_cells, cell_capacity, m_int;
   int cps[3];
-  int count_only, two_sided, rev_only;
+  int count_only, two_sided, rev_only, n_rows, no_public_idx;
   long long n_pad, max_occupancy;
   T cell_size[DIM];
   T cutoff_sq, threshold_sq, band, far;
@@ -125,7 +125,7 @@ template <typename T, int DIM>
 __device__ bool ph_skin(const NbrP<T, DIM>& P) {
   bool moved = false;
   if (P.always_rebuild) return true;
-  for (int i = gtid(); i < P.n; i += gthreads()) {
+  for (int i = gtid(); i < P.n_rows; i += gthreads()) {
     T a[DIM], b[DIM];
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
@@ -330,6 +330,15 @@ __device__ void ph_identity_sort(const NbrP<T, DIM>& P) {
 }
 
 template <typename T, int DIM>
+__global__ void k_pack_range(NbrP<T, DIM> P, int first, int count) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < count; g += stride) {
+    const int a = first + g;
+    P.pos_sorted[P.inv_perm[a]] = load_atom(P, a);
+  }
+}
+
+template <typename T, int DIM>
 __device__ void ph_pack(const NbrP<T, DIM>& P) {
   for (int t = gtid(); t < P.n; t += gthreads()) P.pos_sorted[t] = load_atom(P, P.perm[t]);
 }
@@ -396,10 +405,14 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
   for (int wbase = gtid() - lane; wbase < P.n; wbase += gthreads()) {
     const int slot = wbase + lane;
     long long my_k = 0, my_tot = 0;
-    if (slot < P.n) {
+    const int hid = slot < P.n ? P.perm[slot] : 0x7fffffff;
+    if (slot < P.n && hid >= P.n_rows) {      // ghost atom: candidate only, no row
+      P.cnt[slot] = 0;
+      P.cnt_lower[slot] = 0;
+    }
+    if (hid < P.n_rows) {
       const V4 hv = P.pos_sorted[slot];
       const T hp[3] = {hv.x, hv.y, hv.z};
-      const int hid = P.perm[slot];
       const int c = P.hash[hid];              // own cell (hash of this atom)
       const int cx_n = P.cps[0], cy_n = P.cps[1];
       int cc[3];
@@ -488,6 +501,10 @@ __device__ void ph_build_all_pairs(const NbrP<T, DIM>& P) {
   const int nwarps = gthreads() >> 5;
   long long wmax = 0, wtotal = 0;
   for (int i = warp; i < P.n; i += nwarps) {
+    if (i >= P.n_rows) {                        // ghost: no row (identity order: slot == id)
+      if (lane == 0) { P.cnt[i] = 0; P.cnt_lower[i] = 0; }
+      continue;
+    }
     const V4 hv = P.pos_sorted[i];
     const T hp[3] = {hv.x, hv.y, hv.z};
     int k = 0, kl = 0;
@@ -688,6 +705,7 @@ __global__ void __launch_bounds__(NB, 3) k_nbr_stencil_scan(NbrP<T, DIM> P, int 
 template <typename T, int DIM>
 __global__ void __launch_bounds__(NB, 3) k_nbr_export(NbrP<T, DIM> P, int gated) {
   if (gated && P.state[ST_REBUILD] == 0) return;
+  if (P.no_public_idx) return;
   __shared__ Smem sm;
   ph_export(P, sm);
 }
@@ -723,6 +741,10 @@ void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 template <typename T, int DIM>
 void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   const int G = JMD_SM_COUNT * 8;
+  if (P.no_public_idx) {
+    LAUNCH(PH_FINALIZE, grid_for((long long)P.n * DIM, NB, G));
+    return;
+  }
   if (P.format != JMD_DENSE) {
     const int tiles = grid_for(P.n, SCAN_TILE, G);
     LAUNCH(PH_SP_COUNTS, grid_for(P.n, NB, G));
@@ -804,6 +826,7 @@ template <typename T, int DIM>
 __global__ void __launch_bounds__(NB, 4) k_update_c(NbrP<T, DIM> P) {
   if (P.state[ST_REBUILD] == 0) return;
   __shared__ Smem sm;
+  if (P.no_public_idx) { ph_finalize(P); return; }
   if (P.format != JMD_DENSE) {
     unsigned int* bar = reinterpret_cast<unsigned int*>(&P.state[ST_BARRIER]);
     unsigned int target = 0;
@@ -836,6 +859,8 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   P.m_int = nb->m_int;
   for (int k = 0; k < 3; ++k) P.cps[k] = nb->cps[k] > 0 ? nb->cps[k] : 1;
   P.count_only = 0;
+  P.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
+  P.no_public_idx = nb->no_public_idx;
   P.n_pad = nb->n_pad; P.max_occupancy = nb->max_occupancy;
   for (int k = 0; k < DIM; ++k) P.cell_size[k] = (T)nb->cell_size[k];
   P.cutoff_sq = (T)nb->cutoff_sq; P.threshold_sq = (T)nb->threshold_sq;
@@ -988,6 +1013,21 @@ int jmd_nbr_pack(const jmd_nbr_t* nb, const void* position, void* stream_) {
     int rc = fill(P, nb, position);
     if (rc) return rc;
     k_phase<T, DIM, PH_PACK><<<grid_for(P.n, NB, JMD_SM_COUNT * 8), NB, 0, (cudaStream_t)stream_>>>(P, 0);
+    JMD_LAUNCH_CHECK();
+    return 0;
+  });
+}
+
+int jmd_nbr_pack_range(const jmd_nbr_t* nb, const void* position, int first, int count, void* stream_) {
+  if (count <= 0) return 0;
+  return dispatch(nb, [&](auto t, auto d) -> int {
+    using T = decltype(t);
+    constexpr int DIM = decltype(d)::value;
+    NbrP<T, DIM> P;
+    int rc = fill(P, nb, position);
+    if (rc) return rc;
+    if (first < 0 || first + count > P.n) return JMD_EINVAL;
+    k_pack_range<T, DIM><<<grid_for(count, NB, JMD_SM_COUNT * 8), NB, 0, (cudaStream_t)stream_>>>(P, first, count);
     JMD_LAUNCH_CHECK();
     return 0;
   });

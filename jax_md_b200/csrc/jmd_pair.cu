@@ -22,7 +22,7 @@ constexpr int PAIR_BLOCK = 128;
 
 template <typename T, int DIM>
 struct PairP {
-  int n, m_int;
+  int n, m_int, n_rows;
   long long n_pad;
   Space<T, DIM> sp;
   const typename Vec4<T>::type* pos_sorted;
@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(PAIR_BLOCK) k_pair_force(PairP<T, DIM> Q) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) rv[i] = 0.0;
 
-  if (t < Q.n) {
+  const int ai = t < Q.n ? Q.perm[t] : 0x7fffffff;
+  if (ai < Q.n_rows) {                      // ghosts (ids >= n_rows) have no row
     const V4 pi = Q.pos_sorted[t];
     const int cnt = min(Q.cnt[t], Q.m_int);
-    const int ai = Q.perm[t];
     const int si = (int)pi.w;
     T f[3] = {T(0), T(0), T(0)};
     T e = T(0), ds = T(0), de = T(0);
@@ -313,6 +313,7 @@ int launch_pair(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, void* e_
                 double dt_2, const void* dt_dev, bool want_e, cudaStream_t s) {
   PairP<T, DIM> Q;
   Q.n = nb->n; Q.m_int = nb->m_int; Q.n_pad = nb->n_pad;
+  Q.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
   Q.sp.init(nb->space);
   Q.pos_sorted = (const typename Vec4<T>::type*)nb->pos_sorted;
   Q.nl = nb->nl; Q.cnt = nb->cnt; Q.perm = nb->perm;

@@ -20,7 +20,7 @@ constexpr int SWB = 128;
 
 template <typename T>
 struct SwP {
-  int n, m_int;
+  int n, m_int, n_rows;
   long long n_pad;
   Space<T, 3> sp;
   const typename Vec4<T>::type* pos_sorted;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
   using V4 = typename Vec4<T>::type;
   const int t = blockIdx.x * SWB + threadIdx.x;
   double rv[5] = {0, 0, 0, 0, 0};
-  if (t < S.n) {
+  if (t < S.n && S.perm[t] < S.n_rows) {
     const V4 pi = S.pos_sorted[t];
     const int cnt = min(S.cnt[t], S.m_int);
     const int* col = S.nl + t;
@@ -181,6 +181,7 @@ int launch_sw(const jmd_nbr_t* nb, const jmd_sw_t* sw, void* force, double* red,
               cudaStream_t s) {
   SwP<T> S;
   S.n = nb->n; S.m_int = nb->m_int; S.n_pad = nb->n_pad;
+  S.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
   S.sp.init(nb->space);
   S.pos_sorted = (const typename Vec4<T>::type*)nb->pos_sorted;
   S.nl = nb->nl; S.cnt = nb->cnt; S.perm = nb->perm;

@@ -262,7 +262,7 @@ def neighbor_list(displacement_or_metric,
     # NumPy scalar against an f64 array promotes exactly.
     return float(np_dtype(x)) if isinstance(x, (float, int)) else float(x)
 
-  def _make_workspace(position, extra_capacity):
+  def _make_workspace(position, extra_capacity, n_capacity=None):
     _lib.require_cuda()
     if not isinstance(position, torch.Tensor) or not position.is_cuda:
       raise TypeError('positions must be a CUDA torch.Tensor [N, dim]')
@@ -270,7 +270,11 @@ def neighbor_list(displacement_or_metric,
     if dim not in (2, 3):
       raise ValueError(f'Cell list spatial dimension must be 2 or 3. Found {dim}.')
     np_dtype = np.float32 if position.dtype == torch.float32 else np.float64
+    # per-atom buffers can be over-allocated (domain decomposition: the local
+    # atom count changes at every rebuild; see jax_md_b200/domain.py)
+    n_buf = max(N, int(n_capacity or 0))
     ws = Workspace(N, dim, position.dtype, position.device)
+    ws.n_capacity = n_buf
     c = ws.c
     c.n, c.dtype, c.format = N, _lib.dtype_code(position.dtype), fmt_code
     c.mask_self = 1 if mask_self else 0
@@ -278,7 +282,7 @@ def neighbor_list(displacement_or_metric,
     c.cutoff_sq = _typed(cutoff_sq, np_dtype)
     c.threshold_sq = _typed(threshold_sq, np_dtype)
     c.space = space.space_struct(spec, dim, position.dtype)
-    c.n_pad = ((N + 31) // 32) * 32 if N else 32
+    c.n_pad = ((n_buf + 31) // 32) * 32 if n_buf else 32
 
     use_cells, cell_size, cps, n_cells = False, None, np.ones(3, i32), 0
     if not disable_cell_list:
@@ -298,31 +302,34 @@ def neighbor_list(displacement_or_metric,
     ws.buf('cell_count', (n_cells + 1,), i4, 0)
     ws.buf('cell_start', (n_cells + 1,), i4, 0)
     ws.buf('cell_cursor', (max(n_cells, 1),), i4, 0)
-    ws.buf('scan_tmp', (2 * (max(n_cells, N) // 2048 + 2) + 16,), i4, 0)
-    ws.buf('hash', (max(N, 1),), i4)
-    ws.buf('tmp_ids', (max(N, 1),), i4)
+    ws.buf('scan_tmp', (2 * (max(n_cells, n_buf) // 2048 + 2) + 16,), i4, 0)
+    ws.buf('hash', (max(n_buf, 1),), i4)
+    ws.buf('tmp_ids', (max(n_buf, 1),), i4)
     ws.buf('perm', (c.n_pad,), i4, 0)
-    ws.buf('inv_perm', (max(N, 1),), i4)
+    ws.buf('inv_perm', (max(n_buf, 1),), i4)
     ws.buf('pos_sorted', (c.n_pad, 4), position.dtype, 0)
     ws.buf('cnt', (c.n_pad,), i4, 0)
     ws.buf('cnt_lower', (c.n_pad,), i4, 0)
-    ws.buf('offsets', (N + 1,), torch.int64, 0)
-    ws.buf('reference_position', (N, dim), position.dtype)
+    ws.buf('offsets', (n_buf + 1,), torch.int64, 0)
+    ws.buf('reference_position', (n_buf, dim), position.dtype)
     ws.buf('error', (), torch.uint8, 0)
     ws.buf('state', (_lib.ST_COUNT,), torch.int64, 0)
     ws.cell_size_host = cell_size
     ws.use_cells = use_cells
     return ws
 
-  def allocate_fn(position, extra_capacity: int = 0, **kwargs):
+  def allocate_fn(position, extra_capacity: int = 0, n_capacity=None,
+                  n_rows=None, no_public_idx=False, **kwargs):
     """partition.py:1156-1157 -> neighbor_fn with neighbors=None (not jittable:
     reads occupancies back to the host)."""
     if 'box' in kwargs:
       raise ValueError('Neighbor list cannot accept a box keyword argument if '
                        'fractional_coordinates is not enabled.')
     position = position.contiguous()
-    ws = _make_workspace(position, extra_capacity)
+    ws = _make_workspace(position, extra_capacity, n_capacity)
     c, N, dim = ws.c, ws.n, ws.dim
+    c.n_rows = int(n_rows) if n_rows else 0
+    c.no_public_idx = 1 if no_public_idx else 0
     st, pp = _lib.stream(), _lib.ptr(position)
     # -- cell capacity (partition.py:243-250, 369-373)
     c.cell_capacity = 1
@@ -369,7 +376,9 @@ def neighbor_list(displacement_or_metric,
     c.max_occupancy = max_occupancy
     c.m_int = max(m_int, 1)
     ws.buf('nl', (c.m_int, c.n_pad), torch.int32)
-    if sparse:
+    if no_public_idx:
+      idx = ws.buf('idx', (0,), torch.int32)
+    elif sparse:
       idx = ws.buf('idx', (2, max_occupancy), torch.int32, N)
     else:
       idx = ws.buf('idx', (N, max_occupancy), torch.int32, N)
@@ -377,7 +386,8 @@ def neighbor_list(displacement_or_metric,
       c.idx = None
     _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 0, st)
     _lib.call('jmd_nbr_export', ws.ref(), pp, 0, st)
-    return NeighborList(idx, ws.t['reference_position'],
+    ref = ws.t['reference_position']
+    return NeighborList(idx, ref if n_capacity is None else ref[:N],
                         PartitionError(ws.t['error']), cl_capacity,
                         max_occupancy, format, ws.cell_size_host,
                         'cell_list' if ws.use_cells else None, update_fn, ws)
