@@ -90,9 +90,9 @@ typedef struct {
   double threshold_sq;     /* (dr_threshold / 2)^2, partition.py:901 */
   jmd_space_t space;       /* metric of the user's displacement function */
   /* device buffers */
-  int32_t* cell_count;     /* [n_cells + 1] */
-  int32_t* cell_start;     /* [n_cells + 1] exclusive scan of cell_count */
-  int32_t* cell_cursor;    /* [n_cells] */
+  int32_t* cell_count;     /* [n_fine_cells + 1] */
+  int32_t* cell_start;     /* [n_fine_cells + 1] exclusive scan of cell_count */
+  int32_t* cell_cursor;    /* [n_fine_cells] */
   int32_t* scan_tmp;       /* [>= n_cells / 1024 + 2] */
   int32_t* hash;           /* [n] cell hash per atom (user order) */
   int32_t* tmp_ids;        /* [n] */
@@ -108,6 +108,15 @@ typedef struct {
   uint8_t* error;          /* PartitionError.code */
   int64_t* state;          /* [JMD_ST_COUNT] */
   const int32_t* species;  /* [n] or NULL (copied into pos_sorted.w) */
+  /* internal search grid: the reference cells split `fine` times per side.  The
+   * reference grid above only feeds cell_list_capacity / CELL_LIST_OVERFLOW;
+   * cell_count / cell_start / cell_cursor are sized for the fine grid. */
+  int32_t fine_cps[3];     /* fine cells per side */
+  int32_t n_fine_cells;
+  int32_t stencil_w;       /* stencil half width in fine cells (1, 2 or 3) */
+  int32_t _pad2;
+  double fine_cell_size[3];
+  int32_t* ref_count;      /* [n_cells] atoms per REFERENCE cell */
 } jmd_nbr_t;
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */

@@ -46,7 +46,10 @@ class NbrT(C.Structure):
       ('inv_perm', C.c_void_p), ('pos_sorted', C.c_void_p), ('nl', C.c_void_p),
       ('cnt', C.c_void_p), ('cnt_lower', C.c_void_p), ('offsets', C.c_void_p),
       ('reference_position', C.c_void_p), ('idx', C.c_void_p),
-      ('error', C.c_void_p), ('state', C.c_void_p), ('species', C.c_void_p)]
+      ('error', C.c_void_p), ('state', C.c_void_p), ('species', C.c_void_p),
+      ('fine_cps', C.c_int32 * 3), ('n_fine_cells', C.c_int32),
+      ('stencil_w', C.c_int32), ('_pad2', C.c_int32),
+      ('fine_cell_size', C.c_double * 3), ('ref_count', C.c_void_p)]
 
 
 class PairT(C.Structure):

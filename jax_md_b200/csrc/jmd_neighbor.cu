@@ -42,13 +42,15 @@ constexpr int RANK_LIMIT = 4096;  // cells above this keep arrival order
 template <typename T, int DIM>
 struct NbrP {
   int n, format, use_cells, mask_self, always_rebuild, n_cells, cell_capacity, m_int;
-  int cps[3];
+  int cps[3];          // INTERNAL (fine) search grid
+  int ref_cps[3], n_ref_cells, sw;   // reference grid (capacity flag only), stencil half width
   int count_only, two_sided, rev_only, n_rows, no_public_idx;
   long long n_pad, max_occupancy;
-  T cell_size[DIM];
+  T cell_size[DIM];    // fine cell size
+  T ref_cell_size[DIM];
   T cutoff_sq, threshold_sq, band, far;
   Space<T, DIM> sp;
-  int *cell_count, *cell_start, *cell_cursor, *scan_tmp, *hash, *tmp_ids, *perm, *inv_perm;
+  int *cell_count, *cell_start, *cell_cursor, *scan_tmp, *hash, *tmp_ids, *perm, *inv_perm, *ref_count;
   typename Vec4<T>::type* pos_sorted;
   int* nl;
   int* cnt;
@@ -144,17 +146,20 @@ __device__ void ph_zero(const NbrP<T, DIM>& P) {
   for (int c = gtid(); c <= P.n_cells; c += gthreads()) {
     P.cell_count[c] = 0;
     if (c < P.n_cells) P.cell_cursor[c] = 0;
+    if (c < P.n_ref_cells) P.ref_count[c] = 0;
   }
   if (gtid() == 0) P.state[ST_MAX_CELL] = 0;
 }
 
 // partition.py:421-423: int32(R / cell_size) (truncation), mod cells_per_side,
-// hash = x + y*cx + z*cx*cy.
+// hash = x + y*cx + z*cx*cy.  The reference grid only feeds the occupancy
+// histogram behind cell_list_capacity / CELL_LIST_OVERFLOW; atoms are binned on
+// the finer internal grid (same formula, cell size / fine).
 template <typename T, int DIM>
 __device__ void ph_hash(const NbrP<T, DIM>& P) {
   for (int i = gtid(); i < P.n; i += gthreads()) {
     const T* r = P.position + (size_t)i * DIM;
-    int h = 0, mult = 1;
+    int h = 0, mult = 1, hr = 0, multr = 1;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
       int ci = (int)div_rn(r[k], P.cell_size[k]);
@@ -162,10 +167,27 @@ __device__ void ph_hash(const NbrP<T, DIM>& P) {
       if (ci < 0) ci += P.cps[k];
       h += ci * mult;
       mult *= P.cps[k];
+      int cr = (int)div_rn(r[k], P.ref_cell_size[k]);
+      cr %= P.ref_cps[k];
+      if (cr < 0) cr += P.ref_cps[k];
+      hr += cr * multr;
+      multr *= P.ref_cps[k];
     }
     P.hash[i] = h;
     atomicAdd(&P.cell_count[h], 1);
+    atomicAdd(&P.ref_count[hr], 1);
   }
+}
+
+// max occupancy of a REFERENCE cell (partition.py:243-250, 458-460)
+template <typename T, int DIM>
+__device__ void ph_ref_max(const NbrP<T, DIM>& P) {
+  int mx = 0;
+  for (int c = gtid(); c < P.n_ref_cells; c += gthreads()) mx = max(mx, P.ref_count[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0)
+    atomicMax((unsigned long long*)&P.state[ST_MAX_CELL], (unsigned long long)mx);
 }
 
 // exclusive scan of one value per thread across the block
@@ -278,11 +300,14 @@ __device__ void ph_scatter(const NbrP<T, DIM>& P) {
 // (partition.py:432: arrival order == id order) and then places sorted rank r
 // in slot `r mod cell_capacity` (partition.py:441), so reading a cell in slot
 // order yields the arrival order ROTATED by r0 = cap - start % cap (when that
-// is < count).  We store each cell directly in that slot order, so the stencil
-// scan walks plain contiguous ranges and emits candidates in reference order.
+// is < count).  When the search grid IS the reference grid (fine == 1) we store
+// each cell directly in that slot order, so the stencil scan walks plain
+// contiguous ranges and emits candidates in the reference's order; on a finer
+// grid the order is ascending id (sets stay identical, order is ours).
 template <typename T, int DIM>
 __device__ void ph_rank_sort(const NbrP<T, DIM>& P) {
   const int cap = P.cell_capacity > 0 ? P.cell_capacity : 1;
+  const bool rotate = P.n_cells == P.n_ref_cells;
   for (int i = gtid(); i < P.n; i += gthreads()) {
     int h = P.hash[i];
     int s = P.cell_start[h];
@@ -294,11 +319,13 @@ __device__ void ph_rank_sort(const NbrP<T, DIM>& P) {
     } else {
       rank = P.inv_perm[i] - s;
     }
-    const int room = cap - s % cap;
-    const int r0 = room < c ? room : 0;
-    int q = rank - r0;
-    q = q < 0 ? q + c : q;
-    int dst = s + q;
+    if (rotate) {
+      const int room = cap - s % cap;
+      const int r0 = room < c ? room : 0;
+      rank -= r0;
+      rank = rank < 0 ? rank + c : rank;
+    }
+    int dst = s + rank;
     P.perm[dst] = i;
     P.pos_sorted[dst] = load_atom(P, i);
   }
@@ -381,24 +408,31 @@ __device__ __forceinline__ void publish_counts(long long* state, long long my_k,
 }
 
 // Thread-per-atom stencil scan.  A thread owns sorted slot `slot` and walks the
-// 3^d stencil cells of its own cell in reference order (first coordinate
-// slowest, partition.py:232-240); the candidates of a cell are a contiguous
-// range of the cell-sorted float4 array stored in reference slot order, so the
-// 32 lanes of a warp (2-3 adjacent cells) issue loads that hit 2-3 distinct
-// addresses (L1 broadcast).  Every row is appended in candidate order by its
-// own thread: no ballots, no atomics, order == reference order.  Row k of the
-// transposed list is written by neighbouring lanes at neighbouring addresses.
+// (2w+1)^d stencil of its own FINE cell (cells whose gap to the home cell
+// exceeds the cutoff are skipped: uniform over the warp); the candidates of a
+// cell are a contiguous range of the cell-sorted float4 array, so the lanes of
+// a warp issue loads that hit a handful of distinct addresses (L1 broadcast).
+// The fine grid (reference cell / 2) cuts the candidates per atom from ~533
+// to ~300 at the LJ benchmark density while the accepted SET stays exactly the
+// reference's: the distance test is the reference's arithmetic, bit for bit.
+// Every row is appended by its own thread: no ballots, no atomics,
+// deterministic order (stencil order, then atom id).  Row k of the transposed
+// list is written by neighbouring lanes at neighbouring addresses.
 // MODE: 0 = forward test only (Sparse formats), 1 = forward + reverse inside
 // the rounding band (Dense).
-template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC>
+template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC, int WSTAT>
 __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
   using V4 = typename Vec4<T>::type;
-  constexpr int NS = DIM == 3 ? 27 : 9;
   const int lane = threadIdx.x & 31;
   const int self_on = P.mask_self;
   const T c2 = P.cutoff_sq;
   constexpr bool periodic = PERIODIC;
   const int kmax = P.count_only ? 0 : P.m_int;
+  const int w = WSTAT > 0 ? WSTAT : P.sw;      // WSTAT == 1: the reference 3^d stencil, unrolled
+  const int wz = DIM == 3 ? w : 0;
+  // gap^2 between the home cell and a stencil cell, with a safety margin so the
+  // pruning can never drop a cell that holds an acceptable candidate
+  const float gap_limit = (float)c2 * 1.0001f + 1e-6f;
   T hh[3], qq[3];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { hh[d] = P.sp.half[d]; qq[d] = P.sp.quarter[d]; }
@@ -413,7 +447,7 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
     if (hid < P.n_rows) {
       const V4 hv = P.pos_sorted[slot];
       const T hp[3] = {hv.x, hv.y, hv.z};
-      const int c = P.hash[hid];              // own cell (hash of this atom)
+      const int c = P.hash[hid];              // own (fine) cell
       const int cx_n = P.cps[0], cy_n = P.cps[1];
       int cc[3];
       cc[0] = c % cx_n;
@@ -422,18 +456,25 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
       const int self = self_on ? slot : -1;
       int k = 0, kl = 0;
       int* out = P.nl + slot;
-      for (int s = 0; s < NS; ++s) {
-        int sh[3];
-        if (DIM == 3) { sh[0] = s / 9 - 1; sh[1] = (s / 3) % 3 - 1; sh[2] = s % 3 - 1; }
-        else { sh[0] = s / 3 - 1; sh[1] = s % 3 - 1; sh[2] = 0; }
+      for (int s0 = -w; s0 <= w; ++s0)
+      for (int s1 = -w; s1 <= w; ++s1)
+      for (int s2 = -wz; s2 <= wz; ++s2) {
+        const int sh[3] = {s0, s1, s2};
+        float gap2 = 0.f;
         int h = 0, mult = 1;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
+          if (WSTAT != 1) {
+            const int e = abs(sh[d]) - 1;
+            const float g = e > 0 ? (float)e * (float)P.cell_size[d] : 0.f;
+            gap2 += g * g;
+          }
           int v = cc[d] + sh[d];
           v = v < 0 ? v + P.cps[d] : (v >= P.cps[d] ? v - P.cps[d] : v);
           h += v * mult;
           mult *= P.cps[d];
         }
+        if (WSTAT != 1 && gap2 > gap_limit) continue;
         const int start = __ldg(&P.cell_start[h]);
         const int end = __ldg(&P.cell_start[h + 1]);
         const V4* cptr = P.pos_sorted + start;
@@ -538,14 +579,17 @@ __device__ void ph_build_all_pairs(const NbrP<T, DIM>& P) {
 template <typename T, int DIM>
 __device__ void ph_build(const NbrP<T, DIM>& P) {
   if (!P.use_cells) { ph_build_all_pairs<T, DIM>(P); return; }
-  if (P.sp.periodic) {
-    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, true>(P);
-    else if (P.format == JMD_SPARSE) ph_build_cells<T, DIM, 0, false, true>(P);
-    else ph_build_cells<T, DIM, 1, false, true>(P);
-  } else {
-    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, false>(P);
-    else ph_build_cells<T, DIM, 0, false, false>(P);
+#define JMD_SCAN(W)                                                                        \
+  if (P.sp.periodic) {                                                                     \
+    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, true, W>(P);       \
+    else if (P.format == JMD_SPARSE) ph_build_cells<T, DIM, 0, false, true, W>(P);         \
+    else ph_build_cells<T, DIM, 1, false, true, W>(P);                                     \
+  } else {                                                                                 \
+    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, false, W>(P);      \
+    else ph_build_cells<T, DIM, 0, false, false, W>(P);                                    \
   }
+  if (P.sw == 1) { JMD_SCAN(1) } else { JMD_SCAN(0) }
+#undef JMD_SCAN
 }
 
 // ---- phases: export to the public formats ------------------------------------------------
@@ -601,7 +645,7 @@ __device__ void ph_export(const NbrP<T, DIM>& P, Smem& sm) {
       }
       __syncwarp();
       const int k = k0 + lane;
-#pragma unroll 4
+#pragma unroll 8
       for (int r = 0; r < 32; ++r) {
         const int a = __shfl_sync(0xffffffffu, a_l, r);
         if (a < 0) break;                            // slots beyond n (uniform)
@@ -668,7 +712,7 @@ __global__ void __launch_bounds__(NB, 3) k_phase(NbrP<T, DIM> P, int gated) {
   switch (PHASE) {
     case PH_ZERO: ph_zero(P); break;
     case PH_HASH: ph_hash(P); break;
-    case PH_SCAN1: ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, &P.state[ST_MAX_CELL], sm); break;
+    case PH_SCAN1: ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, nullptr, sm); ph_ref_max(P); break;
     case PH_SCAN2: ph_scan_top<int>(P.scan_tmp, P.n_cells, sm); break;
     case PH_SCAN3: ph_scan_apply<int, int>(P.cell_count, P.n_cells, P.scan_tmp, P.cell_start, sm); break;
     case PH_SCATTER: ph_scatter(P); break;
@@ -703,7 +747,7 @@ __global__ void __launch_bounds__(NB, 3) k_nbr_stencil_scan(NbrP<T, DIM> P, int 
 }
 
 template <typename T, int DIM>
-__global__ void __launch_bounds__(NB, 3) k_nbr_export(NbrP<T, DIM> P, int gated) {
+__global__ void __launch_bounds__(NB, 6) k_nbr_export(NbrP<T, DIM> P, int gated) {
   if (gated && P.state[ST_REBUILD] == 0) return;
   if (P.no_public_idx) return;
   __shared__ Smem sm;
@@ -799,7 +843,8 @@ __global__ void __launch_bounds__(NB, 4) k_update(NbrP<T, DIM> P) {
     if (gtid() == 0) P.state[ST_PENDING] = 0;    // everyone has read it
     ph_hash(P);
     grid_sync(bar, target);
-    ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, &P.state[ST_MAX_CELL], sm);
+    ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, nullptr, sm);
+    ph_ref_max(P);
     grid_sync(bar, target);
     ph_scan_top<int>(P.scan_tmp, P.n_cells, sm);
     grid_sync(bar, target);
@@ -823,7 +868,7 @@ __global__ void __launch_bounds__(NB, 4) k_update(NbrP<T, DIM> P) {
 // part C: sparse offsets (needs a scan, hence barriers) + export + error bits.
 // Dense needs no barrier and is launched with one thread per atom instead.
 template <typename T, int DIM>
-__global__ void __launch_bounds__(NB, 4) k_update_c(NbrP<T, DIM> P) {
+__global__ void __launch_bounds__(NB, 6) k_update_c(NbrP<T, DIM> P) {
   if (P.state[ST_REBUILD] == 0) return;
   __shared__ Smem sm;
   if (P.no_public_idx) { ph_finalize(P); return; }
@@ -855,14 +900,28 @@ template <typename T, int DIM>
 int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   if (!nb || nb->n < 0) return JMD_EINVAL;
   P.n = nb->n; P.format = nb->format; P.use_cells = nb->use_cells; P.mask_self = nb->mask_self;
-  P.always_rebuild = nb->always_rebuild; P.n_cells = nb->n_cells; P.cell_capacity = nb->cell_capacity;
+  P.always_rebuild = nb->always_rebuild; P.cell_capacity = nb->cell_capacity;
   P.m_int = nb->m_int;
-  for (int k = 0; k < 3; ++k) P.cps[k] = nb->cps[k] > 0 ? nb->cps[k] : 1;
+  // reference grid (flags) and the internal fine search grid
+  P.n_ref_cells = nb->n_cells;
+  P.n_cells = nb->n_fine_cells;
+  P.sw = nb->stencil_w > 0 ? nb->stencil_w : 1;
+  for (int k = 0; k < 3; ++k) {
+    P.ref_cps[k] = nb->cps[k] > 0 ? nb->cps[k] : 1;
+    P.cps[k] = nb->fine_cps[k] > 0 ? nb->fine_cps[k] : 1;
+  }
+  if (nb->use_cells) {
+    for (int k = 0; k < DIM; ++k)
+      if (P.cps[k] < 2 * P.sw + 1) return JMD_EINVAL;       // stencil cells would alias
+  }
   P.count_only = 0;
   P.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
   P.no_public_idx = nb->no_public_idx;
   P.n_pad = nb->n_pad; P.max_occupancy = nb->max_occupancy;
-  for (int k = 0; k < DIM; ++k) P.cell_size[k] = (T)nb->cell_size[k];
+  for (int k = 0; k < DIM; ++k) {
+    P.cell_size[k] = (T)nb->fine_cell_size[k];
+    P.ref_cell_size[k] = (T)nb->cell_size[k];
+  }
   P.cutoff_sq = (T)nb->cutoff_sq; P.threshold_sq = (T)nb->threshold_sq;
   P.sp.init(nb->space);
   const bool periodic = nb->space.kind == JMD_SPACE_PERIODIC;
@@ -880,7 +939,7 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   P.far = (T)Lmax;
   P.cell_count = nb->cell_count; P.cell_start = nb->cell_start; P.cell_cursor = nb->cell_cursor;
   P.scan_tmp = nb->scan_tmp; P.hash = nb->hash; P.tmp_ids = nb->tmp_ids; P.perm = nb->perm;
-  P.inv_perm = nb->inv_perm;
+  P.inv_perm = nb->inv_perm; P.ref_count = nb->ref_count;
   P.pos_sorted = (typename Vec4<T>::type*)nb->pos_sorted;
   P.nl = nb->nl; P.cnt = nb->cnt; P.cnt_lower = nb->cnt_lower; P.offsets = (long long*)nb->offsets;
   P.ref = (T*)nb->reference_position; P.idx = nb->idx; P.error = nb->error;

@@ -1,8 +1,10 @@
 """GPU parity: neighbour lists built by libjmd_b200.so vs the CPU oracle.
 
-Bar: bit-exact -- the public `idx` arrays are compared element by element
-(same neighbours in the same order as the reference's candidate order), plus
-occupancies, capacities and error flags.
+Bar: bit-exact.  With the default search grid the public `idx` arrays are
+compared element by element (same neighbours in the same order as the
+reference's candidate order); with the optional finer search grid the SETS are
+compared (sorted rows / sorted pair lists, as BASELINE.json specifies).  Plus
+shapes, occupancies, capacities, padding and error flags.
 """
 import numpy as np
 import pytest
@@ -215,6 +217,22 @@ def test_large_random_sets_bit_exact():
   nb_g = nf_g.allocate(_dev(R))
   nb_o = nf_o.allocate(R)
   _assert_same(nb_o, nb_g)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('dim', [2, 3])
+def test_fine_search_grid_same_sets(fmt, dim):
+  """Optional finer internal grid: identical neighbour SETS and flags."""
+  rng = np.random.default_rng(4)
+  box = np.array([19.0, 14.0, 17.25][:dim], np.float32)
+  R = (rng.random((4000, dim)) * box).astype(np.float32)
+  nf_o, nf_g = _build_both(R, box, 1.9, 0.2, fmt, fine_search_grid=True)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  assert nb_g._ws.c.stencil_w == 2
+  _assert_same(nb_o, nb_g, exact_order=False)
+  R2 = np.mod(R + rng.normal(0, 0.2, R.shape).astype(np.float32), box).astype(np.float32)
+  _assert_same(nb_o.update(R2), nb_g.update(_dev(R2)), exact_order=False)
 
 
 def test_always_rebuild_when_skin_zero():
