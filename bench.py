@@ -339,7 +339,7 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=1000)
-  ap.add_argument('--warmup', type=int, default=300)
+  ap.add_argument('--warmup', type=int, default=500)
   ap.add_argument('--impl', default='b200')
   ap.add_argument('--cells', type=int, default=63, help='fcc cells per side per GPU')
   ap.add_argument('--format', default='OrderedSparse',

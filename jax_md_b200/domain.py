@@ -193,6 +193,10 @@ class SlabDomain:
     self.list_a = torch.empty(self.cap_list, dtype=torch.int32, device=dev)
     self.list_b = torch.empty(self.cap_list, dtype=torch.int32, device=dev)
     self.counters = torch.zeros(2, dtype=torch.int32, device=dev)
+    self._flag_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    self._flag_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+    self._flag_event = torch.cuda.Event()
+    self._decision_pending = False
     self._rebuild(st, first=True)
     self._force(st, kick=False)
     return st
@@ -323,19 +327,48 @@ class SlabDomain:
               self.dt_2, None, 0, _lib.stream())
 
   # -- the step ---------------------------------------------------------------------
-  def step(self, st):
+  def _launch_decision(self, st):
+    """Skin predicate on the CURRENT owned positions -> global OR -> pinned host
+    flag (asynchronously).  Enqueued right after the drift, i.e. before the halo
+    exchange and the force kernel of the same step, so by the time the host
+    needs the answer (start of the next step) the GPU is still busy with the
+    force kernel and never waits for the host."""
     ws = self.nbrs._ws
+    _lib.call('jmd_nbr_skin_check', ws.ref(), _lib.ptr(st.R), _lib.stream())
+    flag = ws.t['state'][_lib.ST_REBUILD:_lib.ST_REBUILD + 1]
+    if self.comm.world > 1:
+      if self.comm.direct:
+        self._flag_dev.copy_(flag)
+        dist.all_reduce(self._flag_dev, op=dist.ReduceOp.MAX, group=self.comm.group)
+        self._flag_host.copy_(self._flag_dev, non_blocking=True)
+      else:                                   # gloo: staged through the host
+        self._flag_host.copy_(flag)
+        dist.all_reduce(self._flag_host, op=dist.ReduceOp.MAX, group=self.comm.group)
+    else:
+      self._flag_host.copy_(flag, non_blocking=True)
+    self._flag_event.record()
+    self._decision_pending = True
+
+  def _take_decision(self, st):
+    if not self._decision_pending:
+      self._launch_decision(st)
+    self._flag_event.synchronize()
+    self._decision_pending = False
+    return bool(int(self._flag_host[0]) != 0)
+
+  def step(self, st):
     s = _lib.stream()
     # 1-2. NeighborList.update semantics (partition.py:1146) with a GLOBAL decision
-    _lib.call('jmd_nbr_skin_check', ws.ref(), _lib.ptr(st.R), s)
-    flag = ws.t['state'][_lib.ST_REBUILD:_lib.ST_REBUILD + 1].clone()
-    if self.comm.any(flag):
+    #      (predicate evaluated on these same positions at the end of the last step)
+    if self._take_decision(st):
       self._rebuild(st)
-      ws = self.nbrs._ws
+    ws = self.nbrs._ws
     # 3. first half kick + drift of owned atoms (in place on the capacity arrays)
     _lib.call('jmd_nve_kick_drift', C.byref(self.sp), self.dtc, st.n_own, ws.ref(),
               _lib.ptr(st.R), _lib.ptr(st.P), _lib.ptr(st.F), _lib.ptr(self.mass), 0,
               self.dt, None, None, _lib.ptr(st.R), _lib.ptr(st.P), s)
+    #    the next step's rebuild decision, overlapped with steps 4-5
+    self._launch_decision(st)
     # 4. halo exchange of the drifted face atoms, refresh the sorted ghost copies
     if st.n_ghost:
       self._halo(st)

@@ -1,0 +1,170 @@
+"""GPU parity at BASELINE.json's full sizes through size-independent
+properties (the oracle cannot run these sizes in seconds):
+
+  * format consistency: Sparse total >= sum of Dense row counts (Dense keeps a
+    pair only if both orientations of the rounded distance test pass), equal up
+    to a handful of 1-ulp boundary pairs; ~2 x OrderedSparse total; Dense rows
+    are symmetric (j in row i <=> i in row j)
+  * rebuild idempotence: rebuilding on the same positions reproduces idx
+  * Newton's third law: sum of forces == 0 (full-list, atomics-free kernel)
+  * energy conservation of the fused NVE step with rebuilds
+  * checksum-of-checksums: total energy from per-particle energies == scalar E
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _jmd():
+  import jax_md_b200 as jmd
+  return jmd
+
+
+def _lj_1m():
+  import bench
+  R, box = bench.fcc((63, 63, 63))
+  rng = np.random.default_rng(5)
+  R = np.mod(R + rng.normal(0, 0.05, R.shape).astype(np.float32), box[0]).astype(np.float32)
+  return torch.as_tensor(R, device='cuda'), box[0]
+
+
+def test_lj_1m_formats_symmetry_idempotence():
+  jmd = _jmd()
+  R, L = _lj_1m()
+  N = R.shape[0]
+  assert N == 1_000_188
+  d, _ = jmd.space.periodic(L)
+  lists = {}
+  for fmt in ('Dense', 'Sparse', 'OrderedSparse'):
+    nf = jmd.partition.neighbor_list(d, L, np.float32(2.5), np.float32(0.3),
+                                     format=jmd.partition.NeighborListFormat[fmt])
+    nb = nf.allocate(R)
+    assert int(nb.error.code) == 0
+    lists[fmt] = nb
+  dense = lists['Dense'].idx
+  row_counts = (dense < N).sum(dim=1)
+  total_dense = int(row_counts.sum())
+  sp = lists['Sparse'].idx
+  total_sparse = int((sp[0] < N).sum())
+  total_ord = int((lists['OrderedSparse'].idx[0] < N).sum())
+  # Reference semantics (oracle/partition.py): Sparse keeps a pair when the forward
+  # test d2(R_i, R_j) < cutoff^2 passes, Dense only when BOTH orientations pass
+  # (prune_neighbor_list_dense re-tests with map_neighbor's reversed arguments).
+  # The two differ by rounding only, i.e. by a handful of 1-ulp boundary pairs.
+  assert total_sparse >= total_dense
+  assert total_sparse - total_dense < 1e-6 * total_dense
+  assert abs(total_sparse - 2 * total_ord) < 1e-6 * total_dense
+  # valid entries come first, padding is N, senders are sorted
+  assert bool((sp[0, :total_sparse] < N).all()) and bool((sp[:, total_sparse:] == N).all())
+  assert bool((sp[1, 1:total_sparse] >= sp[1, :total_sparse - 1]).all())
+  per_sender = torch.bincount(sp[1, :total_sparse].long(), minlength=N)
+  assert bool((per_sender >= row_counts).all())
+  assert int((per_sender - row_counts).sum()) == total_sparse - total_dense
+  # Dense rows are symmetric: order-independent checksum of (i, j) == that of (j, i)
+  rows = torch.arange(N, device='cuda')[:, None].expand_as(dense)
+  m = dense < N
+  s, r = rows[m].long(), dense[m].long()
+  h1 = ((s * 1000003 + r) % 2147483629).sum()
+  h2 = ((r * 1000003 + s) % 2147483629).sum()
+  assert int(h1) == int(h2)
+  assert int((lists['OrderedSparse'].idx[0, :total_ord] < lists['OrderedSparse'].idx[1, :total_ord]).sum()) == total_ord
+  # idempotence: a forced rebuild on identical positions reproduces idx exactly
+  nb = lists['Dense']
+  before = nb.idx.clone()
+  b0 = nb._ws.state_host()[4]
+  Rm = R.clone()
+  Rm[0, 0] = torch.remainder(Rm[0, 0] + 0.2, float(L))      # one atom past skin/2
+  nb = nb.update(Rm)                                        # -> rebuild on Rm
+  nb = nb.update(R)                                         # -> rebuild back on R
+  assert nb._ws.state_host()[4] == b0 + 2
+  assert int(nb.error.code) == 0
+  assert torch.equal(nb.idx, before)
+  nf = jmd.partition.neighbor_list(d, L, np.float32(2.5), np.float32(0.3))
+  again = nf.allocate(R)
+  assert torch.equal(again.idx, before)
+
+
+def test_lj_1m_newton_energy_checksum_and_nve():
+  jmd = _jmd()
+  R, L = _lj_1m()
+  N = R.shape[0]
+  d, s = jmd.space.periodic(L)
+  nf, efn = jmd.energy.lennard_jones_neighbor_list(d, L, dr_threshold=0.3,
+                                                   format=jmd.partition.Sparse)
+  _, efn_pp = jmd.energy.lennard_jones_neighbor_list(d, L, dr_threshold=0.3, per_particle=True,
+                                                     format=jmd.partition.Sparse)
+  nbrs = nf.allocate(R)
+  F = jmd.quantity.force(efn)(R, neighbor=nbrs)
+  assert float(F.sum(0).abs().max()) < 1e-2 * float(F.abs().mean()) * np.sqrt(N)   # third law
+  E = float(efn(R, neighbor=nbrs))
+  Epp = efn_pp(R, neighbor=nbrs)
+  np.testing.assert_allclose(float(Epp.sum(dtype=torch.float64)), E, rtol=1e-6)
+  # bitwise reproducibility of the atomics-free kernel
+  F2 = jmd.quantity.force(efn)(R, neighbor=nbrs)
+  assert torch.equal(F, F2)
+  # fused NVE with rebuilds conserves energy
+  init, step = jmd.simulate.nve(efn, s, 5e-3)
+  P = torch.as_tensor(util.momenta(N, 3, 0.7), device='cuda')
+  st = init(0, R, kT=0.7, momenta=P, neighbor=nbrs)
+  KE = lambda st: float(jmd.quantity.kinetic_energy(momentum=st.momentum, mass=st.mass))
+  E0 = float(efn(st.position, neighbor=nbrs)) + KE(st)
+  b0 = nbrs._ws.state_host()[4]
+  for _ in range(200):
+    nbrs = nbrs.update(st.position)
+    st = step(st, neighbor=nbrs)
+  assert not bool(nbrs.did_buffer_overflow)
+  assert nbrs._ws.state_host()[4] > b0 + 5
+  E1 = float(efn(st.position, neighbor=nbrs)) + KE(st)
+  assert abs(E1 - E0) / N < 1e-4
+  # momentum conservation (sum of forces == 0 every step)
+  assert float(st.momentum.sum(0, dtype=torch.float64).abs().max()) < 1e-1
+
+
+def test_sw_512k_energy_and_third_law():
+  """BASELINE config 4 size: diamond Si 40^3 x 8 = 512,000 atoms."""
+  jmd = _jmd()
+  R, L = util.diamond(40, a=5.431, dtype=np.float32)
+  Rj = util.jitter(R, np.float32(L), 0.05, seed=1)
+  Rd = torch.as_tensor(Rj, device='cuda')
+  d, _ = jmd.space.periodic(np.float32(L))
+  nf, efn = jmd.energy.stillinger_weber_neighbor_list(d, np.float32(L))
+  nbrs = nf.allocate(Rd)
+  assert int(nbrs.error.code) == 0
+  assert nbrs.max_occupancy >= 16
+  F = jmd.quantity.force(efn)(Rd, neighbor=nbrs)
+  assert float(F.sum(0, dtype=torch.float64).abs().max()) < 1e-2 * float(F.abs().mean()) * np.sqrt(len(R))
+  # perfect lattice: golden energy per atom at this lattice constant, zero force
+  Rp = torch.as_tensor(R, device='cuda')
+  nb2 = nf.allocate(Rp)
+  e = float(efn(Rp, neighbor=nb2)) / len(R)
+  np.testing.assert_allclose(e, -4.3366, rtol=2e-4)          # a = 5.431 (golden is at 5.428)
+  assert float(jmd.quantity.force(efn)(Rp, neighbor=nb2).abs().max()) < 5e-3
+
+
+def test_soft_sphere_256k_fire_reduces_energy():
+  """BASELINE config 3 size: bidisperse soft spheres, 2-D, N = 256,000."""
+  jmd = _jmd()
+  N = 256_000
+  rng = np.random.default_rng(2)
+  L = np.float32(np.sqrt(N / 0.8))
+  R = torch.as_tensor((rng.random((N, 2)) * L).astype(np.float32), device='cuda')
+  species = torch.as_tensor((np.arange(N) % 2).astype(np.int32), device='cuda')
+  sigma = np.array([[1.0, 1.2], [1.2, 1.4]], np.float32)
+  d, s = jmd.space.periodic(L)
+  nf, efn = jmd.energy.soft_sphere_neighbor_list(d, L, species=species, sigma=sigma)
+  nbrs = nf.allocate(R)
+  init, step = jmd.minimize.fire_descent(efn, s)
+  st = init(R, neighbor=nbrs)
+  E0 = float(efn(st.position, neighbor=nbrs))
+  for _ in range(100):
+    nbrs = nbrs.update(st.position)
+    st = step(st, neighbor=nbrs)
+  if bool(nbrs.did_buffer_overflow):
+    nbrs = nf.allocate(st.position)
+  E1 = float(efn(st.position, neighbor=nbrs))
+  assert E1 < 0.5 * E0
+  assert torch.isfinite(st.position).all()
