@@ -103,32 +103,19 @@ def peaks():
 # ------------------------------------------------------------------------------
 
 def cpu_port_run(n, steps, warmup):
-  """Times the oracle (a CPU port of the reference path) on a bounded sample:
-  fcc N = 4 n^3, `steps` update+NVE steps.  Returns (atom-steps/s, N, seconds)."""
-  from oracle import energy as oenergy, partition as opart
-  from oracle import simulate as osim, space as ospace
+  """Times the CPU port of the reference path (oracle/c, multi-threaded C; the
+  NumPy oracle is ~14x slower) on a bounded sample: fcc N = 4 n^3, `steps`
+  update+NVE steps.  Returns (atom-steps/s, N, seconds, threads)."""
+  from oracle import cport
   R, box = fcc((n, n, n))
-  L = box[0]
-  d, s = ospace.periodic(L)
-  pot = oenergy.PairPotential('lj', np.float32(2.0), np.float32(2.5))
-  nf = opart.neighbor_list(d, L, np.float32(R_CUT), np.float32(SKIN),
-                           format=opart.OrderedSparse)
-  holder = {'nb': nf.allocate(R)}
-
-  def force(Rx):
-    holder['nb'] = holder['nb'].update(Rx)
-    return oenergy.pair_neighbor_list_energy(
-        pot, d, Rx, holder['nb'], want_grads=True, sigma=np.float32(1.0),
-        epsilon=np.float32(1.0))[1]
-  init, step = osim.nve(force, s, DT)
-  st = init(R, momenta(len(R)), mass=np.float32(1.0))
-  for _ in range(warmup):
-    st = step(st)
+  sysc = cport.LJSystem(R, box[0], r_cutoff=R_CUT, skin=SKIN, r_onset=2.0)
+  sysc.run(momenta(len(R)), DT, warmup)
   t0 = time.perf_counter()
-  for _ in range(steps):
-    st = step(st)
+  sysc.run(None, DT, steps)
   dt = time.perf_counter() - t0
-  return len(R) * steps / dt, len(R), dt
+  th = sysc.threads
+  sysc.close()
+  return len(R) * steps / dt, len(R), dt, th
 
 
 def run_reference(args):
@@ -137,11 +124,12 @@ def run_reference(args):
     return
   n = args.cpu_cells
   steps = max(1, min(args.steps, args.cpu_steps))
-  warm = 1
-  v, N, secs = cpu_port_run(n, steps, warm)
+  warm = max(1, min(args.warmup, 2))
+  v, N, secs, th = cpu_port_run(n, steps, warm)
   ms = secs / steps * 1e3
-  sample = (f'LJ fcc N={N} (n={n}), {steps} update+NVE steps through the NumPy '
-            f'oracle port (jax is not installable here; reference not runnable)')
+  sample = (f'LJ fcc N={N} (n={n}), {steps} update+NVE steps through the C port of the '
+            f'reference path on {th} threads (jax is not installable here: the reference '
+            f'itself is not runnable)')
   line = {
       'impl': 'reference', 'metric': 'atom-timesteps/s', 'value': v,
       'unit': 'atom-timesteps/s', 'n_gpus': args.gpus, 'steps': steps,
@@ -150,7 +138,7 @@ def run_reference(args):
       'data': 'synthetic',
       'config': {'workload': f'LJ fcc rho={RHO} rc={R_CUT} skin={SKIN} NVE, '
                              f'bounded CPU sample N={N}'},
-      'cpu_baseline': {'value': v, 'unit': 'atom-timesteps/s', 'cores': 1,
+      'cpu_baseline': {'value': v, 'unit': 'atom-timesteps/s', 'cores': th,
                        'kind': 'port', 'sample': sample},
       'e2e': {'value': v, 'unit': 'atom-timesteps/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
@@ -311,10 +299,10 @@ def run_b200(args):
   # ---- CPU baseline (oracle port, bounded sample) -------------------------------
   cpu = None
   if not args.no_cpu:
-    v, Nc, secs = cpu_port_run(args.cpu_cells, args.cpu_steps, 1)
-    cpu = {'value': v, 'unit': 'atom-timesteps/s', 'cores': 1, 'kind': 'port',
-           'sample': f'LJ fcc N={Nc}, {args.cpu_steps} update+NVE steps, NumPy oracle '
-                     f'port ({secs:.1f} s); host has {os.cpu_count()} cores'}
+    v, Nc, secs, th = cpu_port_run(args.cpu_cells, args.cpu_steps, 2)
+    cpu = {'value': v, 'unit': 'atom-timesteps/s', 'cores': th, 'kind': 'port',
+           'sample': f'LJ fcc N={Nc}, {args.cpu_steps} update+NVE steps, C port of the '
+                     f'reference path on {th} threads ({secs:.1f} s)'}
 
   rebuild_kernels = 12 if args.format == 'Dense' else 16
   line = {
@@ -346,8 +334,8 @@ def main():
                   choices=['Dense', 'Sparse', 'OrderedSparse'])
   ap.add_argument('--block', type=int, default=100)
   ap.add_argument('--kernel-reps', type=int, default=20)
-  ap.add_argument('--cpu-cells', type=int, default=20)
-  ap.add_argument('--cpu-steps', type=int, default=20)
+  ap.add_argument('--cpu-cells', type=int, default=40)
+  ap.add_argument('--cpu-steps', type=int, default=40)
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--update-mode', default='fused', choices=['fused', 'gated'],
                   help="how update()'s lax.cond is realised: one cooperative kernel or gated kernels")

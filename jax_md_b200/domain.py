@@ -246,19 +246,26 @@ class SlabDomain:
     gir = torch.empty((n_from_r,), dtype=torch.int64, device=self.device)
     self.comm.exchange(sl, sr, rl, rr)
     self.comm.exchange(gl, gr, gil, gir)
-    keep = torch.ones(st.n_own, dtype=torch.bool, device=self.device)
-    keep[go_l.long()] = False
-    keep[go_r.long()] = False
-    n_keep = int(keep.sum())
+    # Compact in O(#leavers): move the tail atoms that stay into the holes left
+    # in the head, then append the arrivals.
+    n_old = st.n_own
+    leave = torch.cat([go_l, go_r]).long()
+    n_keep = n_old - leave.numel()
     n_new = n_keep + n_from_l + n_from_r
     if n_new > self.cap:
       raise RuntimeError('slab capacity exceeded; raise capacity_factor')
-    inc = torch.cat([rl, rr], dim=0)
-    for arr, c0 in ((st.R, 0), (st.P, dim), (st.F, 2 * dim)):
-      kept = arr[:st.n_own][keep]
-      arr[:n_keep] = kept
-      arr[n_keep:n_new] = inc[:, c0:c0 + dim]
-    st.gid[:n_new] = torch.cat([st.gid[:st.n_own][keep], gil, gir])
+    if leave.numel():
+      tail = torch.arange(n_keep, n_old, device=self.device)
+      fillers = tail[~torch.isin(tail, leave)]
+      holes = leave[leave < n_keep]
+      if holes.numel():
+        for arr in (st.R, st.P, st.F, st.gid):
+          arr[holes] = arr[fillers]
+    if n_from_l + n_from_r:
+      inc = torch.cat([rl, rr], dim=0)
+      for arr, c0 in ((st.R, 0), (st.P, dim), (st.F, 2 * dim)):
+        arr[n_keep:n_new] = inc[:, c0:c0 + dim]
+      st.gid[n_keep:n_new] = torch.cat([gil, gir])
     st.n_own = n_new
 
   def _ghosts(self, st):
@@ -273,20 +280,30 @@ class SlabDomain:
       raise RuntimeError('slab capacity exceeded (ghosts); raise capacity_factor')
     self._lists = (face_l, face_r, n_from_l, n_from_r)
     st.n_ghost = n_from_l + n_from_r
+    self._send_l = torch.empty((face_l.numel(), self.dim), dtype=self.dtype, device=self.device)
+    self._send_r = torch.empty((face_r.numel(), self.dim), dtype=self.dtype, device=self.device)
     self._halo(st)
-    # ghost ids (diagnostics / gather)
+
+  def ghost_ids(self, st):
+    """Global ids of the ghost atoms (diagnostics; one extra exchange)."""
+    if self._lists is None:
+      return st.gid[st.n_own:st.n_own]
+    face_l, face_r, n_from_l, n_from_r = self._lists
     gl = st.gid[face_l.long()].contiguous()
     gr = st.gid[face_r.long()].contiguous()
     o = st.n_own
     self.comm.exchange(gl, gr, st.gid[o:o + n_from_l], st.gid[o + n_from_l:o + st.n_ghost])
+    return st.gid[o:o + st.n_ghost]
 
   def _halo(self, st):
     """Face positions -> neighbours' ghost slots (every step)."""
     if self._lists is None:
       return
     face_l, face_r, n_from_l, n_from_r = self._lists
-    sl = self._pack(st.R, face_l, self.dim)
-    sr = self._pack(st.R, face_r, self.dim)
+    sl, sr = self._send_l, self._send_r
+    for idx, out in ((face_l, sl), (face_r, sr)):
+      _lib.call('jmd_dd_pack', self.dtc, self.dim, idx.numel(), _lib.ptr(idx), _lib.ptr(st.R),
+                _lib.ptr(out), _lib.stream())
     o = st.n_own
     self.comm.exchange(sl, sr, st.R[o:o + n_from_l], st.R[o + n_from_l:o + n_from_l + n_from_r])
 

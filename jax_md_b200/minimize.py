@@ -19,7 +19,7 @@ class FireDescentState:
   dt: Any
   alpha: Any
   n_pos: Any
-  _fire: Any = dataclasses.static_field(default=None)
+  _fire: Any = None          # [dt, alpha] device buffer the kernels read
 
 
 def fire_descent(energy_or_force, shift_fn, dt_start=0.1, dt_max=0.4, n_min=5,

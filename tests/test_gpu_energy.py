@@ -380,3 +380,50 @@ def test_generic_force_fn_path():
   E1 = float(efn(st.position)) + float(jmd.quantity.kinetic_energy(
       momentum=st.momentum, mass=st.mass))
   assert abs(E1 - E0) < 1e-3 * E0
+
+
+@pytest.mark.parametrize('kind', ['nve', 'nvt', 'fire'])
+def test_fori_loop_cuda_graph_matches_eager(kind):
+  """lax.fori_loop (CUDA-graph replay of the step body, rebuild decision on the
+  device) follows the eager loop; it is the analogue of jit(lax.fori_loop)."""
+  jmd = _jmd()
+  dtype = np.float64
+  s = _pair_setup('lj' if kind != 'fire' else 'soft_sphere', dtype, 'Dense', n=6)
+  R = _dev(s['R'])
+  P = _dev(util.momenta(len(s['R']), 3, kT=1.0, dtype=dtype))
+  if kind == 'nve':
+    init, step = jmd.simulate.nve(s['e_g'], s['s_g'], 2e-3)
+    mk = lambda nb: init(0, R, kT=1.0, momenta=P, neighbor=nb)
+  elif kind == 'nvt':
+    init, step = jmd.simulate.nvt_nose_hoover(s['e_g'], s['s_g'], 2e-3, 0.8, chain_length=3)
+    mk = lambda nb: init(0, R, momenta=P, neighbor=nb)
+  else:
+    init, step = jmd.minimize.fire_descent(s['e_g'], s['s_g'])
+    mk = lambda nb: init(R, neighbor=nb)
+
+  def body(i, carry):
+    st, nb = carry
+    nb = nb.update(st.position)
+    return step(st, neighbor=nb), nb
+  steps = 120
+  nb_e = s['nf_g'].allocate(R)
+  st_e = mk(nb_e)
+  for i in range(steps):
+    st_e, nb_e = body(i, (st_e, nb_e))
+  nb_g = s['nf_g'].allocate(R)
+  st_g = mk(nb_g)
+  b0 = nb_g._ws.state_host()[4]
+  st_g, nb_g = jmd.lax.fori_loop(0, steps, body, (st_g, nb_g), unroll=20)
+  assert not bool(nb_g.did_buffer_overflow)
+  if kind != 'fire':
+    assert nb_g._ws.state_host()[4] > b0          # rebuilt inside the graph
+  dR = (st_g.position - st_e.position).cpu().numpy()
+  dR -= np.round(dR / s['L']) * s['L']
+  assert np.abs(dR).max() < 1e-8
+  np.testing.assert_allclose(st_g.momentum.cpu().numpy(), st_e.momentum.cpu().numpy(), atol=1e-7)
+  if kind == 'nvt':
+    np.testing.assert_allclose(st_g.chain.momentum.cpu().numpy(), st_e.chain.momentum.cpu().numpy(),
+                               rtol=1e-7, atol=1e-9)
+  if kind == 'fire':
+    assert int(st_g.n_pos) == int(st_e.n_pos)
+    np.testing.assert_allclose(float(st_g.dt), float(st_e.dt), rtol=1e-12)
