@@ -211,7 +211,8 @@ typedef struct {
   double sigma, A, B, lam, gamma, epsilon, three_body_strength, cutoff;
 } jmd_sw_t;
 
-int jmd_sw_force(const jmd_nbr_t* nb, const jmd_sw_t* sw, void* force,
+/* scratch: int32[(m_int + 1) * n_pad] for the compact in-range rows. */
+int jmd_sw_force(const jmd_nbr_t* nb, const jmd_sw_t* sw, int32_t* scratch, void* force,
                  double* red, double* partials, void* momentum,
                  const void* mass, int mass_is_array, double dt_2,
                  const void* dt_dev, void* stream);

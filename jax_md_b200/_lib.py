@@ -83,7 +83,7 @@ _SIGNATURES = {
     'jmd_dd_pack': [_I, _I, _I, _P, _P, _P, _P],
     'jmd_pair_force': [C.POINTER(NbrT), C.POINTER(PairT), _P, _P, _P, _P, _P,
                        _P, _P, _I, _D, _P, _I, _P],
-    'jmd_sw_force': [C.POINTER(NbrT), C.POINTER(SwT), _P, _P, _P, _P, _P, _I,
+    'jmd_sw_force': [C.POINTER(NbrT), C.POINTER(SwT), _P, _P, _P, _P, _P, _P, _I,
                      _D, _P, _P],
     'jmd_nve_kick_drift': [C.POINTER(SpaceT), _I, _I, C.POINTER(NbrT), _P, _P,
                            _P, _P, _I, _D, _P, _P, _P, _P, _P],

@@ -209,7 +209,11 @@ class StillingerWeberFn:
     partials = smap.Scratch.get(ws.n, R.device)
     sw = self._struct()
     mass_is_array = 1 if (mass is not None and mass.numel() > 1) else 0
-    _lib.call('jmd_sw_force', ws.ref(), C.byref(sw), _lib.ptr(force),
+    scratch = ws.t.get('sw_scratch')
+    need = (ws.c.m_int + 1) * ws.c.n_pad
+    if scratch is None or scratch.numel() < need:
+      scratch = ws.buf_plain('sw_scratch', (need,), torch.int32)
+    _lib.call('jmd_sw_force', ws.ref(), C.byref(sw), _lib.ptr(scratch), _lib.ptr(force),
               _lib.ptr(red), _lib.ptr(partials), _lib.ptr(momentum),
               _lib.ptr(mass), mass_is_array, float(dt_2), _lib.ptr(dt_dev),
               _lib.stream())

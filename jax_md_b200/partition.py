@@ -108,6 +108,12 @@ class Workspace:
     setattr(self.c, name, t.data_ptr())
     return t
 
+  def buf_plain(self, name, shape, dtype):
+    """Scratch owned by the workspace but not part of the C descriptor."""
+    t = torch.empty(shape, dtype=dtype, device=self.device)
+    self.t[name] = t
+    return t
+
   def ref(self):
     return C.byref(self.c)
 
