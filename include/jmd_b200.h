@@ -262,19 +262,65 @@ int jmd_fire_mix(int dtype, int64_t count, void* momentum, const void* force,
 
 /* ---- slab domain decomposition helpers (no reference equivalent) */
 
-/* For atoms i < n: d = (pos[i, axis] - lo) wrapped into [-L/2, L/2).  Appends i to
+/* `info` words of the rebuild-time pipeline (device int32[JMD_DD_INFO_COUNT]); the host
+ * writes JMD_DD_N_OWN / clears JMD_DD_ERROR and reads everything back once per rebuild. */
+enum {
+  JMD_DD_N_OWN = 0,   /* owned atoms (in: before migration, out: after) */
+  JMD_DD_FACE_L = 1,  /* face atoms sent to the left / right neighbour every step */
+  JMD_DD_FACE_R = 2,
+  JMD_DD_FROM_L = 3,  /* ghost atoms received from the left / right neighbour */
+  JMD_DD_FROM_R = 4,
+  JMD_DD_ERROR = 5,   /* sticky: JMD_DD_ELIST | JMD_DD_ECAP */
+  JMD_DD_MIG_L = 6,   /* atoms that left to the left / right in the last migration */
+  JMD_DD_MIG_R = 7,
+  JMD_DD_IN_L = 8,    /* atoms that arrived from the left / right */
+  JMD_DD_IN_R = 9,
+  JMD_DD_INFO_COUNT = 16
+};
+#define JMD_DD_ELIST 1 /* a selection list exceeded its capacity */
+#define JMD_DD_ECAP 2  /* owned + ghost atoms exceed the array capacity */
+
+/* For atoms i < n (i < min(n, *n_dev) when n_dev != NULL, so the count can stay on the
+ * device): d = (pos[i, axis] - lo) wrapped into [-L/2, L/2).  Appends i to
  * list_a when d < thr_a and to list_b when d >= thr_b (unordered; counters[0..1]
  * must be zeroed by the caller; entries beyond `cap` are counted, not stored).
  * Migration uses thr_a = 0, thr_b = width; ghost selection thr_a = ghost_width,
  * thr_b = width - ghost_width. */
-int jmd_dd_select(int dtype, int dim, int n, const void* position, int axis,
-                  double lo, double L, double thr_a, double thr_b,
+int jmd_dd_select(int dtype, int dim, int n, const int32_t* n_dev, const void* position,
+                  int axis, double lo, double L, double thr_a, double thr_b,
                   int32_t* list_a, int32_t* list_b, int32_t* counters, int cap,
                   void* stream);
 
-/* dst[i, :] = src[idx[i], :] for rows of `ncomp` elements (halo / migration pack). */
+/* dst[i, :] = src[idx[i], :] for rows of `ncomp` elements (per-step halo pack). */
 int jmd_dd_pack(int dtype, int ncomp, int n_idx, const int32_t* idx,
                 const void* src, void* dst, void* stream);
+
+/* Fixed-capacity messages that carry their own count, so a rebuild needs no count
+ * exchange and no host round trip before the data exchange:
+ *   pack_migrate: pay_x[i, :] = R | P | F of atom list_x[i] (3*dim values),
+ *                 gid_x[0] = min(counters[x], cap_mig), gid_x[1 + i] = gid[list_x[i]]
+ *                 (x = a: to the left neighbour, b: to the right).
+ *   compact:      removes the leavers (lists sorted ascending) from the owned arrays by
+ *                 moving staying tail atoms into the holes, appends the arrivals
+ *                 (in_l then in_r, counts in gid_in_x[0]) and updates info[JMD_DD_N_OWN].
+ *                 scratch: int32[6 * cap_mig].
+ *   pack_counted: dst[0, 0] = min(*count, cap); dst[1 + i, :] = src[idx[i], :].
+ *   place:        ghost rows R[n_own + k] = [recv_l rows | recv_r rows] (counts in
+ *                 recv_x[0, 0]); fills info FACE_x / FROM_x / ERROR. */
+int jmd_dd_pack_migrate(int dtype, int dim, int cap_mig, const int32_t* list_a,
+                        const int32_t* list_b, const int32_t* counters, const void* R,
+                        const void* P, const void* F, const int64_t* gid, void* pay_a,
+                        void* pay_b, int64_t* gid_a, int64_t* gid_b, void* stream);
+int jmd_dd_compact(int dtype, int dim, int cap_own, int cap_mig, const int32_t* list_a,
+                   const int32_t* list_b, const int32_t* counters, const void* in_l,
+                   const int64_t* gid_in_l, const void* in_r, const int64_t* gid_in_r,
+                   void* R, void* P, void* F, int64_t* gid, int32_t* scratch,
+                   int32_t* info, void* stream);
+int jmd_dd_pack_counted(int dtype, int ncomp, int cap, const int32_t* idx,
+                        const int32_t* count, const void* src, void* dst, void* stream);
+int jmd_dd_place(int dtype, int dim, int cap_total, int cap_list, const int32_t* counters,
+                 const void* recv_l, const void* recv_r, void* R, int32_t* info,
+                 void* stream);
 
 const char* jmd_version(void);
 

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libjmd_b200.so')
+LIB_PATH = os.environ.get('JMD_B200_LIB', os.path.join(_HERE, 'libjmd_b200.so'))
 
 F32, F64 = 0, 1
 DENSE, SPARSE, ORDERED_SPARSE = 0, 1, 2
@@ -19,6 +19,11 @@ POT_LJ, POT_SOFT_SPHERE, POT_MORSE = 0, 1, 2
 PARAM_SCALAR, PARAM_PER_ATOM, PARAM_SPECIES, PARAM_MATRIX = 0, 1, 2, 3
 ST_REBUILD, ST_MAX_CELL_OCC, ST_MAX_ROW, ST_TOTAL, ST_BUILDS = 0, 1, 2, 3, 4
 ST_COUNT = 8
+# jmd_dd_* info words (include/jmd_b200.h)
+(DD_N_OWN, DD_FACE_L, DD_FACE_R, DD_FROM_L, DD_FROM_R, DD_ERROR, DD_MIG_L, DD_MIG_R,
+ DD_IN_L, DD_IN_R) = range(10)
+DD_INFO_COUNT = 16
+DD_ELIST, DD_ECAP = 1, 2
 RED_ENERGY, RED_KINETIC, RED_VIRIAL = 0, 1, 2
 RED_DSIGMA, RED_DEPSILON, RED_FF, RED_PP, RED_FP = 8, 9, 10, 11, 12
 RED_COUNT = 16
@@ -79,8 +84,12 @@ _SIGNATURES = {
     'jmd_nbr_state_host': [C.POINTER(NbrT), C.POINTER(C.c_int64), _P],
     'jmd_nbr_pack': [C.POINTER(NbrT), _P, _P],
     'jmd_nbr_pack_range': [C.POINTER(NbrT), _P, _I, _I, _P],
-    'jmd_dd_select': [_I, _I, _I, _P, _I, _D, _D, _D, _D, _P, _P, _P, _I, _P],
+    'jmd_dd_select': [_I, _I, _I, _P, _P, _I, _D, _D, _D, _D, _P, _P, _P, _I, _P],
     'jmd_dd_pack': [_I, _I, _I, _P, _P, _P, _P],
+    'jmd_dd_pack_migrate': [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'jmd_dd_compact': [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'jmd_dd_pack_counted': [_I, _I, _I, _P, _P, _P, _P, _P],
+    'jmd_dd_place': [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     'jmd_pair_force': [C.POINTER(NbrT), C.POINTER(PairT), _P, _P, _P, _P, _P,
                        _P, _P, _I, _D, _P, _I, _P],
     'jmd_sw_force': [C.POINTER(NbrT), C.POINTER(SwT), _P, _P, _P, _P, _P, _P, _I,

@@ -18,7 +18,10 @@
 
 namespace {
 
-constexpr int PAIR_BLOCK = 128;
+#ifndef JMD_PAIR_BLOCK
+#define JMD_PAIR_BLOCK 256
+#endif
+constexpr int PAIR_BLOCK = JMD_PAIR_BLOCK;
 
 template <typename T, int DIM>
 struct PairP {

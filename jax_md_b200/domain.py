@@ -27,6 +27,7 @@ import torch.distributed as dist
 from . import _lib, partition, smap, space
 
 f32 = np.float32
+_INT_MAX = 2**31 - 1
 
 
 class RingComm:
@@ -49,32 +50,41 @@ class RingComm:
   def exchange(self, send_left, send_right, recv_left, recv_right):
     """send_left -> left neighbour (arrives there as its `recv_right`),
     send_right -> right neighbour.  All tensors contiguous; sizes agreed
-    beforehand (exchange_counts)."""
+    beforehand (exchange_counts) or fixed (messages that carry their count)."""
+    self.exchange_many([(send_left, send_right, recv_left, recv_right)])
+
+  def exchange_many(self, messages):
+    """Several (send_left, send_right, recv_left, recv_right) groups in ONE
+    batched send/recv (one NCCL group launch)."""
     if self.world == 1:
-      recv_right.copy_(send_left)
-      recv_left.copy_(send_right)
+      for sl, sr, rl, rr in messages:
+        rr.copy_(sl)
+        rl.copy_(sr)
       return
-    sl, sr = self._stage(send_left), self._stage(send_right)
-    rl = recv_left if (self.direct or not recv_left.is_cuda) else torch.empty_like(recv_left, device='cpu')
-    rr = recv_right if (self.direct or not recv_right.is_cuda) else torch.empty_like(recv_right, device='cpu')
-    # With two ranks left == right: messages between one pair match in issue
-    # order, so receive-from-right is posted before receive-from-left.
-    ops = []
-    if sl.numel():
-      ops.append(dist.P2POp(dist.isend, sl, self.left, self.group))
-    if sr.numel():
-      ops.append(dist.P2POp(dist.isend, sr, self.right, self.group))
-    if rr.numel():
-      ops.append(dist.P2POp(dist.irecv, rr, self.right, self.group))
-    if rl.numel():
-      ops.append(dist.P2POp(dist.irecv, rl, self.left, self.group))
+    ops, staged = [], []
+    for send_left, send_right, recv_left, recv_right in messages:
+      sl, sr = self._stage(send_left), self._stage(send_right)
+      rl = recv_left if (self.direct or not recv_left.is_cuda) else torch.empty_like(recv_left, device='cpu')
+      rr = recv_right if (self.direct or not recv_right.is_cuda) else torch.empty_like(recv_right, device='cpu')
+      # With two ranks left == right: messages between one pair match in issue
+      # order, so receive-from-right is posted before receive-from-left.
+      if sl.numel():
+        ops.append(dist.P2POp(dist.isend, sl, self.left, self.group))
+      if sr.numel():
+        ops.append(dist.P2POp(dist.isend, sr, self.right, self.group))
+      if rr.numel():
+        ops.append(dist.P2POp(dist.irecv, rr, self.right, self.group))
+      if rl.numel():
+        ops.append(dist.P2POp(dist.irecv, rl, self.left, self.group))
+      staged.append((rl, recv_left, rr, recv_right))
     if ops:
       for w in dist.batch_isend_irecv(ops):
         w.wait()
-    if rl is not recv_left:
-      recv_left.copy_(rl)
-    if rr is not recv_right:
-      recv_right.copy_(rr)
+    for rl, recv_left, rr, recv_right in staged:
+      if rl is not recv_left:
+        recv_left.copy_(rl)
+      if rr is not recv_right:
+        recv_right.copy_(rr)
 
   def exchange_counts(self, n_to_left, n_to_right):
     """-> (n_from_left, n_from_right) as Python ints (host sync)."""
@@ -95,6 +105,14 @@ class RingComm:
       dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
       return bool(t.item() != 0)
     return bool(flag_tensor.item() != 0)
+
+  def max_int(self, value):
+    """Global maximum of a Python int (setup time; host sync)."""
+    if self.world == 1:
+      return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device='cuda' if self.direct else 'cpu')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+    return int(t.item())
 
   def sum(self, t):
     if self.world > 1:
@@ -170,12 +188,15 @@ class SlabDomain:
     """R_own / P_own: this rank's atoms (any order), CUDA tensors [n, dim]."""
     dev, dt = R_own.device, R_own.dtype
     n = R_own.shape[0]
-    cap = int(n * self.capacity_factor) + 1024
+    # capacities are sized from the largest slab so that the fixed-size rebuild
+    # messages have the same length on every rank
+    n_max = self.comm.max_int(n)
+    cap = int(n_max * self.capacity_factor) + 1024
     n_ghost_est = 0
     if self.comm.world > 1:
-      n_ghost_est = int(2 * n * self.ghost_width / self.width * self.capacity_factor) + 1024
+      n_ghost_est = int(2 * n_max * self.ghost_width / self.width * self.capacity_factor) + 1024
     self.cap = cap + n_ghost_est
-    self.cap_list = max(n_ghost_est, int(0.25 * n) + 1024)
+    self.cap_list = max(n_ghost_est, int(0.25 * n_max) + 1024)
     R = torch.zeros((self.cap, self.dim), dtype=dt, device=dev)
     P = torch.zeros_like(R)
     F = torch.zeros_like(R)
@@ -190,9 +211,26 @@ class SlabDomain:
     self.red = torch.zeros(_lib.RED_COUNT, dtype=torch.float64, device=dev)
     self.partials = smap.Scratch.get(self.cap, dev)
     self.sp = space.space_struct(space.get_spec(self.shift), self.dim, dt)
-    self.list_a = torch.empty(self.cap_list, dtype=torch.int32, device=dev)
-    self.list_b = torch.empty(self.cap_list, dtype=torch.int32, device=dev)
-    self.counters = torch.zeros(2, dtype=torch.int32, device=dev)
+    # Rebuild-time pipeline (no host round trip before the single read of `info`):
+    # fixed-capacity selection lists and messages that carry their own counts.
+    i32 = dict(dtype=torch.int32, device=dev)
+    self.cap_mig = int(0.02 * n_max) + 4096
+    self.list_a = torch.empty(self.cap_list, **i32)       # face atoms (sorted)
+    self.list_b = torch.empty(self.cap_list, **i32)
+    self.mig_a = torch.empty(self.cap_mig, **i32)         # leavers (sorted)
+    self.mig_b = torch.empty(self.cap_mig, **i32)
+    self.counters = torch.zeros(2, **i32)                 # face counts
+    self.mig_counters = torch.zeros(2, **i32)
+    self.info = torch.zeros(_lib.DD_INFO_COUNT, **i32)
+    self.info_host = torch.zeros(_lib.DD_INFO_COUNT, dtype=torch.int32).pin_memory()
+    self.mig_scratch = torch.empty(6 * self.cap_mig, **i32)
+    t = dict(dtype=dt, device=dev)
+    self.mig_pay = [torch.zeros((self.cap_mig, 3 * self.dim), **t) for _ in range(4)]     # out l, r; in l, r
+    self.mig_gid = [torch.zeros(self.cap_mig + 1, dtype=torch.int64, device=dev) for _ in range(4)]
+    self.face_msg = [torch.zeros((self.cap_list + 1, self.dim), **t) for _ in range(4)]   # out l, r; in l, r
+    self._send_l = torch.empty((self.cap_list, self.dim), **t)
+    self._send_r = torch.empty((self.cap_list, self.dim), **t)
+    self.info[_lib.DD_N_OWN] = n
     self._flag_dev = torch.zeros(1, dtype=torch.int64, device=dev)
     self._flag_host = torch.zeros(1, dtype=torch.int64).pin_memory()
     self._flag_event = torch.cuda.Event()
@@ -202,87 +240,62 @@ class SlabDomain:
     return st
 
   # -- pieces -----------------------------------------------------------------------
-  def _select(self, st, thr_a, thr_b):
-    """Indices (sorted, int32) of owned atoms with d < thr_a / d >= thr_b."""
-    self.counters.zero_()
-    _lib.call('jmd_dd_select', self.dtc, self.dim, st.n_own, _lib.ptr(st.R), self.axis,
-              float(self.lo), float(self.box[self.axis]), float(thr_a), float(thr_b),
-              _lib.ptr(self.list_a), _lib.ptr(self.list_b), _lib.ptr(self.counters),
-              self.cap_list, _lib.stream())
-    na, nb = (int(x) for x in self.counters.tolist())
-    if na > self.cap_list or nb > self.cap_list:
-      raise RuntimeError('domain decomposition list capacity exceeded')
-    a = torch.sort(self.list_a[:na]).values
-    b = torch.sort(self.list_b[:nb]).values
-    return a, b
-
-  def _pack(self, src, idx, ncomp):
-    out = torch.empty((idx.numel(), ncomp), dtype=src.dtype, device=src.device)
-    _lib.call('jmd_dd_pack', _lib.dtype_code(src.dtype), ncomp, idx.numel(),
-              _lib.ptr(idx), _lib.ptr(src), _lib.ptr(out), _lib.stream())
-    return out
+  def _select(self, st, thr_a, thr_b, list_a, list_b, counters):
+    """Sorted int32 indices of owned atoms with d < thr_a / d >= thr_b into the
+    fixed-capacity lists (padding: INT32_MAX); counts stay on the device."""
+    counters.zero_()
+    list_a.fill_(_INT_MAX)
+    list_b.fill_(_INT_MAX)
+    _lib.call('jmd_dd_select', self.dtc, self.dim, self.cap, _lib.ptr(self.info), _lib.ptr(st.R),
+              self.axis, float(self.lo), float(self.box[self.axis]), float(thr_a), float(thr_b),
+              _lib.ptr(list_a), _lib.ptr(list_b), _lib.ptr(counters), list_a.numel(), _lib.stream())
+    # sorted lists make the atom order (hence the summation order) reproducible
+    list_a.copy_(torch.sort(list_a).values)
+    list_b.copy_(torch.sort(list_b).values)
 
   def _migrate(self, st):
-    """Atoms that left [lo, lo + width) move to the neighbouring rank."""
-    if self.comm.world == 1:
-      return
-    go_l, go_r = self._select(st, 0.0, self.width)
-    n_from_l, n_from_r = self.comm.exchange_counts(go_l.numel(), go_r.numel())
-    dim = self.dim
-
-    def payload(idx):
-      # R | P | F per atom, plus the global id in a separate integer message
-      if idx.numel() == 0:
-        return (torch.empty((0, 3 * dim), dtype=self.dtype, device=self.device),
-                torch.empty((0,), dtype=torch.int64, device=self.device))
-      buf = torch.cat([self._pack(st.R, idx, dim), self._pack(st.P, idx, dim),
-                       self._pack(st.F, idx, dim)], dim=1).contiguous()
-      return buf, st.gid[idx.long()].contiguous()
-    sl, gl = payload(go_l)
-    sr, gr = payload(go_r)
-    rl = torch.empty((n_from_l, 3 * dim), dtype=self.dtype, device=self.device)
-    rr = torch.empty((n_from_r, 3 * dim), dtype=self.dtype, device=self.device)
-    gil = torch.empty((n_from_l,), dtype=torch.int64, device=self.device)
-    gir = torch.empty((n_from_r,), dtype=torch.int64, device=self.device)
-    self.comm.exchange(sl, sr, rl, rr)
-    self.comm.exchange(gl, gr, gil, gir)
-    # Compact in O(#leavers): move the tail atoms that stay into the holes left
-    # in the head, then append the arrivals.
-    n_old = st.n_own
-    leave = torch.cat([go_l, go_r]).long()
-    n_keep = n_old - leave.numel()
-    n_new = n_keep + n_from_l + n_from_r
-    if n_new > self.cap:
-      raise RuntimeError('slab capacity exceeded; raise capacity_factor')
-    if leave.numel():
-      tail = torch.arange(n_keep, n_old, device=self.device)
-      fillers = tail[~torch.isin(tail, leave)]
-      holes = leave[leave < n_keep]
-      if holes.numel():
-        for arr in (st.R, st.P, st.F, st.gid):
-          arr[holes] = arr[fillers]
-    if n_from_l + n_from_r:
-      inc = torch.cat([rl, rr], dim=0)
-      for arr, c0 in ((st.R, 0), (st.P, dim), (st.F, 2 * dim)):
-        arr[n_keep:n_new] = inc[:, c0:c0 + dim]
-      st.gid[n_keep:n_new] = torch.cat([gil, gir])
-    st.n_own = n_new
+    """Atoms that left [lo, lo + width) move to the neighbouring rank (device
+    side: select -> pack -> exchange -> compact; info[N_OWN] is updated)."""
+    s = _lib.stream()
+    self._select(st, 0.0, self.width, self.mig_a, self.mig_b, self.mig_counters)
+    out_l, out_r, in_l, in_r = self.mig_pay
+    g_out_l, g_out_r, g_in_l, g_in_r = self.mig_gid
+    _lib.call('jmd_dd_pack_migrate', self.dtc, self.dim, self.cap_mig, _lib.ptr(self.mig_a),
+              _lib.ptr(self.mig_b), _lib.ptr(self.mig_counters), _lib.ptr(st.R), _lib.ptr(st.P),
+              _lib.ptr(st.F), _lib.ptr(st.gid), _lib.ptr(out_l), _lib.ptr(out_r), _lib.ptr(g_out_l),
+              _lib.ptr(g_out_r), s)
+    self.comm.exchange_many([(out_l, out_r, in_l, in_r), (g_out_l, g_out_r, g_in_l, g_in_r)])
+    _lib.call('jmd_dd_compact', self.dtc, self.dim, self.cap, self.cap_mig, _lib.ptr(self.mig_a),
+              _lib.ptr(self.mig_b), _lib.ptr(self.mig_counters), _lib.ptr(in_l), _lib.ptr(g_in_l),
+              _lib.ptr(in_r), _lib.ptr(g_in_r), _lib.ptr(st.R), _lib.ptr(st.P), _lib.ptr(st.F),
+              _lib.ptr(st.gid), _lib.ptr(self.mig_scratch), _lib.ptr(self.info), s)
 
   def _ghosts(self, st):
-    """Select face atoms, exchange the ghost layer, remember the send lists."""
-    if self.comm.world == 1:
-      st.n_ghost = 0
-      self._lists = None
-      return
-    face_l, face_r = self._select(st, self.ghost_width, self.width - self.ghost_width)
-    n_from_l, n_from_r = self.comm.exchange_counts(face_l.numel(), face_r.numel())
-    if st.n_own + n_from_l + n_from_r > self.cap:
-      raise RuntimeError('slab capacity exceeded (ghosts); raise capacity_factor')
-    self._lists = (face_l, face_r, n_from_l, n_from_r)
+    """Select face atoms and exchange the ghost layer; ends with the one host
+    read of a rebuild (`info`: owned / face / ghost counts and error bits)."""
+    s = _lib.stream()
+    self._select(st, self.ghost_width, self.width - self.ghost_width, self.list_a, self.list_b,
+                 self.counters)
+    out_l, out_r, in_l, in_r = self.face_msg
+    for k, (idx, out) in enumerate(((self.list_a, out_l), (self.list_b, out_r))):
+      _lib.call('jmd_dd_pack_counted', self.dtc, self.dim, self.cap_list, _lib.ptr(idx),
+                _lib.ptr(self.counters[k:]), _lib.ptr(st.R), _lib.ptr(out), s)
+    self.comm.exchange(out_l, out_r, in_l, in_r)
+    _lib.call('jmd_dd_place', self.dtc, self.dim, self.cap, self.cap_list, _lib.ptr(self.counters),
+              _lib.ptr(in_l), _lib.ptr(in_r), _lib.ptr(st.R), _lib.ptr(self.info), s)
+    self.info_host.copy_(self.info, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    info = self.info_host.tolist()
+    if info[_lib.DD_ERROR] & _lib.DD_ELIST:
+      raise RuntimeError('domain decomposition list capacity exceeded')
+    if info[_lib.DD_ERROR] & _lib.DD_ECAP:
+      raise RuntimeError('slab capacity exceeded; raise capacity_factor')
+    st.n_own = info[_lib.DD_N_OWN]
+    n_from_l, n_from_r = info[_lib.DD_FROM_L], info[_lib.DD_FROM_R]
     st.n_ghost = n_from_l + n_from_r
-    self._send_l = torch.empty((face_l.numel(), self.dim), dtype=self.dtype, device=self.device)
-    self._send_r = torch.empty((face_r.numel(), self.dim), dtype=self.dtype, device=self.device)
-    self._halo(st)
+    self._lists = (self.list_a[:info[_lib.DD_FACE_L]], self.list_b[:info[_lib.DD_FACE_R]],
+                   n_from_l, n_from_r)
+    self.last_info = info
 
   def ghost_ids(self, st):
     """Global ids of the ghost atoms (diagnostics; one extra exchange)."""
@@ -296,11 +309,12 @@ class SlabDomain:
     return st.gid[o:o + st.n_ghost]
 
   def _halo(self, st):
-    """Face positions -> neighbours' ghost slots (every step)."""
+    """Face positions -> neighbours' ghost slots (every step; exact sizes known
+    on the host since the last rebuild)."""
     if self._lists is None:
       return
     face_l, face_r, n_from_l, n_from_r = self._lists
-    sl, sr = self._send_l, self._send_r
+    sl, sr = self._send_l[:face_l.numel()], self._send_r[:face_r.numel()]
     for idx, out in ((face_l, sl), (face_r, sr)):
       _lib.call('jmd_dd_pack', self.dtc, self.dim, idx.numel(), _lib.ptr(idx), _lib.ptr(st.R),
                 _lib.ptr(out), _lib.stream())
@@ -308,11 +322,12 @@ class SlabDomain:
     self.comm.exchange(sl, sr, st.R[o:o + n_from_l], st.R[o + n_from_l:o + n_from_l + n_from_r])
 
   def _rebuild(self, st, first=False):
-    if not first:
-      self._migrate(st)
+    if self.comm.world > 1:
+      self._migrate(st)       # also fixes up atoms handed in slightly outside the slab
+      self._ghosts(st)
     else:
-      self._migrate_initial(st)
-    self._ghosts(st)
+      st.n_ghost = 0
+      self._lists = None
     n_loc = st.n_own + st.n_ghost
     Rl = st.R[:n_loc]
     if self.nbrs is None:
@@ -327,10 +342,6 @@ class SlabDomain:
       _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 0, s)
       _lib.call('jmd_nbr_export', ws.ref(), pp, 0, s)
     self.rebuilds += 1
-
-  def _migrate_initial(self, st):
-    """The caller may hand every rank atoms slightly outside its slab."""
-    self._migrate(st)
 
   def _force(self, st, kick):
     ws = self.nbrs._ws
