@@ -112,11 +112,18 @@ typedef struct {
    * reference grid above only feeds cell_list_capacity / CELL_LIST_OVERFLOW;
    * cell_count / cell_start / cell_cursor are sized for the fine grid. */
   int32_t fine_cps[3];     /* fine cells per side */
-  int32_t n_fine_cells;
+  int32_t n_fine_cells;    /* storage cells: prod_k ceil(fine_cps[k] / brick) * brick */
   int32_t stencil_w;       /* stencil half width in fine cells (1, 2 or 3) */
-  int32_t _pad2;
+  int32_t no_filter;       /* 1: disable the stencil scan's contracted pre-filter (exact test on every candidate) */
   double fine_cell_size[3];
   int32_t* ref_count;      /* [n_cells] atoms per REFERENCE cell */
+  /* storage order of the cells: bricks of (1 << brick_shift)^dim cells (0 = the
+   * reference's x-fastest order).  n_fine_cells counts STORAGE cells, i.e. the
+   * grid padded to whole bricks.  ref_start: [n_cells + 1] scratch (prefix sums
+   * in reference order, for the slot rotation of partition.py:441). */
+  int32_t brick_shift;
+  int32_t _pad3;
+  int32_t* ref_start;
 } jmd_nbr_t;
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */

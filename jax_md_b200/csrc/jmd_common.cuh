@@ -90,6 +90,11 @@ struct Space {
     T r = rint_magic(d * inv_side[k]);
     return d - side_f[k] * r;
   }
+  // the same on an already formed difference
+  __device__ __forceinline__ T wrap_fast(T d, int k) const {
+    T r = rint_magic(d * inv_side[k]);
+    return d - side_f[k] * r;
+  }
   // shift_fn (space.py:250-252 / 268-270)
   __device__ __forceinline__ T shift(T r, T dr, int k) const {
     T s = add_rn(r, dr);

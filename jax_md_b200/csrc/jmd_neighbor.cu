@@ -38,17 +38,22 @@ constexpr int NB = 256;           // threads per block, every kernel here
 constexpr int NWARP = NB / 32;
 constexpr int SCAN_TILE = NB * 8;
 constexpr int RANK_LIMIT = 4096;  // cells above this keep arrival order
+constexpr int CELL_DIRTY = 1 << 30;  // cell_cursor bit: the cell holds an atom outside its cell's geometry
 
 template <typename T, int DIM>
 struct NbrP {
   int n, format, use_cells, mask_self, always_rebuild, n_cells, cell_capacity, m_int;
   int cps[3];          // INTERNAL (fine) search grid
+  int bs, nb[3], rotate;   // storage order: bricks of (1 << bs)^DIM cells, nb bricks per side
+  int* ref_start;          // [n_ref_cells + 1] exclusive scan of the counts in REFERENCE hash order
   int ref_cps[3], n_ref_cells, sw;   // reference grid (capacity flag only), stencil half width
   int count_only, two_sided, rev_only, n_rows, no_public_idx;
   long long n_pad, max_occupancy;
   T cell_size[DIM];    // fine cell size
   T ref_cell_size[DIM];
   T cutoff_sq, threshold_sq, band, far;
+  T f_lo, f_hi;        // pre-filter: a2 < f_lo accepts, a2 > f_hi rejects, else exact test
+  int filter;          // pre-filter usable (periodic, cps >= 2*sw+3 on every axis)
   Space<T, DIM> sp;
   int *cell_count, *cell_start, *cell_cursor, *scan_tmp, *hash, *tmp_ids, *perm, *inv_perm, *ref_count;
   typename Vec4<T>::type* pos_sorted;
@@ -122,6 +127,43 @@ __device__ __forceinline__ typename Vec4<T>::type load_atom(const NbrP<T, DIM>& 
   return make_v4<T>(r[0], r[1], z, w);
 }
 
+
+// ---- cell storage order ---------------------------------------------------------
+// The reference hashes cells x-fastest (partition.py:212-224); that order only
+// matters for (a) the order candidates are visited in -- the stencil walk below
+// follows it explicitly -- and (b) the slot rotation of partition.py:441, which
+// needs the reference-order prefix sums (ref_start).  WHERE a cell's atoms live in
+// the cell-sorted arrays is ours to choose: cells are stored brick by brick
+// ((1 << bs)^DIM cells per brick, bricks x-fastest) so that the 32 slots of a warp
+// and the 256 of a block are spatially compact and the neighbour gathers of the
+// force kernel stay inside the L1.  bs == 0 is the plain reference order.
+template <typename T, int DIM>
+__device__ __forceinline__ int cell_id(const NbrP<T, DIM>& P, const int (&v)[3]) {
+  if (P.bs == 0) return v[0] + P.cps[0] * (v[1] + (DIM == 3 ? P.cps[1] * v[2] : 0));
+  const int bs = P.bs, m = (1 << bs) - 1;
+  const int brick = (v[0] >> bs) + P.nb[0] * ((v[1] >> bs) + (DIM == 3 ? P.nb[1] * (v[2] >> bs) : 0));
+  const int inner = (v[0] & m) | ((v[1] & m) << bs) | (DIM == 3 ? (v[2] & m) << (2 * bs) : 0);
+  return (brick << (DIM * bs)) | inner;
+}
+
+template <typename T, int DIM>
+__device__ __forceinline__ void cell_coords(const NbrP<T, DIM>& P, int id, int (&v)[3]) {
+  if (P.bs == 0) {
+    v[0] = id % P.cps[0];
+    v[1] = (id / P.cps[0]) % P.cps[1];
+    v[2] = DIM == 3 ? id / (P.cps[0] * P.cps[1]) : 0;
+    return;
+  }
+  const int bs = P.bs, m = (1 << bs) - 1;
+  const int inner = id & ((1 << (DIM * bs)) - 1);
+  const int brick = id >> (DIM * bs);
+  const int b0 = brick % P.nb[0], b1 = (brick / P.nb[0]) % P.nb[1];
+  const int b2 = DIM == 3 ? brick / (P.nb[0] * P.nb[1]) : 0;
+  v[0] = (b0 << bs) | (inner & m);
+  v[1] = (b1 << bs) | ((inner >> bs) & m);
+  v[2] = DIM == 3 ? (b2 << bs) | ((inner >> (2 * bs)) & m) : 0;
+}
+
 // ---- phase: skin predicate (partition.py:1146-1154) ------------------------------
 template <typename T, int DIM>
 __device__ bool ph_skin(const NbrP<T, DIM>& P) {
@@ -159,23 +201,29 @@ template <typename T, int DIM>
 __device__ void ph_hash(const NbrP<T, DIM>& P) {
   for (int i = gtid(); i < P.n; i += gthreads()) {
     const T* r = P.position + (size_t)i * DIM;
-    int h = 0, mult = 1, hr = 0, multr = 1;
+    int hr = 0, multr = 1;
+    int cv[3] = {0, 0, 0};
+    bool regular = true;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
       int ci = (int)div_rn(r[k], P.cell_size[k]);
+      // "regular": the coordinate lies in the primary box and in the cell it is
+      // binned to (no wrap by the mod below) -- what the scan's pre-filter assumes
+      regular = regular && (r[k] >= T(0)) && (ci >= 0) && (ci < P.cps[k]);
       ci %= P.cps[k];
       if (ci < 0) ci += P.cps[k];
-      h += ci * mult;
-      mult *= P.cps[k];
+      cv[k] = ci;
       int cr = (int)div_rn(r[k], P.ref_cell_size[k]);
       cr %= P.ref_cps[k];
       if (cr < 0) cr += P.ref_cps[k];
       hr += cr * multr;
       multr *= P.ref_cps[k];
     }
+    const int h = cell_id(P, cv);
     P.hash[i] = h;
     atomicAdd(&P.cell_count[h], 1);
     atomicAdd(&P.ref_count[hr], 1);
+    if (!regular) atomicOr(&P.cell_cursor[h], CELL_DIRTY);   // exact test for this cell
   }
 }
 
@@ -290,7 +338,7 @@ template <typename T, int DIM>
 __device__ void ph_scatter(const NbrP<T, DIM>& P) {
   for (int i = gtid(); i < P.n; i += gthreads()) {
     int h = P.hash[i];
-    int pos = P.cell_start[h] + atomicAdd(&P.cell_cursor[h], 1);
+    int pos = P.cell_start[h] + (atomicAdd(&P.cell_cursor[h], 1) & (CELL_DIRTY - 1));
     P.tmp_ids[pos] = i;
     P.inv_perm[i] = pos;
   }
@@ -307,7 +355,7 @@ __device__ void ph_scatter(const NbrP<T, DIM>& P) {
 template <typename T, int DIM>
 __device__ void ph_rank_sort(const NbrP<T, DIM>& P) {
   const int cap = P.cell_capacity > 0 ? P.cell_capacity : 1;
-  const bool rotate = P.n_cells == P.n_ref_cells;
+  const bool rotate = P.rotate != 0;
   for (int i = gtid(); i < P.n; i += gthreads()) {
     int h = P.hash[i];
     int s = P.cell_start[h];
@@ -320,7 +368,14 @@ __device__ void ph_rank_sort(const NbrP<T, DIM>& P) {
       rank = P.inv_perm[i] - s;
     }
     if (rotate) {
-      const int room = cap - s % cap;
+      // sorted rank of the cell's first atom in the REFERENCE's hash order
+      int s_ref = s;
+      if (P.bs > 0) {
+        int v[3];
+        cell_coords(P, h, v);
+        s_ref = P.ref_start[v[0] + P.cps[0] * (v[1] + (DIM == 3 ? P.cps[1] * v[2] : 0))];
+      }
+      const int room = cap - s_ref % cap;
       const int r0 = room < c ? room : 0;
       rank -= r0;
       rank = rank < 0 ? rank + c : rank;
@@ -420,7 +475,85 @@ __device__ __forceinline__ void publish_counts(long long* state, long long my_k,
 // list is written by neighbouring lanes at neighbouring addresses.
 // MODE: 0 = forward test only (Sparse formats), 1 = forward + reverse inside
 // the rounding band (Dense).
-template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC, int WSTAT>
+// Pins a loop-invariant value in a register: the empty asm makes it opaque, so
+// ptxas cannot rematerialise it (recompute / reload constants) inside the loop.
+__device__ __forceinline__ void keep_in_register(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void keep_in_register(double& x) { asm volatile("" : "+d"(x)); }
+__device__ __forceinline__ void keep_in_register(int& x) { asm volatile("" : "+r"(x)); }
+
+// keep = (a2 < lo) && rank != self;  if (keep && off < off_end) { nl[off] = rank; off += n_pad; }
+// k += keep.  `off` is a 32-bit ELEMENT offset into nl (m_int * n_pad < 2^32 is checked
+// on the host).  Spelled in PTX so the append stays a handful of predicated instructions
+// (ptxas otherwise turns the selects into a chain of moves or a branch).
+#define JMD_APPEND_ASM(FT, FC)                                                                   \
+  asm volatile(                                                                                  \
+      "{\n\t.reg .pred pk, pw;\n\t.reg .u64 ad;\n\t"                                           \
+      "setp.lt." FT " pk, %2, %3;\n\t"                                                          \
+      "setp.ne.and.s32 pk, %4, %5, pk;\n\t"                                                     \
+      "setp.lt.and.u32 pw, %0, %6, pk;\n\t"                                                     \
+      "mad.wide.u32 ad, %0, 4, %8;\n\t"                                                         \
+      "@pw st.global.s32 [ad], %4;\n\t"                                                         \
+      "@pw add.u32 %0, %0, %7;\n\t"                                                             \
+      "@pk add.s32 %1, %1, 1;\n\t}"                                                             \
+      : "+r"(off), "+r"(k)                                                                       \
+      : FC(a2), FC(lo), "r"(rank), "r"(self), "r"(off_end), "r"(n_pad), "l"(nl)                  \
+      : "memory")
+__device__ __forceinline__ void append_if_below(float a2, float lo, int rank, int self, unsigned off_end,
+                                                unsigned n_pad, int* nl, unsigned& off, int& k) {
+  JMD_APPEND_ASM("f32", "f");
+}
+__device__ __forceinline__ void append_if_below(double a2, double lo, int rank, int self, unsigned off_end,
+                                                unsigned n_pad, int* nl, unsigned& off, int& k) {
+  JMD_APPEND_ASM("f64", "d");
+}
+#undef JMD_APPEND_ASM
+
+// The reference's candidate test on one (home, candidate) pair, bit for bit:
+// forward d2(R_i, R_c) < cutoff^2 (partition.py:945-951) and, for Dense (MODE 1),
+// the reverse-orientation re-test inside the rounding band (partition.py:960-980).
+template <typename T, int DIM, int MODE, bool PERIODIC>
+__device__ __forceinline__ bool exact_keep(const NbrP<T, DIM>& P, const T (&hp)[3],
+                                           const typename Vec4<T>::type& cv, const T (&hh)[3],
+                                           const T (&qq)[3], T c2) {
+  // forward displacement d(R_i, R_c), exact (space.py:213-235)
+  T dd[3];
+  dd[0] = sub_rn(hp[0], cv.x);
+  dd[1] = sub_rn(hp[1], cv.y);
+  dd[2] = DIM == 3 ? sub_rn(hp[2], cv.z) : T(0);
+  T d2;
+  bool slow = false;
+  if (!PERIODIC) {
+    d2 = mul_rn(dd[0], dd[0]);
+#pragma unroll
+    for (int d = 1; d < DIM; ++d) d2 = add_rn(d2, mul_rn(dd[d], dd[d]));
+  } else {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) slow = slow || !(fabs(dd[d]) <= qq[d]);
+    if (!slow) {
+      // |d| <= L/4: mod() is the identity on fl(d + h) (see Space::disp)
+      T m0 = sub_rn(add_rn(dd[0], hh[0]), hh[0]);
+      d2 = mul_rn(m0, m0);
+#pragma unroll
+      for (int d = 1; d < DIM; ++d) {
+        T m = sub_rn(add_rn(dd[d], hh[d]), hh[d]);
+        d2 = add_rn(d2, mul_rn(m, m));
+      }
+    } else {
+      const T cp[3] = {cv.x, cv.y, cv.z};
+      d2 = dist2_exact<T, DIM>(P.sp, hp, cp);
+    }
+  }
+  bool keep = d2 < c2;
+  if (MODE == 1 && PERIODIC) {
+    if (slow || (fabs(d2 - c2) <= P.band)) {
+      const T cp[3] = {cv.x, cv.y, cv.z};
+      keep = keep && (dist2_exact<T, DIM>(P.sp, cp, hp) < c2);
+    }
+  }
+  return keep;
+}
+
+template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC, int WSTAT, bool FILTER, bool COUNT>
 __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
   using V4 = typename Vec4<T>::type;
   const int lane = threadIdx.x & 31;
@@ -436,6 +569,7 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
   T hh[3], qq[3];
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { hh[d] = P.sp.half[d]; qq[d] = P.sp.quarter[d]; }
+  const V4* __restrict__ const pos = P.pos_sorted;
   for (int wbase = gtid() - lane; wbase < P.n; wbase += gthreads()) {
     const int slot = wbase + lane;
     long long my_k = 0, my_tot = 0;
@@ -448,20 +582,28 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
       const V4 hv = P.pos_sorted[slot];
       const T hp[3] = {hv.x, hv.y, hv.z};
       const int c = P.hash[hid];              // own (fine) cell
-      const int cx_n = P.cps[0], cy_n = P.cps[1];
       int cc[3];
-      cc[0] = c % cx_n;
-      cc[1] = (c / cx_n) % cy_n;
-      cc[2] = DIM == 3 ? c / (cx_n * cy_n) : 0;
-      const int self = self_on ? slot : -1;
+      cell_coords(P, c, cc);
+      int self = self_on ? slot : -1;
+      keep_in_register(self);
+      const bool home_dirty = FILTER ? (__ldg(&P.cell_cursor[c]) & CELL_DIRTY) != 0 : false;
       int k = 0, kl = 0;
-      int* out = P.nl + slot;
+      int* const out = P.nl + slot;
+      // 32-bit element offsets of this slot's next / past-the-end row entry
+      unsigned off = (unsigned)slot;
+      int off_end_i = (int)((unsigned)kmax * (unsigned)P.n_pad + (unsigned)slot);
+      keep_in_register(off_end_i);
+      const unsigned off_end = (unsigned)off_end_i;
       for (int s0 = -w; s0 <= w; ++s0)
       for (int s1 = -w; s1 <= w; ++s1)
       for (int s2 = -wz; s2 <= wz; ++s2) {
         const int sh[3] = {s0, s1, s2};
         float gap2 = 0.f;
-        int h = 0, mult = 1;
+        int sv[3] = {0, 0, 0};
+        // FILTER: home position moved into the stencil cell's periodic image, so
+        // hs - R_c is the minimum-image displacement up to rounding (valid for
+        // regular atoms: |hs - R_c| <= (w+1) cell sizes < L/2)
+        T hs[3] = {hp[0], hp[1], hp[2]};
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
           if (WSTAT != 1) {
@@ -470,58 +612,60 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
             gap2 += g * g;
           }
           int v = cc[d] + sh[d];
-          v = v < 0 ? v + P.cps[d] : (v >= P.cps[d] ? v - P.cps[d] : v);
-          h += v * mult;
-          mult *= P.cps[d];
+          if (v < 0) { v += P.cps[d]; hs[d] = hp[d] + P.sp.side[d]; }
+          else if (v >= P.cps[d]) { v -= P.cps[d]; hs[d] = hp[d] - P.sp.side[d]; }
+          sv[d] = v;
         }
+        const int h = cell_id(P, sv);
         if (WSTAT != 1 && gap2 > gap_limit) continue;
         const int start = __ldg(&P.cell_start[h]);
         const int end = __ldg(&P.cell_start[h + 1]);
-        const V4* cptr = P.pos_sorted + start;
-        for (int rank = start; rank < end; ++rank, ++cptr) {
-          const V4 cv = *cptr;
-          // forward displacement d(R_i, R_c), exact (space.py:213-235)
-          T dd[3];
-          dd[0] = sub_rn(hp[0], cv.x);
-          dd[1] = sub_rn(hp[1], cv.y);
-          dd[2] = DIM == 3 ? sub_rn(hp[2], cv.z) : T(0);
-          T d2;
-          bool slow = false;
-          if (!periodic) {
-            d2 = mul_rn(dd[0], dd[0]);
-#pragma unroll
-            for (int d = 1; d < DIM; ++d) d2 = add_rn(d2, mul_rn(dd[d], dd[d]));
-          } else {
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) slow = slow || !(fabs(dd[d]) <= qq[d]);
-            if (!slow) {
-              // |d| <= L/4: mod() is the identity on fl(d + h) (see Space::disp)
-              T m0 = sub_rn(add_rn(dd[0], hh[0]), hh[0]);
-              d2 = mul_rn(m0, m0);
-#pragma unroll
-              for (int d = 1; d < DIM; ++d) {
-                T m = sub_rn(add_rn(dd[d], hh[d]), hh[d]);
-                d2 = add_rn(d2, mul_rn(m, m));
-              }
-            } else {
-              const T cp[3] = {cv.x, cv.y, cv.z};
-              d2 = dist2_exact<T, DIM>(P.sp, hp, cp);
-            }
-          }
-          bool keep = d2 < c2;
-          if (MODE == 1 && periodic) {
-            if (slow || (fabs(d2 - c2) <= P.band)) {
-              const T cp[3] = {cv.x, cv.y, cv.z};
-              keep = keep && (dist2_exact<T, DIM>(P.sp, cp, hp) < c2);
-            }
-          }
-          keep = keep && (rank != self);
-          if (keep) {
-            if (k < kmax) { *out = rank; out += P.n_pad; }
-            ++k;
-            if (ORDERED) kl += (__ldg(&P.perm[rank]) < hid);
+        T lo_c = P.f_lo, hi_c = P.f_hi;
+        if (FILTER) {
+          if (home_dirty || (__ldg(&P.cell_cursor[h]) & CELL_DIRTY)) {
+            lo_c = T(-1);                       // a2 >= 0: never accepted unseen
+            hi_c = (T)INFINITY;                 // never rejected unseen
           }
         }
+        if (FILTER) {
+          // Branch-free common path: contracted arithmetic, predicated append.  The
+          // exact reference arithmetic runs only inside the rounding band around
+          // cutoff^2 (or for cells flagged dirty), a rarely taken branch.
+          T h0 = hs[0], h1 = hs[1], h2 = hs[2];
+          keep_in_register(h0); keep_in_register(h1); keep_in_register(h2);
+          keep_in_register(lo_c); keep_in_register(hi_c);
+          for (int rank = start; rank < end; ++rank) {
+            const V4 cv = pos[rank];
+            const T ax = h0 - cv.x, ay = h1 - cv.y;
+            T a2 = ax * ax + ay * ay;
+            if (DIM == 3) { const T az = h2 - cv.z; a2 += az * az; }
+            if (!(a2 < lo_c) && !(a2 > hi_c))     // rare: inside the band / dirty cell
+              a2 = exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2) ? T(-2) : (T)INFINITY;
+            const int k_before = k;
+            append_if_below(a2, lo_c, rank, self, off_end, (unsigned)P.n_pad, P.nl, off, k);
+            const bool keep = k != k_before;
+            if (ORDERED && COUNT) { if (keep) kl += (__ldg(&P.perm[rank]) < hid); }
+          }
+        } else {
+          for (int rank = start; rank < end; ++rank) {
+            const V4 cv = pos[rank];
+            bool keep = exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2);
+            keep = keep && (rank != self);
+            if (keep) {
+              if (off < off_end) { P.nl[off] = rank; off += (unsigned)P.n_pad; }
+              ++k;
+              if (ORDERED && COUNT) kl += (__ldg(&P.perm[rank]) < hid);
+            }
+          }
+        }
+      }
+      if (ORDERED && !COUNT) {
+        // entries whose atom id is below the row's id (OrderedSparse keeps those,
+        // partition.py:1021-1022): counted from the finished row, off the hot loop
+        const int kk_end = k < kmax ? k : kmax;
+#pragma unroll 4
+        for (int kk = 0; kk < kk_end; ++kk)
+          kl += (__ldg(&P.perm[__ldcg(out + (size_t)kk * P.n_pad)]) < hid);
       }
       P.cnt[slot] = k;
       P.cnt_lower[slot] = kl;
@@ -576,22 +720,6 @@ __device__ void ph_build_all_pairs(const NbrP<T, DIM>& P) {
   }
 }
 
-template <typename T, int DIM>
-__device__ void ph_build(const NbrP<T, DIM>& P) {
-  if (!P.use_cells) { ph_build_all_pairs<T, DIM>(P); return; }
-#define JMD_SCAN(W)                                                                        \
-  if (P.sp.periodic) {                                                                     \
-    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, true, W>(P);       \
-    else if (P.format == JMD_SPARSE) ph_build_cells<T, DIM, 0, false, true, W>(P);         \
-    else ph_build_cells<T, DIM, 1, false, true, W>(P);                                     \
-  } else {                                                                                 \
-    if (P.format == JMD_ORDERED_SPARSE) ph_build_cells<T, DIM, 0, true, false, W>(P);      \
-    else ph_build_cells<T, DIM, 0, false, false, W>(P);                                    \
-  }
-  if (P.sw == 1) { JMD_SCAN(1) } else { JMD_SCAN(0) }
-#undef JMD_SCAN
-}
-
 // ---- phases: export to the public formats ------------------------------------------------
 
 // per-atom (user order) number of public sparse entries
@@ -637,10 +765,19 @@ __device__ void ph_export(const NbrP<T, DIM>& P, Smem& sm) {
       const int rows = min(32, cmax - k0);       // rows of this tile that hold data
       __syncwarp();
       if (slot < P.n) {
+        // row entries (coalesced along slots) -> atom ids (perm gather), 8 independent
+        // load->gather chains in flight per lane; the tile holds ATOM IDS
         const int* src = P.nl + (size_t)k0 * P.n_pad + slot;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          if (r < rows) tile[r][lane] = __ldcs(src + (size_t)r * P.n_pad);
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+          int jv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)     // entries past this slot's own row are garbage
+            jv[u] = (k0 + r0 + u < c_l) ? __ldcs(src + (size_t)(r0 + u) * P.n_pad) : -1;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) jv[u] = jv[u] >= 0 ? __ldg(&P.perm[jv[u]]) : P.n;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) tile[r0 + u][lane] = jv[u];
         }
       }
       __syncwarp();
@@ -651,8 +788,7 @@ __device__ void ph_export(const NbrP<T, DIM>& P, Smem& sm) {
         if (a < 0) break;                            // slots beyond n (uniform)
         const int c = __shfl_sync(0xffffffffu, c_l, r);
         const bool in_row = k < c;
-        int v = P.n;
-        if (in_row) v = __ldg(&P.perm[tile[lane][r]]);
+        const int v = in_row ? tile[lane][r] : P.n;
         if (dense) {
           if (k < cap) P.idx[(size_t)a * cap + k] = v;
         } else {
@@ -699,6 +835,15 @@ __device__ void ph_finalize(const NbrP<T, DIM>& P) {
   }
 }
 
+// the reference-order prefix sums are needed only when cells are stored in brick
+// order AND the slot rotation applies (search grid == reference grid)
+template <typename T, int DIM>
+__device__ __forceinline__ bool ref_scan(const NbrP<T, DIM>& P) { return P.bs > 0 && P.rotate; }
+template <typename T, int DIM>
+__device__ __forceinline__ int* ref_sums(const NbrP<T, DIM>& P) {
+  return P.scan_tmp + (P.n_cells / SCAN_TILE + 2);     // behind the storage-order tile sums
+}
+
 // ---- one ordinary kernel per phase (allocate path / gated fallback) -----------------------
 enum Phase { PH_ZERO, PH_HASH, PH_SCAN1, PH_SCAN2, PH_SCAN3, PH_SCATTER, PH_RANK, PH_INVPERM,
              PH_IDENTITY, PH_PACK, PH_BUILD_RESET, PH_BUILD, PH_SP_COUNTS, PH_SP_SCAN1,
@@ -712,16 +857,26 @@ __global__ void __launch_bounds__(NB, 3) k_phase(NbrP<T, DIM> P, int gated) {
   switch (PHASE) {
     case PH_ZERO: ph_zero(P); break;
     case PH_HASH: ph_hash(P); break;
-    case PH_SCAN1: ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, nullptr, sm); ph_ref_max(P); break;
-    case PH_SCAN2: ph_scan_top<int>(P.scan_tmp, P.n_cells, sm); break;
-    case PH_SCAN3: ph_scan_apply<int, int>(P.cell_count, P.n_cells, P.scan_tmp, P.cell_start, sm); break;
+    case PH_SCAN1:
+      ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, nullptr, sm);
+      if (ref_scan(P)) ph_scan_tiles<int, int>(P.ref_count, P.n_ref_cells, ref_sums(P), nullptr, sm);
+      ph_ref_max(P);
+      break;
+    case PH_SCAN2:
+      ph_scan_top<int>(P.scan_tmp, P.n_cells, sm);
+      if (ref_scan(P)) ph_scan_top<int>(ref_sums(P), P.n_ref_cells, sm);
+      break;
+    case PH_SCAN3:
+      ph_scan_apply<int, int>(P.cell_count, P.n_cells, P.scan_tmp, P.cell_start, sm);
+      if (ref_scan(P)) ph_scan_apply<int, int>(P.ref_count, P.n_ref_cells, ref_sums(P), P.ref_start, sm);
+      break;
     case PH_SCATTER: ph_scatter(P); break;
     case PH_RANK: ph_rank_sort(P); break;
     case PH_INVPERM: ph_inv_perm(P); break;
     case PH_IDENTITY: ph_identity_sort(P); break;
     case PH_PACK: ph_pack(P); break;
     case PH_BUILD_RESET: ph_build_reset(P); break;
-    case PH_BUILD: ph_build(P); break;
+    case PH_BUILD: break;   // own kernels: k_nbr_stencil_scan / k_nbr_all_pairs
     case PH_SP_COUNTS: ph_sparse_counts(P); break;
     case PH_SP_SCAN1: ph_scan_tiles<int, long long>(P.tmp_ids, P.n, sp_sums, nullptr, sm); break;
     case PH_SP_SCAN2: ph_scan_top<long long>(sp_sums, P.n, sm); break;
@@ -740,10 +895,53 @@ inline int grid_for(long long work_items, int per_block, int cap_blocks) {
 }
 
 // The two heavy phases get their own kernel names so profiles are readable.
-template <typename T, int DIM>
+// FMT: 0 Dense (forward + reverse test), 1 Sparse, 2 OrderedSparse.  Each variant
+// is its own kernel so that it gets its own register allocation.
+template <typename T, int DIM, int FMT, bool PERIODIC, int W, bool FILTER>
 __global__ void __launch_bounds__(NB, 3) k_nbr_stencil_scan(NbrP<T, DIM> P, int gated) {
   if (gated && P.state[ST_REBUILD] == 0) return;
-  ph_build(P);
+  // COUNT (OrderedSparse occupancy pass of allocate: no rows are written, so the
+  // id-lower count has to be taken inside the candidate loop)
+  if (FMT == 2 && P.count_only)
+    ph_build_cells<T, DIM, (FMT == 0 && PERIODIC) ? 1 : 0, FMT == 2, PERIODIC, W, FILTER, true>(P);
+  else
+    ph_build_cells<T, DIM, (FMT == 0 && PERIODIC) ? 1 : 0, FMT == 2, PERIODIC, W, FILTER, false>(P);
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(NB, 3) k_nbr_all_pairs(NbrP<T, DIM> P, int gated) {
+  if (gated && P.state[ST_REBUILD] == 0) return;
+  ph_build_all_pairs<T, DIM>(P);
+}
+
+template <typename T, int DIM, int FMT, bool PERIODIC>
+void launch_scan_wf(const NbrP<T, DIM>& P, int gated, int grid, cudaStream_t stream) {
+  if (PERIODIC && P.filter) {
+    if (P.sw == 1) k_nbr_stencil_scan<T, DIM, FMT, PERIODIC, 1, PERIODIC><<<grid, NB, 0, stream>>>(P, gated);
+    else k_nbr_stencil_scan<T, DIM, FMT, PERIODIC, 0, PERIODIC><<<grid, NB, 0, stream>>>(P, gated);
+  } else {
+    if (P.sw == 1) k_nbr_stencil_scan<T, DIM, FMT, PERIODIC, 1, false><<<grid, NB, 0, stream>>>(P, gated);
+    else k_nbr_stencil_scan<T, DIM, FMT, PERIODIC, 0, false><<<grid, NB, 0, stream>>>(P, gated);
+  }
+}
+
+template <typename T, int DIM>
+void launch_scan(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+  if (!P.use_cells) {
+    k_nbr_all_pairs<T, DIM><<<grid_for((long long)P.n * 32, NB, JMD_SM_COUNT * 16), NB, 0, stream>>>(P, gated);
+    return;
+  }
+  const int grid = grid_for(P.n, NB, 1 << 30);
+  const int fmt = P.format == JMD_DENSE ? 0 : (P.format == JMD_SPARSE ? 1 : 2);
+  if (P.sp.periodic) {
+    if (fmt == 0) launch_scan_wf<T, DIM, 0, true>(P, gated, grid, stream);
+    else if (fmt == 1) launch_scan_wf<T, DIM, 1, true>(P, gated, grid, stream);
+    else launch_scan_wf<T, DIM, 2, true>(P, gated, grid, stream);
+  } else {
+    // free space: Dense has no reverse test (MODE 0), same rows as Sparse
+    if (fmt == 2) launch_scan_wf<T, DIM, 2, false>(P, gated, grid, stream);
+    else launch_scan_wf<T, DIM, 1, false>(P, gated, grid, stream);
+  }
 }
 
 template <typename T, int DIM>
@@ -755,7 +953,6 @@ __global__ void __launch_bounds__(NB, 6) k_nbr_export(NbrP<T, DIM> P, int gated)
 }
 
 #define LAUNCH(PH, grid) k_phase<T, DIM, PH><<<(grid), NB, 0, stream>>>(P, gated)
-#define LAUNCH_SCAN(grid) k_nbr_stencil_scan<T, DIM><<<(grid), NB, 0, stream>>>(P, gated)
 
 template <typename T, int DIM>
 void launch_bin(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
@@ -778,8 +975,7 @@ void launch_bin(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 template <typename T, int DIM>
 void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   LAUNCH(PH_BUILD_RESET, 1);
-  if (P.use_cells) LAUNCH_SCAN(grid_for(P.n, NB, 1 << 30));
-  else LAUNCH_SCAN(grid_for((long long)P.n * 32, NB, JMD_SM_COUNT * 16));
+  launch_scan<T, DIM>(P, gated, stream);
 }
 
 template <typename T, int DIM>
@@ -844,11 +1040,14 @@ __global__ void __launch_bounds__(NB, 4) k_update(NbrP<T, DIM> P) {
     ph_hash(P);
     grid_sync(bar, target);
     ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, nullptr, sm);
+    if (ref_scan(P)) ph_scan_tiles<int, int>(P.ref_count, P.n_ref_cells, ref_sums(P), nullptr, sm);
     ph_ref_max(P);
     grid_sync(bar, target);
     ph_scan_top<int>(P.scan_tmp, P.n_cells, sm);
+    if (ref_scan(P)) ph_scan_top<int>(ref_sums(P), P.n_ref_cells, sm);
     grid_sync(bar, target);
     ph_scan_apply<int, int>(P.cell_count, P.n_cells, P.scan_tmp, P.cell_start, sm);
+    if (ref_scan(P)) ph_scan_apply<int, int>(P.ref_count, P.n_ref_cells, ref_sums(P), P.ref_start, sm);
     grid_sync(bar, target);
     ph_scatter(P);
     grid_sync(bar, target);
@@ -904,16 +1103,30 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   P.m_int = nb->m_int;
   // reference grid (flags) and the internal fine search grid
   P.n_ref_cells = nb->n_cells;
-  P.n_cells = nb->n_fine_cells;
+  P.n_cells = nb->n_fine_cells;       // storage cells (padded to whole bricks)
+  P.bs = nb->use_cells ? nb->brick_shift : 0;
+  if (P.bs < 0 || P.bs > 3) return JMD_EINVAL;
+  P.rotate = 1;
+  P.ref_start = nb->ref_start;
   P.sw = nb->stencil_w > 0 ? nb->stencil_w : 1;
   for (int k = 0; k < 3; ++k) {
     P.ref_cps[k] = nb->cps[k] > 0 ? nb->cps[k] : 1;
     P.cps[k] = nb->fine_cps[k] > 0 ? nb->fine_cps[k] : 1;
+    P.nb[k] = (P.cps[k] + (1 << P.bs) - 1) >> P.bs;
+    if (P.cps[k] != P.ref_cps[k]) P.rotate = 0;       // finer search grid: ascending-id cells
+  }
+  if (nb->use_cells) {
+    long long storage = 1;
+    for (int k = 0; k < DIM; ++k) storage *= (long long)P.nb[k] << P.bs;
+    if (storage != P.n_cells) return JMD_EINVAL;
+    if (P.bs > 0 && P.rotate && !P.ref_start) return JMD_EINVAL;
   }
   if (nb->use_cells) {
     for (int k = 0; k < DIM; ++k)
       if (P.cps[k] < 2 * P.sw + 1) return JMD_EINVAL;       // stencil cells would alias
   }
+  // the stencil scan addresses nl with 32-bit element offsets
+  if ((unsigned long long)nb->m_int * (unsigned long long)nb->n_pad >= (1ull << 32)) return JMD_EINVAL;
   P.count_only = 0;
   P.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
   P.no_public_idx = nb->no_public_idx;
@@ -937,6 +1150,14 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   double band = DIM * (2.0 * (c + delta) + delta) * delta + 2.0 * (DIM + 1) * u * 1.01 * nb->cutoff_sq;
   P.band = (T)(2.0 * band);
   P.far = (T)Lmax;
+  // Pre-filter (see ph_build_cells): the contracted image-shifted d2 differs from
+  // either exact orientation by less than `band` (delta above covers 10 half-ulps
+  // of L per component; the exact path accumulates <= 4, the filter <= 2.4).
+  P.f_lo = (T)(nb->cutoff_sq - 2.0 * band);
+  P.f_hi = (T)(nb->cutoff_sq + 2.0 * band);
+  P.filter = (nb->use_cells && periodic && !nb->no_filter) ? 1 : 0;
+  for (int k = 0; k < DIM; ++k)
+    if (P.cps[k] < 2 * P.sw + 3) P.filter = 0;
   P.cell_count = nb->cell_count; P.cell_start = nb->cell_start; P.cell_cursor = nb->cell_cursor;
   P.scan_tmp = nb->scan_tmp; P.hash = nb->hash; P.tmp_ids = nb->tmp_ids; P.perm = nb->perm;
   P.inv_perm = nb->inv_perm; P.ref_count = nb->ref_count;
@@ -983,9 +1204,7 @@ int launch_update(NbrP<T, DIM>& P, cudaStream_t stream) {
   int grid = 0, rc;
   if ((rc = coop_grid(k_update<T, DIM>, cache_a, &grid))) return rc;
   k_update<T, DIM><<<grid, NB, 0, stream>>>(P);
-  const int gated = 1;
-  if (P.use_cells) LAUNCH_SCAN(grid_for(P.n, NB, 1 << 30));
-  else LAUNCH_SCAN(grid_for((long long)P.n * 32, NB, JMD_SM_COUNT * 16));
+  launch_scan<T, DIM>(P, 1, stream);
   if (P.format == JMD_DENSE) {
     k_update_c<T, DIM><<<grid_for(P.n, NB, 1 << 30), NB, 0, stream>>>(P);
   } else {

@@ -22,6 +22,19 @@ namespace {
 #define JMD_PAIR_BLOCK 256
 #endif
 constexpr int PAIR_BLOCK = JMD_PAIR_BLOCK;
+#ifndef JMD_PAIR_UNROLL
+#define JMD_PAIR_UNROLL 4
+#endif
+constexpr int PAIR_UNROLL = JMD_PAIR_UNROLL;
+#ifndef JMD_PAIR_BATCH
+#define JMD_PAIR_BATCH 0
+#endif
+#ifndef JMD_PAIR_ALWAYS_WRAP
+#define JMD_PAIR_ALWAYS_WRAP 0
+#endif
+#ifndef JMD_PAIR_MIN_BLOCKS
+#define JMD_PAIR_MIN_BLOCKS 1
+#endif
 
 template <typename T, int DIM>
 struct PairP {
@@ -135,8 +148,9 @@ __device__ __forceinline__ void pair_eval(int has_cutoff, T r2, T sigma, T eps, 
     // energy.py:562-574: S = (rc2-r2)^2 (rc2 + 2 r2 - 3 ro2) / (rc2-ro2)^3 on [ro, rc)
     const bool sw = r2 >= ro2;
     const T a = rc2 - r2;
-    const T S = sw ? a * a * (rc2 + T(2) * r2 - T(3) * ro2) * inv_denom : T(1);
-    const T dS_r = sw ? T(12) * a * (ro2 - r2) * inv_denom : T(0);        // (dS/dr)/r
+    const T ai = a * inv_denom;
+    const T S = sw ? ai * a * (T(2) * r2 + (rc2 - T(3) * ro2)) : T(1);
+    const T dS_r = sw ? T(12) * ai * (ro2 - r2) : T(0);                   // (dS/dr)/r
     du_r = dS_r * u + S * du_r;
     u = S * u;
     dus = S * dus;
@@ -170,7 +184,7 @@ __device__ __forceinline__ T lookup(const PairP<T, DIM>& Q, int k, int ai, int a
 template <int RED> struct RedN { static constexpr int value = RED == 0 ? 1 : (RED == 1 ? 4 : 13); };
 
 template <typename T, int DIM, int POT, bool SCALAR, int RED, bool KICK>
-__global__ void __launch_bounds__(PAIR_BLOCK) k_pair_force(PairP<T, DIM> Q) {
+__global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_MIN_BLOCKS) k_pair_force(PairP<T, DIM> Q) {
   using V4 = typename Vec4<T>::type;
   constexpr bool WANT_E = RED == 2;
   constexpr int NV = RedN<RED>::value;
@@ -189,14 +203,27 @@ __global__ void __launch_bounds__(PAIR_BLOCK) k_pair_force(PairP<T, DIM> Q) {
     T vir[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
     const int* col = Q.nl + t;
     const T sig0 = Q.scalar[0], eps0 = Q.scalar[1], alp0 = Q.scalar[2];
-#pragma unroll 4
-    for (int k = 0; k < cnt; ++k) {
-      const int j = __ldcs(col + (size_t)k * Q.n_pad);   // streamed once: keep it out of L1
-      const V4 pj = ld_pos(&Q.pos_sorted[j]);
+    // free space: half = +inf, never "far"
+    const T hx = Q.sp.periodic ? Q.sp.half[0] : (T)INFINITY;
+    const T hy = Q.sp.periodic ? Q.sp.half[1] : (T)INFINITY;
+    const T hz = Q.sp.periodic ? Q.sp.half[DIM - 1] : (T)INFINITY;
+    // one neighbour: displacement, potential, accumulation
+    auto pair = [&](const int j, const V4& pj) {
+      // minimum image (tolerance-level, handles unwrapped positions): a raw
+      // difference within half a box side on every axis IS the minimum image --
+      // the case for every pair of an atom away from the box faces -- so the
+      // rint() form runs only behind a rarely taken branch.
       T d[3];
-      d[0] = Q.sp.disp_fast(pi.x, pj.x, 0);
-      d[1] = Q.sp.disp_fast(pi.y, pj.y, 1);
-      d[2] = DIM == 3 ? Q.sp.disp_fast(pi.z, pj.z, DIM - 1) : T(0);
+      d[0] = pi.x - pj.x;
+      d[1] = pi.y - pj.y;
+      d[2] = DIM == 3 ? pi.z - pj.z : T(0);
+      bool far = fabs(d[0]) > hx || fabs(d[1]) > hy;
+      if (DIM == 3) far = far || fabs(d[2]) > hz;
+      if (JMD_PAIR_ALWAYS_WRAP || far) {
+        d[0] = Q.sp.wrap_fast(d[0], 0);
+        d[1] = Q.sp.wrap_fast(d[1], 1);
+        if (DIM == 3) d[2] = Q.sp.wrap_fast(d[2], DIM - 1);
+      }
       const T r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
       T sigma = sig0, eps = eps0, alpha = alp0;
       if (!SCALAR) {
@@ -232,7 +259,32 @@ __global__ void __launch_bounds__(PAIR_BLOCK) k_pair_force(PairP<T, DIM> Q) {
             atomicAdd(&Q.dparam[Q.n_species * Q.n_species + cell], 0.5 * (double)due);
         }
       }
+    };
+#if JMD_PAIR_BATCH > 0
+    // Explicit batches: JMD_PAIR_BATCH row entries, then their JMD_PAIR_BATCH
+    // position gathers, all in flight before the first pair is evaluated.
+    int k = 0;
+    for (; k + JMD_PAIR_BATCH <= cnt; k += JMD_PAIR_BATCH) {
+      int jj[JMD_PAIR_BATCH];
+      V4 pp4[JMD_PAIR_BATCH];
+#pragma unroll
+      for (int u = 0; u < JMD_PAIR_BATCH; ++u) jj[u] = __ldcs(col + (size_t)(k + u) * Q.n_pad);
+#pragma unroll
+      for (int u = 0; u < JMD_PAIR_BATCH; ++u) pp4[u] = ld_pos(&Q.pos_sorted[jj[u]]);
+#pragma unroll
+      for (int u = 0; u < JMD_PAIR_BATCH; ++u) pair(jj[u], pp4[u]);
     }
+    for (; k < cnt; ++k) {
+      const int j = __ldcs(col + (size_t)k * Q.n_pad);
+      pair(j, ld_pos(&Q.pos_sorted[j]));
+    }
+#else
+#pragma unroll(PAIR_UNROLL)
+    for (int k = 0; k < cnt; ++k) {
+      const int j = __ldcs(col + (size_t)k * Q.n_pad);   // streamed once: keep it out of L1
+      pair(j, ld_pos(&Q.pos_sorted[j]));
+    }
+#endif
     T* fo = Q.force + (size_t)ai * DIM;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) fo[k] = f[k];

@@ -10,6 +10,7 @@ syncs and is CUDA-graph capturable.
 """
 import ctypes as C
 import logging
+import os
 from enum import Enum, IntEnum
 from typing import Any, Callable, Optional
 
@@ -317,21 +318,35 @@ def neighbor_list(displacement_or_metric,
       cs_min = min(c.cell_size[k] for k in range(dim))
       if cs_min >= float(cutoff) * (1.0 + 1e-4) and all(2 * cps[k] >= 5 for k in range(dim)):
         fine, w = 2, 2
+    # Storage order of the cells (csrc/jmd_neighbor.cu "cell storage order"):
+    # `cell_brick_shift=b` (static kwarg) stores cells in bricks of (2^b)^dim so
+    # warps / blocks are spatially compact.  Measured on B200 (LJ, N=1M): no gain
+    # (force kernel 0.27 ms vs 0.26 ms in the reference's x-fastest order, which
+    # keeps the three x-neighbour cells of a stencil row contiguous), so the
+    # default is the reference order; public `idx` is identical either way.
+    bshift = int(static_kwargs.get('cell_brick_shift', os.environ.get('JMD_BRICK_SHIFT', 0))) if use_cells else 0
+    brick = 1 << bshift
     n_fine = 1
     for k in range(3):
       c.fine_cps[k] = int(cps[k]) * fine if k < dim else 1
-      n_fine *= c.fine_cps[k]
+      if k < dim:
+        n_fine *= -(-c.fine_cps[k] // brick) * brick
     for k in range(dim):
       c.fine_cell_size[k] = c.cell_size[k] / fine        # exact (power of two)
     c.n_fine_cells = n_fine if use_cells else 0
+    c.brick_shift = bshift
     c.stencil_w = w
+    # exact_scan=True (static kwarg): evaluate the reference arithmetic on every
+    # candidate instead of only inside the pre-filter's rounding band (testing).
+    c.no_filter = 1 if static_kwargs.get('exact_scan', False) else 0
     n_cells_buf = c.n_fine_cells
     i4 = torch.int32
     ws.buf('cell_count', (n_cells_buf + 1,), i4, 0)
     ws.buf('cell_start', (n_cells_buf + 1,), i4, 0)
     ws.buf('cell_cursor', (max(n_cells_buf, 1),), i4, 0)
     ws.buf('ref_count', (max(n_cells, 1),), i4, 0)
-    ws.buf('scan_tmp', (2 * (max(n_cells_buf, n_buf) // 2048 + 2) + 16,), i4, 0)
+    ws.buf('ref_start', (max(n_cells, 1) + 1,), i4, 0)
+    ws.buf('scan_tmp', (2 * (max(n_cells_buf, n_buf) // 2048 + 2) + 16,), i4, 0)   # two int scans or one int64 scan
     ws.buf('hash', (max(n_buf, 1),), i4)
     ws.buf('tmp_ids', (max(n_buf, 1),), i4)
     ws.buf('perm', (c.n_pad,), i4, 0)

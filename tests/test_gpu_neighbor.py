@@ -80,11 +80,18 @@ def test_random_rectangular_box(fmt, dim, dtype):
 
 @pytest.mark.parametrize('fmt', FORMATS)
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
-def test_fcc_lj_config(fmt, dtype):
-  """BASELINE config: LJ fcc, rho=0.8442, rc=2.5, skin 0.3 (N=4*12^3=6912)."""
+@pytest.mark.parametrize('brick', [0, 1, 2])
+def test_fcc_lj_config(fmt, dtype, brick):
+  """BASELINE config: LJ fcc, rho=0.8442, rc=2.5, skin 0.3 (N=4*12^3=6912);
+  also with the cells stored brick-wise (same public idx, element by element)."""
   R, L = util.fcc(12, dtype=dtype)
   R = util.jitter(R, L, 0.05)
   nf_o, nf_g = _build_both(R, L, np.float32(2.5), np.float32(0.3), fmt)
+  if brick:
+    jmd = _mods()
+    nf_g = jmd.partition.neighbor_list(
+        jmd.space.periodic(L)[0], L, np.float32(2.5), np.float32(0.3),
+        format=jmd.partition.NeighborListFormat[fmt], cell_brick_shift=brick)
   nb_o = nf_o.allocate(R)
   nb_g = nf_g.allocate(_dev(R))
   _assert_same(nb_o, nb_g)
@@ -264,3 +271,62 @@ def test_update_is_graph_capturable():
   g.replay()
   torch.cuda.synchronize()
   assert nb_g._ws.state_host()[4] == b0 + 1
+
+
+def _adversarial(N, L, cut, dtype, seed):
+  """Random atoms plus partners placed within a few ulps of the list cutoff,
+  atoms exactly on / just outside the box faces and unwrapped copies."""
+  rng = np.random.default_rng(seed)
+  R = (rng.random((N, 3)) * L).astype(dtype)
+  m = N // 4
+  u = rng.normal(size=(m, 3))
+  u /= np.linalg.norm(u, axis=1, keepdims=True)
+  eps = np.finfo(dtype).eps
+  scale = 1.0 + rng.integers(-6, 7, (m, 1)) * eps * rng.choice([1, 4, 16, 64], (m, 1))
+  R[m:2 * m] = (R[:m].astype(np.float64) + u * float(cut) * scale).astype(dtype)
+  R[m:2 * m] = np.mod(R[m:2 * m], dtype(L))          # may round to exactly L: intended
+  k = 2 * m
+  R[k + 0] = [0, 0, 0]
+  R[k + 1] = [L, L, L]                                # bins to cell 0, sits at L
+  R[k + 2] = [-1e-6, 1.0, 2.0]
+  R[k + 3] = [np.nextafter(dtype(L), dtype(0)), 0.5 * L, L]
+  R[k + 4:k + 40] += dtype(L)                         # unwrapped: one box up
+  R[k + 40:k + 80] -= dtype(3) * dtype(L)             # three boxes down
+  return R
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_prefilter_adversarial_boundaries(fmt, dtype):
+  """The stencil scan's contracted pre-filter must not change a single entry:
+  pairs within a few ulps of cutoff^2, atoms on the faces, unwrapped atoms."""
+  L = np.float32(21.7)
+  cut, skin = np.float32(2.5), np.float32(0.3)
+  R = _adversarial(4000, L, cut + skin, dtype, 7)
+  nf_o, nf_g = _build_both(R, L, cut, skin, fmt)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  ws = nb_g._ws
+  assert ws.c.no_filter == 0 and min(ws.c.fine_cps[k] for k in range(3)) >= 5
+  _assert_same(nb_o, nb_g)
+  R2 = _adversarial(4000, L, cut + skin, dtype, 8)
+  # rebuild through update() (every atom moved): same kernels, gated launch
+  _assert_same(nb_o.update(R2), nb_g.update(_dev(R2)))
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+def test_prefilter_equals_exact_scan_at_scale(fmt):
+  """200k atoms (random + adversarial): default scan == exact_scan=True scan."""
+  N = 200_000
+  L = np.float32((N / 0.8442) ** (1 / 3))
+  R = _adversarial(N, L, np.float32(2.8), np.float32, 9)
+  jmd = _mods()
+  d_g, _ = jmd.space.periodic(L)
+  F = jmd.partition.NeighborListFormat[fmt]
+  a = jmd.partition.neighbor_list(d_g, L, np.float32(2.5), np.float32(0.3), format=F).allocate(_dev(R))
+  b = jmd.partition.neighbor_list(d_g, L, np.float32(2.5), np.float32(0.3), format=F,
+                                  exact_scan=True).allocate(_dev(R))
+  assert a._ws.c.no_filter == 0 and b._ws.c.no_filter == 1
+  assert a.max_occupancy == b.max_occupancy
+  assert torch.equal(a.idx, b.idx)
+  assert int(a.error.code) == int(b.error.code)
