@@ -122,8 +122,13 @@ typedef struct {
    * grid padded to whole bricks.  ref_start: [n_cells + 1] scratch (prefix sums
    * in reference order, for the slot rotation of partition.py:441). */
   int32_t brick_shift;
-  int32_t _pad3;
+  int32_t staged;          /* 1: nl16 / blk_table are allocated and maintained by the build */
   int32_t* ref_start;
+  /* shared-memory staging plan of the force kernel (see csrc/jmd_common.cuh):
+   * nl16 [m_int, n_pad] uint16 = the rows of `nl` as indices into the staging
+   * buffer of the 256-slot block that owns the row; blk_table [n_pad / 256 + 1, 256]. */
+  uint16_t* nl16;
+  int32_t* blk_table;
 } jmd_nbr_t;
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */

@@ -55,7 +55,8 @@ class NbrT(C.Structure):
       ('fine_cps', C.c_int32 * 3), ('n_fine_cells', C.c_int32),
       ('stencil_w', C.c_int32), ('no_filter', C.c_int32),
       ('fine_cell_size', C.c_double * 3), ('ref_count', C.c_void_p),
-      ('brick_shift', C.c_int32), ('_pad3', C.c_int32), ('ref_start', C.c_void_p)]
+      ('brick_shift', C.c_int32), ('staged', C.c_int32), ('ref_start', C.c_void_p),
+      ('nl16', C.c_void_p), ('blk_table', C.c_void_p)]
 
 
 class PairT(C.Structure):

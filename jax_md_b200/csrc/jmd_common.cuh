@@ -13,6 +13,26 @@
     if (e__ != cudaSuccess) return (int)e__;       \
   } while (0)
 
+// ---- shared-memory staging of neighbour positions (force kernel) -----------------
+// A force-kernel block owns JMD_STAGE_BLOCK consecutive cell-sorted slots.  With cells
+// stored x-fastest, the 3^d stencils of its home cells are a few contiguous slot
+// ranges: <= JMD_STAGE_SEGS row segments x 9 (dy, dz) stencil rows x 2 pieces (periodic
+// wrap in x).
+// The neighbour build writes that plan into a per-block table and a second copy of
+// the neighbour rows as 16-bit indices into the block's staging buffer; the force
+// kernel copies the ranges into shared memory once and gathers from there.
+#define JMD_STAGE_BLOCK 256
+#define JMD_STAGE_BYTES 57344          /* 3584 float4 / 1792 double4; 4 blocks per SM */
+#define JMD_STAGE_SEGS 4               /* consecutive cell rows a block may span */
+#define JMD_TBL_INTS 256               /* per-block table stride */
+#define JMD_TBL_MODE 0                 /* 1: staged, 0: gather from global (32-bit rows) */
+#define JMD_TBL_TOTAL 1                /* staged entries */
+#define JMD_TBL_ROW0 2                 /* row id (cell / cells_x) of segment 0; segment s is row ROW0 + s */
+#define JMD_TBL_NSEG 3
+#define JMD_TBL_ENTRIES 8              /* then SEGS x 18 x {first slot, length, first staging index} */
+#define JMD_TBL_NENTRIES (JMD_STAGE_SEGS * 18)
+#define JMD_TBL_ENTRY(seg, dy, dz, piece) (JMD_TBL_ENTRIES + 3 * (((((seg) * 3 + (dy) + 1) * 3 + (dz) + 1) * 2) + (piece)))
+
 template <typename T> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };

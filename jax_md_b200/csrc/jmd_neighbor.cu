@@ -34,6 +34,12 @@ enum { ST_REBUILD = JMD_ST_REBUILD, ST_MAX_CELL = JMD_ST_MAX_CELL_OCC,
        ST_BUILDS = JMD_ST_BUILDS, ST_TICKET = JMD_ST_SCAN_TICKET,
        ST_PENDING = 6, ST_BARRIER = 7 };
 
+#ifndef JMD_SCAN_UNROLL2
+#define JMD_SCAN_UNROLL2 0
+#endif
+#ifndef JMD_SCAN_MIN_BLOCKS
+#define JMD_SCAN_MIN_BLOCKS 3
+#endif
 constexpr int NB = 256;           // threads per block, every kernel here
 constexpr int NWARP = NB / 32;
 constexpr int SCAN_TILE = NB * 8;
@@ -46,6 +52,10 @@ struct NbrP {
   int cps[3];          // INTERNAL (fine) search grid
   int bs, nb[3], rotate;   // storage order: bricks of (1 << bs)^DIM cells, nb bricks per side
   int* ref_start;          // [n_ref_cells + 1] exclusive scan of the counts in REFERENCE hash order
+  int staged;              // maintain the force kernel's staging plan (blk_table, nl16)
+  int stage_cap;           // staging entries per block (JMD_STAGE_BYTES / sizeof(Vec4<T>))
+  int* blk_table;
+  unsigned short* nl16;
   int ref_cps[3], n_ref_cells, sw;   // reference grid (capacity flag only), stencil half width
   int count_only, two_sided, rev_only, n_rows, no_public_idx;
   long long n_pad, max_occupancy;
@@ -392,6 +402,67 @@ __device__ void ph_inv_perm(const NbrP<T, DIM>& P) {
   for (int t = gtid(); t < P.n; t += gthreads()) P.inv_perm[P.perm[t]] = t;
 }
 
+
+// ---- phase: staging plan of the force kernel (see jmd_common.cuh) ---------------------
+// One thread per 256-slot block: the block's home cells are a run of consecutive
+// cells in the x-fastest order, i.e. a few row segments; every (dy, dz)
+// stencil row of a segment is one contiguous slot range, or two when the
+// x-interval wraps around the box.  Blocks that do not fit (more than
+// JMD_STAGE_SEGS segments, more atoms than the staging buffer) are marked "direct".
+template <typename T, int DIM>
+__device__ void ph_plan(const NbrP<T, DIM>& P) {
+  if (!P.staged) return;
+  const int nblk = (P.n + JMD_STAGE_BLOCK - 1) / JMD_STAGE_BLOCK;
+  for (int b = gtid(); b < nblk; b += gthreads()) {
+    int* tb = P.blk_table + (size_t)b * JMD_TBL_INTS;
+    for (int i = 0; i < JMD_TBL_INTS; ++i) tb[i] = 0;
+    tb[JMD_TBL_ROW0] = -1;
+    if (!P.use_cells || P.sw != 1 || P.bs != 0) continue;          // mode 0: direct
+    const int s_first = b * JMD_STAGE_BLOCK;
+    const int s_last = min(s_first + JMD_STAGE_BLOCK, P.n) - 1;
+    const int c_first = P.hash[P.perm[s_first]], c_last = P.hash[P.perm[s_last]];
+    const int cx = P.cps[0], cy = P.cps[1], cz = DIM == 3 ? P.cps[2] : 1;
+    const int r_first = c_first / cx, r_last = c_last / cx;
+    if (r_last - r_first >= JMD_STAGE_SEGS) continue;
+    const int nseg = r_last - r_first + 1;
+    tb[JMD_TBL_ROW0] = r_first;
+    tb[JMD_TBL_NSEG] = nseg;
+    int total = 0;
+    bool fits = true;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int row = r_first + seg;
+      const int y = row % cy, z = row / cy;
+      const int x0 = (seg == 0) ? c_first % cx : 0;
+      const int x1 = (row == r_last) ? c_last % cx : cx - 1;
+      // x-interval [x0-1, x1+1], periodic: piece 0 / piece 1
+      int xa[2], xb[2];
+      xa[1] = 0; xb[1] = -1;
+      if (x1 - x0 + 3 >= cx) { xa[0] = 0; xb[0] = cx - 1; }
+      else if (x0 - 1 < 0) { xa[0] = 0; xb[0] = x1 + 1; xa[1] = cx - 1; xb[1] = cx - 1; }
+      else if (x1 + 1 >= cx) { xa[0] = x0 - 1; xb[0] = cx - 1; xa[1] = 0; xb[1] = 0; }
+      else { xa[0] = x0 - 1; xb[0] = x1 + 1; }
+      for (int dy = -1; dy <= 1; ++dy)
+      for (int dz = (DIM == 3 ? -1 : 0); dz <= (DIM == 3 ? 1 : 0); ++dz) {
+        int yy = y + dy, zz = z + dz;
+        yy = yy < 0 ? yy + cy : (yy >= cy ? yy - cy : yy);
+        zz = zz < 0 ? zz + cz : (zz >= cz ? zz - cz : zz);
+        const int rowbase = (zz * cy + yy) * cx;
+        for (int piece = 0; piece < 2; ++piece) {
+          if (xb[piece] < xa[piece]) continue;
+          const int g0 = P.cell_start[rowbase + xa[piece]];
+          const int len = P.cell_start[rowbase + xb[piece] + 1] - g0;
+          int* e = tb + JMD_TBL_ENTRY(seg, dy, dz, piece);
+          e[0] = g0; e[1] = len; e[2] = total;
+          total += len;
+          fits = fits && total <= P.stage_cap;
+        }
+      }
+    }
+    tb[JMD_TBL_TOTAL] = total;
+    tb[JMD_TBL_MODE] = fits ? 1 : 0;
+  }
+}
+
 template <typename T, int DIM>
 __device__ void ph_build_reset(const NbrP<T, DIM>& P) {
   if (gtid() == 0) {
@@ -486,24 +557,48 @@ __device__ __forceinline__ void keep_in_register(int& x) { asm volatile("" : "+r
 // on the host).  Spelled in PTX so the append stays a handful of predicated instructions
 // (ptxas otherwise turns the selects into a chain of moves or a branch).
 #define JMD_APPEND_ASM(FT, FC)                                                                   \
-  asm volatile(                                                                                  \
-      "{\n\t.reg .pred pk, pw;\n\t.reg .u64 ad;\n\t"                                           \
-      "setp.lt." FT " pk, %2, %3;\n\t"                                                          \
-      "setp.ne.and.s32 pk, %4, %5, pk;\n\t"                                                     \
-      "setp.lt.and.u32 pw, %0, %6, pk;\n\t"                                                     \
-      "mad.wide.u32 ad, %0, 4, %8;\n\t"                                                         \
-      "@pw st.global.s32 [ad], %4;\n\t"                                                         \
-      "@pw add.u32 %0, %0, %7;\n\t"                                                             \
-      "@pk add.s32 %1, %1, 1;\n\t}"                                                             \
-      : "+r"(off), "+r"(k)                                                                       \
-      : FC(a2), FC(lo), "r"(rank), "r"(self), "r"(off_end), "r"(n_pad), "l"(nl)                  \
-      : "memory")
+  if (STAGE) {                                                                                   \
+    asm volatile(                                                                                \
+        "{\n\t.reg .pred pk, pw;\n\t.reg .u64 ad;\n\t.reg .u32 cd;\n\t.reg .u16 ch;\n\t"     \
+        "setp.lt." FT " pk, %2, %3;\n\t"                                                        \
+        "setp.ne.and.s32 pk, %4, %5, pk;\n\t"                                                   \
+        "setp.lt.and.u32 pw, %0, %6, pk;\n\t"                                                   \
+        "mad.wide.u32 ad, %0, 4, %8;\n\t"                                                       \
+        "@pw st.global.s32 [ad], %4;\n\t"                                                       \
+        "mad.wide.u32 ad, %0, 2, %9;\n\t"                                                       \
+        "add.s32 cd, %4, %10;\n\t"                                                              \
+        "cvt.u16.u32 ch, cd;\n\t"                                                               \
+        "@pw st.global.u16 [ad], ch;\n\t"                                                       \
+        "@pw add.u32 %0, %0, %7;\n\t"                                                           \
+        "@pk add.s32 %1, %1, 1;\n\t}"                                                           \
+        : "+r"(off), "+r"(k)                                                                     \
+        : FC(a2), FC(lo), "r"(rank), "r"(self), "r"(off_end), "r"(n_pad), "l"(nl), "l"(nl16),    \
+          "r"(lbase)                                                                             \
+        : "memory");                                                                             \
+  } else {                                                                                       \
+    asm volatile(                                                                                \
+        "{\n\t.reg .pred pk, pw;\n\t.reg .u64 ad;\n\t"                                         \
+        "setp.lt." FT " pk, %2, %3;\n\t"                                                        \
+        "setp.ne.and.s32 pk, %4, %5, pk;\n\t"                                                   \
+        "setp.lt.and.u32 pw, %0, %6, pk;\n\t"                                                   \
+        "mad.wide.u32 ad, %0, 4, %8;\n\t"                                                       \
+        "@pw st.global.s32 [ad], %4;\n\t"                                                       \
+        "@pw add.u32 %0, %0, %7;\n\t"                                                           \
+        "@pk add.s32 %1, %1, 1;\n\t}"                                                           \
+        : "+r"(off), "+r"(k)                                                                     \
+        : FC(a2), FC(lo), "r"(rank), "r"(self), "r"(off_end), "r"(n_pad), "l"(nl)                \
+        : "memory");                                                                             \
+  }
+template <bool STAGE>
 __device__ __forceinline__ void append_if_below(float a2, float lo, int rank, int self, unsigned off_end,
-                                                unsigned n_pad, int* nl, unsigned& off, int& k) {
+                                                unsigned n_pad, int* nl, unsigned short* nl16, int lbase,
+                                                unsigned& off, int& k) {
   JMD_APPEND_ASM("f32", "f");
 }
+template <bool STAGE>
 __device__ __forceinline__ void append_if_below(double a2, double lo, int rank, int self, unsigned off_end,
-                                                unsigned n_pad, int* nl, unsigned& off, int& k) {
+                                                unsigned n_pad, int* nl, unsigned short* nl16, int lbase,
+                                                unsigned& off, int& k) {
   JMD_APPEND_ASM("f64", "d");
 }
 #undef JMD_APPEND_ASM
@@ -553,7 +648,7 @@ __device__ __forceinline__ bool exact_keep(const NbrP<T, DIM>& P, const T (&hp)[
   return keep;
 }
 
-template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC, int WSTAT, bool FILTER, bool COUNT>
+template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC, int WSTAT, bool FILTER, bool COUNT, bool STAGE>
 __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
   using V4 = typename Vec4<T>::type;
   const int lane = threadIdx.x & 31;
@@ -570,10 +665,17 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
 #pragma unroll
   for (int d = 0; d < DIM; ++d) { hh[d] = P.sp.half[d]; qq[d] = P.sp.quarter[d]; }
   const V4* __restrict__ const pos = P.pos_sorted;
-  for (int wbase = gtid() - lane; wbase < P.n; wbase += gthreads()) {
-    const int slot = wbase + lane;
+  __shared__ int tbl[JMD_TBL_INTS];              // this block's staging plan (ph_plan)
+  for (int blk = blockIdx.x; blk * NB < P.n; blk += gridDim.x) {
+    const int slot = blk * NB + threadIdx.x;
+    (void)lane;
     long long my_k = 0, my_tot = 0;
     const int hid = slot < P.n ? P.perm[slot] : 0x7fffffff;
+    if (STAGE) {
+      __syncthreads();
+      if (threadIdx.x < JMD_TBL_INTS) tbl[threadIdx.x] = P.blk_table[(size_t)blk * JMD_TBL_INTS + threadIdx.x];
+      __syncthreads();
+    }
     if (slot < P.n && hid >= P.n_rows) {      // ghost atom: candidate only, no row
       P.cnt[slot] = 0;
       P.cnt_lower[slot] = 0;
@@ -584,6 +686,9 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
       const int c = P.hash[hid];              // own (fine) cell
       int cc[3];
       cell_coords(P, c, cc);
+      // staging: which row segment of the block this home cell belongs to
+      const bool stage_on = STAGE && tbl[JMD_TBL_MODE] != 0;
+      const int seg = STAGE ? c / P.cps[0] - tbl[JMD_TBL_ROW0] : 0;
       int self = self_on ? slot : -1;
       keep_in_register(self);
       const bool home_dirty = FILTER ? (__ldg(&P.cell_cursor[c]) & CELL_DIRTY) != 0 : false;
@@ -620,6 +725,13 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
         if (WSTAT != 1 && gap2 > gap_limit) continue;
         const int start = __ldg(&P.cell_start[h]);
         const int end = __ldg(&P.cell_start[h + 1]);
+        // staging index of a candidate = lbase + its slot (see ph_plan)
+        int lbase = 0;
+        if (STAGE && stage_on) {
+          const int* e = tbl + JMD_TBL_ENTRY(seg, WSTAT == 1 ? s1 : 0, (WSTAT == 1 && DIM == 3) ? s2 : 0, 0);
+          if (!(start >= e[0] && start < e[0] + e[1])) e += 3;         // second piece (x wrap)
+          lbase = e[2] - e[0];
+        }
         T lo_c = P.f_lo, hi_c = P.f_hi;
         if (FILTER) {
           if (home_dirty || (__ldg(&P.cell_cursor[h]) & CELL_DIRTY)) {
@@ -634,25 +746,37 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
           T h0 = hs[0], h1 = hs[1], h2 = hs[2];
           keep_in_register(h0); keep_in_register(h1); keep_in_register(h2);
           keep_in_register(lo_c); keep_in_register(hi_c);
-          for (int rank = start; rank < end; ++rank) {
-            const V4 cv = pos[rank];
+          auto process = [&](const int rank, const V4& cv) {
             const T ax = h0 - cv.x, ay = h1 - cv.y;
             T a2 = ax * ax + ay * ay;
             if (DIM == 3) { const T az = h2 - cv.z; a2 += az * az; }
             if (!(a2 < lo_c) && !(a2 > hi_c))     // rare: inside the band / dirty cell
               a2 = exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2) ? T(-2) : (T)INFINITY;
             const int k_before = k;
-            append_if_below(a2, lo_c, rank, self, off_end, (unsigned)P.n_pad, P.nl, off, k);
-            const bool keep = k != k_before;
-            if (ORDERED && COUNT) { if (keep) kl += (__ldg(&P.perm[rank]) < hid); }
+            append_if_below<STAGE>(a2, lo_c, rank, self, off_end, (unsigned)P.n_pad, P.nl, P.nl16, lbase, off, k);
+            if (ORDERED && COUNT) { if (k != k_before) kl += (__ldg(&P.perm[rank]) < hid); }
+          };
+          int rank = start;
+#if JMD_SCAN_UNROLL2
+          // two candidates per trip: both loads in flight before either is tested
+          for (; rank + 1 < end; rank += 2) {
+            const V4 cv0 = pos[rank], cv1 = pos[rank + 1];
+            process(rank, cv0);
+            process(rank + 1, cv1);
           }
+#endif
+          for (; rank < end; ++rank) process(rank, pos[rank]);
         } else {
           for (int rank = start; rank < end; ++rank) {
             const V4 cv = pos[rank];
             bool keep = exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2);
             keep = keep && (rank != self);
             if (keep) {
-              if (off < off_end) { P.nl[off] = rank; off += (unsigned)P.n_pad; }
+              if (off < off_end) {
+                P.nl[off] = rank;
+                if (STAGE) P.nl16[off] = (unsigned short)(lbase + rank);
+                off += (unsigned)P.n_pad;
+              }
               ++k;
               if (ORDERED && COUNT) kl += (__ldg(&P.perm[rank]) < hid);
             }
@@ -876,7 +1000,7 @@ __global__ void __launch_bounds__(NB, 3) k_phase(NbrP<T, DIM> P, int gated) {
     case PH_IDENTITY: ph_identity_sort(P); break;
     case PH_PACK: ph_pack(P); break;
     case PH_BUILD_RESET: ph_build_reset(P); break;
-    case PH_BUILD: break;   // own kernels: k_nbr_stencil_scan / k_nbr_all_pairs
+    case PH_BUILD: ph_plan(P); break;   // the scans are their own kernels: k_nbr_stencil_scan / k_nbr_all_pairs
     case PH_SP_COUNTS: ph_sparse_counts(P); break;
     case PH_SP_SCAN1: ph_scan_tiles<int, long long>(P.tmp_ids, P.n, sp_sums, nullptr, sm); break;
     case PH_SP_SCAN2: ph_scan_top<long long>(sp_sums, P.n, sm); break;
@@ -898,14 +1022,18 @@ inline int grid_for(long long work_items, int per_block, int cap_blocks) {
 // FMT: 0 Dense (forward + reverse test), 1 Sparse, 2 OrderedSparse.  Each variant
 // is its own kernel so that it gets its own register allocation.
 template <typename T, int DIM, int FMT, bool PERIODIC, int W, bool FILTER>
-__global__ void __launch_bounds__(NB, 3) k_nbr_stencil_scan(NbrP<T, DIM> P, int gated) {
+__global__ void __launch_bounds__(NB, JMD_SCAN_MIN_BLOCKS) k_nbr_stencil_scan(NbrP<T, DIM> P, int gated) {
   if (gated && P.state[ST_REBUILD] == 0) return;
+  constexpr int MODE = (FMT == 0 && PERIODIC) ? 1 : 0;
   // COUNT (OrderedSparse occupancy pass of allocate: no rows are written, so the
-  // id-lower count has to be taken inside the candidate loop)
+  // id-lower count has to be taken inside the candidate loop); STAGE: also emit
+  // the 16-bit staging rows of the force kernel (reference stencil only)
   if (FMT == 2 && P.count_only)
-    ph_build_cells<T, DIM, (FMT == 0 && PERIODIC) ? 1 : 0, FMT == 2, PERIODIC, W, FILTER, true>(P);
+    ph_build_cells<T, DIM, MODE, FMT == 2, PERIODIC, W, FILTER, true, false>(P);
+  else if (W == 1 && P.staged && !P.count_only)
+    ph_build_cells<T, DIM, MODE, FMT == 2, PERIODIC, W, FILTER, false, W == 1>(P);
   else
-    ph_build_cells<T, DIM, (FMT == 0 && PERIODIC) ? 1 : 0, FMT == 2, PERIODIC, W, FILTER, false>(P);
+    ph_build_cells<T, DIM, MODE, FMT == 2, PERIODIC, W, FILTER, false, false>(P);
 }
 
 template <typename T, int DIM>
@@ -975,6 +1103,7 @@ void launch_bin(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 template <typename T, int DIM>
 void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   LAUNCH(PH_BUILD_RESET, 1);
+  if (P.staged) LAUNCH(PH_BUILD, grid_for((P.n + JMD_STAGE_BLOCK - 1) / JMD_STAGE_BLOCK, NB, JMD_SM_COUNT * 8));
   launch_scan<T, DIM>(P, gated, stream);
 }
 
@@ -1055,11 +1184,13 @@ __global__ void __launch_bounds__(NB, 4) k_update(NbrP<T, DIM> P) {
     ph_build_reset(P);
     grid_sync(bar, target);
     ph_inv_perm(P);
+    ph_plan(P);
   } else {
     grid_sync(bar, target);
     if (gtid() == 0) P.state[ST_PENDING] = 0;
     ph_identity_sort(P);
     ph_build_reset(P);
+    ph_plan(P);                                   // all blocks "direct" (needs no perm)
   }
   grid_exit(bar);
 }
@@ -1108,6 +1239,10 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   if (P.bs < 0 || P.bs > 3) return JMD_EINVAL;
   P.rotate = 1;
   P.ref_start = nb->ref_start;
+  P.staged = (nb->staged && nb->blk_table && nb->nl16) ? 1 : 0;
+  P.stage_cap = JMD_STAGE_BYTES / (int)sizeof(typename Vec4<T>::type);
+  P.blk_table = nb->blk_table;
+  P.nl16 = nb->nl16;
   P.sw = nb->stencil_w > 0 ? nb->stencil_w : 1;
   for (int k = 0; k < 3; ++k) {
     P.ref_cps[k] = nb->cps[k] > 0 ? nb->cps[k] : 1;

@@ -420,6 +420,18 @@ def neighbor_list(displacement_or_metric,
     c.max_occupancy = max_occupancy
     c.m_int = max(m_int, 1)
     ws.buf('nl', (c.m_int, c.n_pad), torch.int32)
+    # Force-kernel staging plan (csrc/jmd_common.cuh): 16-bit copy of the rows as
+    # indices into the owning block's shared-memory staging buffer + the
+    # per-block range table.  Opt-in (`stage_positions=True` static kwarg): measured
+    # on B200 (LJ, N=1M) the staged kernel is not faster than the L1 gather kernel
+    # (0.29-0.31 ms vs 0.26 ms) and emitting the 16-bit rows slows the rebuild.
+    stage = static_kwargs.get('stage_positions', os.environ.get('JMD_STAGE', '0') != '0')
+    if stage and ws.use_cells and c.stencil_w == 1 and c.brick_shift == 0:
+      ws.buf('nl16', (c.m_int, c.n_pad), torch.uint16)
+      ws.buf('blk_table', (c.n_pad // 256 + 1, 256), torch.int32, 0)
+      c.staged = 1
+    else:
+      c.staged = 0
     if no_public_idx:
       idx = ws.buf('idx', (0,), torch.int32)
     elif sparse:

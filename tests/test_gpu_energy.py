@@ -427,3 +427,47 @@ def test_fori_loop_cuda_graph_matches_eager(kind):
   if kind == 'fire':
     assert int(st_g.n_pos) == int(st_e.n_pos)
     np.testing.assert_allclose(float(st_g.dt), float(st_e.dt), rtol=1e-12)
+
+
+@pytest.mark.parametrize('kind', ['lj', 'soft_sphere'])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_staged_force_kernel_bitwise_equals_direct(kind, dtype):
+  """The shared-memory staged force kernel (16-bit staging rows) evaluates the
+  same pairs in the same order as the global-gather kernel: forces, energies and
+  the fused half kick are bitwise equal.  N=13500: 1-2 row segments per block,
+  x wrap pieces, partially filled last block."""
+  jmd = _jmd()
+  R, L = util.fcc(15, dtype=dtype)
+  R = util.jitter(R, L, 0.05)
+  N = len(R)
+  d_g, s_g = jmd.space.periodic(L)
+  sp = _dev((np.arange(N) % 2).astype(np.int32))
+  outs = []
+  for stage in (True, False):
+    if kind == 'lj':
+      nf, efn = jmd.energy.lennard_jones_neighbor_list(
+          d_g, L, dr_threshold=0.3, format=jmd.partition.OrderedSparse, stage_positions=stage)
+    else:
+      nf, efn = jmd.energy.soft_sphere_neighbor_list(
+          d_g, L, species=sp, sigma=np.array([[1.0, 1.2], [1.2, 1.4]], np.float32),
+          dr_threshold=0.2, format=jmd.partition.Dense, stage_positions=stage)
+    Rd = _dev(R)
+    nb = nf.allocate(Rd)
+    ws = nb._ws
+    assert ws.c.staged == (1 if stage else 0)
+    if stage:
+      modes = ws.t['blk_table'][:(N + 255) // 256, 0]
+      cap = 57344 // (16 if dtype == np.float32 else 32)
+      if dtype == np.float32 and kind == 'lj':   # short rows (9 cells): a few blocks span too many rows
+        assert int(modes.sum()) >= 0.8 * modes.numel(), 'most blocks should be staged here'
+      assert int((ws.t['blk_table'][:(N + 255) // 256, 1] * modes).max()) <= cap
+    E = efn(Rd, neighbor=nb)
+    F = jmd.quantity.force(efn)(Rd, neighbor=nb)
+    init, step = jmd.simulate.nve(efn, s_g, 5e-3)
+    st = init(0, Rd, kT=1.0, momenta=_dev(util.momenta(N, 3, dtype=dtype)), neighbor=nb)
+    for _ in range(25):                       # crosses at least one rebuild
+      nb = nb.update(st.position)
+      st = step(st, neighbor=nb)
+    outs.append((E, F, st.position.clone(), st.momentum.clone(), nb.idx.clone()))
+  for a, b in zip(*outs):
+    assert torch.equal(a, b)

@@ -1,7 +1,9 @@
-"""Builds experiment variants of libjmd_b200.so (extra -D flags on one unit),
-as jax_md_b200/libjmd_b200_<tag>.so; select one with JMD_B200_LIB=<path>.
+"""Builds experiment variants of libjmd_b200.so (extra -D flags on the pair-force
+units), as jax_md_b200/libjmd_b200_<tag>.so; select one with JMD_B200_LIB=<path>.
 
-    python tools/build_variants.py tag unit.cu -DX=1 [-DY=2 ...]
+    python tools/build_variants.py tag [unit.cu ...] -DX=1 [-DY=2 ...]
+
+Units default to the pair-force units.
 """
 import os
 import subprocess
@@ -11,16 +13,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from jax_md_b200 import build as B   # noqa: E402
 
+PAIR_UNITS = ['jmd_pair.cu', 'jmd_pair_staged.cu']
+
 
 def main():
-  tag, unit, flags = sys.argv[1], sys.argv[2], sys.argv[3:]
+  tag = sys.argv[1]
+  units = [a for a in sys.argv[2:] if a.endswith('.cu')] or PAIR_UNITS
+  flags = [a for a in sys.argv[2:] if not a.endswith('.cu')]
   B.build()
-  obj = os.path.join(B.OBJ, unit.replace('.cu', f'_{tag}.o'))
-  cmd = [B.NVCC] + B.ARCH + B.COMMON + flags + ['-c', os.path.join(B.CSRC, unit), '-o', obj]
-  subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-  objs = [obj if u == unit else os.path.join(B.OBJ, u.replace('.cu', '.o')) for u in B.UNITS]
+  procs, objs = [], []
+  for u in B.UNITS:
+    if u in units:
+      obj = os.path.join(B.OBJ, u.replace('.cu', f'_{tag}.o'))
+      cmd = [B.NVCC] + B.ARCH + B.COMMON + flags + ['-c', os.path.join(B.CSRC, u), '-o', obj]
+      procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    else:
+      obj = os.path.join(B.OBJ, u.replace('.cu', '.o'))
+    objs.append(obj)
+  for p in procs:
+    assert p.wait() == 0
   out = os.path.join(B.HERE, f'libjmd_b200_{tag}.so')
-  subprocess.run([B.NVCC, '-shared', '-o', out] + objs + ['-lcudart'], check=True)
+  subprocess.run([B.NVCC, '-shared', '-o', out] + objs + ['-lcudart'], check=True,
+                 stderr=subprocess.DEVNULL)
   print(out)
 
 
