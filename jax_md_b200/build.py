@@ -54,7 +54,7 @@ def _run(cmd, verbose, log):
 def build(force=False, verbose=False):
   """Compile every CUDA unit for sm_100a; returns the .so path."""
   os.makedirs(OBJ, exist_ok=True)
-  stamp = os.path.join(OBJ, 'digest.txt')
+  stamp = OUT + '.digest'      # next to the .so: travels with it (csrc/_build does not)
   digest = _digest()
   if (not force and os.path.exists(OUT) and os.path.exists(stamp)
       and open(stamp).read() == digest):
