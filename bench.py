@@ -187,10 +187,24 @@ def run_b200(args):
   nbrs._ws.update_mode = args.update_mode
   state = init_fn(0, Rd, kT=KT, momenta=Pd, neighbor=nbrs)
 
+  def body(i, carry):
+    state, nbrs = carry
+    nbrs = nbrs.update(state.position)
+    state = apply_fn(state, neighbor=nbrs)
+    return state, nbrs
+
+  loop = {'g': None}
+
   def md_steps(state, nbrs, k):
-    for _ in range(k):
-      nbrs = nbrs.update(state.position)
-      state = apply_fn(state, neighbor=nbrs)
+    # the loop of examples/nve_neighbor_list.py:186-195; --loop graph runs it through
+    # jax_md_b200.lax.fori_loop (the jit(lax.fori_loop) of the reference: one CUDA
+    # graph of `unroll` steps, replayed), --loop eager launches step by step
+    if args.loop == 'graph' and k >= args.unroll:
+      out = jmd.lax.fori_loop(0, k, body, (state, nbrs), unroll=args.unroll, graph=loop['g'])
+      loop['g'] = jmd.lax.fori_loop.last
+      return out
+    for i in range(k):
+      state, nbrs = body(i, (state, nbrs))
     return state, nbrs
 
   def barrier():
@@ -202,6 +216,7 @@ def run_b200(args):
   if bool(nbrs.did_buffer_overflow):
     nbrs = nf.allocate(state.position)
     nbrs._ws.update_mode = args.update_mode
+    loop['g'] = None
   builds0 = nbrs._ws.state_host()[_lib.ST_BUILDS]
 
   # ---- timed region: exactly K steps, device timed ------------------------------
@@ -277,6 +292,7 @@ def run_b200(args):
   Pd = P_pin.to(dev, non_blocking=True)
   nb2 = nf.allocate(Rd)
   nb2._ws.update_mode = args.update_mode
+  loop['g'] = None            # a new list: its own graph (capture is inside the timed region)
   st2 = init_fn(0, Rd, kT=KT, momenta=Pd, neighbor=nb2)
   d2h = 0
   for _ in range(n_blocks):
@@ -304,7 +320,17 @@ def run_b200(args):
            'sample': f'LJ fcc N={Nc}, {args.cpu_steps} update+NVE steps, C port of the '
                      f'reference path on {th} threads ({secs:.1f} s)'}
 
-  rebuild_kernels = 12 if args.format == 'Dense' else 16
+  # kernels launched per step (all of them ours; gated launches that find
+  # nothing to do on a non-rebuild step are still launches): fused update =
+  # k_update + k_nbr_stencil_scan + k_update_c, then k_kick_drift + k_pair_force
+  if args.update_mode == 'fused':
+    per_step = 5
+  else:
+    per_step = 1 + 8 + 2 + (2 if args.format == 'Dense' else 7) + 2
+  # ncu --set full of this kernel at the default workload (profiles/r01_*): DRAM
+  # bytes per launch = the 4 B/pair index stream; positions stay in L2/L1
+  traffic = 356667648 if (N == 1000188 and args.format == 'OrderedSparse') else None
+  roofline['traffic'] = traffic
   line = {
       'metric': 'atom-timesteps/s', 'value': value, 'unit': 'atom-timesteps/s',
       'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
@@ -317,7 +343,7 @@ def run_b200(args):
                  'neighbor_overflow': overflow},
       'neighbor_rebuild_ms': rebuild_ms,
       'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
-      'gpu_launches': int(args.steps * 3 + builds * rebuild_kernels),
+      'gpu_launches': int(args.steps * per_step),
       'clocks': clocks,
   }
   print(json.dumps(line))
@@ -337,6 +363,8 @@ def main():
   ap.add_argument('--cpu-cells', type=int, default=40)
   ap.add_argument('--cpu-steps', type=int, default=40)
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--loop', default='graph', choices=['eager', 'graph'])
+  ap.add_argument('--unroll', type=int, default=20, help='steps per captured CUDA graph')
   ap.add_argument('--update-mode', default='fused', choices=['fused', 'gated'],
                   help="how update()'s lax.cond is realised: one cooperative kernel or gated kernels")
   args = ap.parse_args()

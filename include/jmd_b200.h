@@ -129,6 +129,14 @@ typedef struct {
    * buffer of the 256-slot block that owns the row; blk_table [n_pad / 256 + 1, 256]. */
   uint16_t* nl16;
   int32_t* blk_table;
+  /* Skin predicate fused into the drift (jmd_nve_kick_drift): skin_blk[b] != 0 iff an
+   * atom of drift block b (256 atoms, user order) moved further than skin/2 from its
+   * reference position.  skin_pre = 1 tells jmd_nbr_update that skin_blk describes
+   * exactly the `position` it is given (the host checks tensor identity), so the
+   * predicate pass over the positions is skipped. */
+  int32_t* skin_blk;       /* [n_pad / 256 + 1] or NULL */
+  int32_t skin_pre;
+  int32_t _pad4;
 } jmd_nbr_t;
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */

@@ -56,7 +56,8 @@ class NbrT(C.Structure):
       ('stencil_w', C.c_int32), ('no_filter', C.c_int32),
       ('fine_cell_size', C.c_double * 3), ('ref_count', C.c_void_p),
       ('brick_shift', C.c_int32), ('staged', C.c_int32), ('ref_start', C.c_void_p),
-      ('nl16', C.c_void_p), ('blk_table', C.c_void_p)]
+      ('nl16', C.c_void_p), ('blk_table', C.c_void_p),
+      ('skin_blk', C.c_void_p), ('skin_pre', C.c_int32), ('_pad4', C.c_int32)]
 
 
 class PairT(C.Structure):

@@ -25,6 +25,12 @@ struct StepP {
   typename Vec4<T>::type* pos_sorted;
   const int* inv_perm;
   const int* species;
+  // fused skin predicate (partition.py:1146-1154) against the list's reference positions
+  const T* ref;
+  int* skin_blk;
+  int n_rows;
+  T threshold_sq;
+  Space<T, DIM> nsp;       // the neighbour list's metric
 };
 
 template <typename T>
@@ -36,28 +42,42 @@ template <> __device__ __forceinline__ double4 mk4<double>(double x, double y, d
 template <typename T, int DIM>
 __global__ void __launch_bounds__(IB) k_kick_drift(StepP<T, DIM> S) {
   const int a = blockIdx.x * IB + threadIdx.x;
-  if (a >= S.n) return;
-  T dt = S.dt, dt_2 = S.dt_2;
-  if (S.dt_dev) {
-    dt = (T)(float)(*S.dt_dev);
-    dt_2 = (T)(float)(dt / T(2));
-  }
-  const T scale = S.scale_dev ? *S.scale_dev : T(1);
-  const T m = S.mass_is_array ? S.mass[a] : S.mass[0];
-  T r[3] = {T(0), T(0), T(0)};
+  bool moved = false;
+  if (a < S.n) {
+    T dt = S.dt, dt_2 = S.dt_2;
+    if (S.dt_dev) {
+      dt = (T)(float)(*S.dt_dev);
+      dt_2 = (T)(float)(dt / T(2));
+    }
+    const T scale = S.scale_dev ? *S.scale_dev : T(1);
+    const T m = S.mass_is_array ? S.mass[a] : S.mass[0];
+    T r[3] = {T(0), T(0), T(0)};
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) {
-    const size_t o = (size_t)a * DIM + k;
-    T p = S.p_in[o];
-    if (S.scale_dev) p *= scale;
-    p = p + dt_2 * S.f_in[o];
-    S.p_out[o] = p;
-    r[k] = S.sp.shift(S.r_in[o], dt * p / m, k);
-    S.r_out[o] = r[k];
+    for (int k = 0; k < DIM; ++k) {
+      const size_t o = (size_t)a * DIM + k;
+      T p = S.p_in[o];
+      if (S.scale_dev) p *= scale;
+      p = p + dt_2 * S.f_in[o];
+      S.p_out[o] = p;
+      r[k] = S.sp.shift(S.r_in[o], dt * p / m, k);
+      S.r_out[o] = r[k];
+    }
+    if (S.pos_sorted) {
+      T w = S.species ? (T)S.species[a] : T(0);
+      S.pos_sorted[S.inv_perm[a]] = mk4<T>(r[0], r[1], r[2], w);
+    }
+    if (S.skin_blk && a < S.n_rows) {
+      // the next NeighborList.update(R') asks: did any atom move further than skin/2
+      // from its reference position (strict >, min-image metric, exact arithmetic)?
+      T b[DIM];
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) b[k] = S.ref[(size_t)a * DIM + k];
+      moved = dist2_exact<T, DIM>(S.nsp, r, b) > S.threshold_sq;
+    }
   }
-  if (S.pos_sorted) {
-    T w = S.species ? (T)S.species[a] : T(0);
-    S.pos_sorted[S.inv_perm[a]] = mk4<T>(r[0], r[1], r[2], w);
+  if (S.skin_blk) {
+    const int any = __syncthreads_or(moved ? 1 : 0);
+    if (threadIdx.x == 0) S.skin_blk[blockIdx.x] = any;      // plain store: overwritten every drift
   }
 }
 
@@ -210,6 +230,14 @@ int launch_kick_drift(const jmd_space_t* sp, int n, const jmd_nbr_t* nb, const v
   S.pos_sorted = nb ? (typename Vec4<T>::type*)nb->pos_sorted : nullptr;
   S.inv_perm = nb ? nb->inv_perm : nullptr;
   S.species = nb ? nb->species : nullptr;
+  S.ref = nullptr; S.skin_blk = nullptr; S.n_rows = 0; S.threshold_sq = T(0);
+  S.nsp.init(nb ? nb->space : *sp);
+  if (nb && nb->skin_blk && nb->reference_position && nb->n == n) {
+    S.ref = (const T*)nb->reference_position;
+    S.skin_blk = nb->skin_blk;
+    S.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
+    S.threshold_sq = (T)nb->threshold_sq;
+  }
   k_kick_drift<T, DIM><<<(int)jmd_div_up(n > 0 ? n : 1, IB), IB, 0, s>>>(S);
   JMD_LAUNCH_CHECK();
   return 0;

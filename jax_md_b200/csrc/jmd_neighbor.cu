@@ -52,6 +52,8 @@ struct NbrP {
   int cps[3];          // INTERNAL (fine) search grid
   int bs, nb[3], rotate;   // storage order: bricks of (1 << bs)^DIM cells, nb bricks per side
   int* ref_start;          // [n_ref_cells + 1] exclusive scan of the counts in REFERENCE hash order
+  const int* skin_blk;     // per-drift-block predicate flags (jmd_nve_kick_drift)
+  int skin_pre;            // skin_blk describes exactly this `position`
   int staged;              // maintain the force kernel's staging plan (blk_table, nl16)
   int stage_cap;           // staging entries per block (JMD_STAGE_BYTES / sizeof(Vec4<T>))
   int* blk_table;
@@ -1156,11 +1158,22 @@ __global__ void __launch_bounds__(NB, 4) k_update(NbrP<T, DIM> P) {
   __shared__ Smem sm;
   unsigned int* bar = reinterpret_cast<unsigned int*>(&P.state[ST_BARRIER]);
   unsigned int target = 0;
-  const bool moved = ph_skin(P);
-  const int any = __syncthreads_or(moved ? 1 : 0);
-  if (threadIdx.x == 0 && any) atomicOr((unsigned long long*)&P.state[ST_PENDING], 1ull);
-  grid_sync(bar, target);
-  const bool rebuild = __ldcg(&P.state[ST_PENDING]) != 0 || P.always_rebuild;
+  bool rebuild;
+  if (P.skin_pre) {
+    // the drift kernel already evaluated the predicate for exactly these positions:
+    // every block ORs the per-drift-block flags itself (a few KB out of L2), no
+    // pass over the positions and no grid barrier on the common no-rebuild step
+    const int nblk = (P.n_rows + 255) / 256;
+    bool moved = false;
+    for (int b = threadIdx.x; b < nblk; b += NB) moved = moved || (__ldcg(&P.skin_blk[b]) != 0);
+    rebuild = __syncthreads_or(moved ? 1 : 0) != 0 || P.always_rebuild;
+  } else {
+    const bool moved = ph_skin(P);
+    const int any = __syncthreads_or(moved ? 1 : 0);
+    if (threadIdx.x == 0 && any) atomicOr((unsigned long long*)&P.state[ST_PENDING], 1ull);
+    grid_sync(bar, target);
+    rebuild = __ldcg(&P.state[ST_PENDING]) != 0 || P.always_rebuild;
+  }
   if (gtid() == 0) P.state[ST_REBUILD] = rebuild ? 1 : 0;
   if (!rebuild) { grid_exit(bar); return; }       // uniform over the whole grid
   if (P.use_cells) {
@@ -1240,6 +1253,8 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   if (P.bs < 0 || P.bs > 3) return JMD_EINVAL;
   P.rotate = 1;
   P.ref_start = nb->ref_start;
+  P.skin_blk = nb->skin_blk;
+  P.skin_pre = (nb->skin_pre && nb->skin_blk) ? 1 : 0;
   P.staged = (nb->staged && nb->blk_table && nb->nl16) ? 1 : 0;
   P.stage_cap = JMD_STAGE_BYTES / (int)sizeof(typename Vec4<T>::type);
   P.blk_table = nb->blk_table;

@@ -21,6 +21,7 @@ from . import _lib, dataclasses, space
 
 f32 = np.float32
 i32 = np.int32
+_FUSED_SKIN = os.environ.get('JMD_FUSED_SKIN', '1') != '0'    # debugging / A-B switch
 
 
 class PartitionErrorCode(IntEnum):
@@ -358,6 +359,9 @@ def neighbor_list(displacement_or_metric,
     ws.buf('reference_position', (n_buf, dim), position.dtype)
     ws.buf('error', (), torch.uint8, 0)
     ws.buf('state', (_lib.ST_COUNT,), torch.int64, 0)
+    # skin predicate fused into the drift kernel (simulate._Stepper.step)
+    ws.buf('skin_blk', (c.n_pad // 256 + 1,), i4, 0)
+    ws.drift_out = None            # (weakref to the drift's position tensor, its version)
     ws.cell_size_host = cell_size
     ws.use_cells = use_cells
     return ws
@@ -461,7 +465,13 @@ def neighbor_list(displacement_or_metric,
     position = position.contiguous()
     st, pp = _lib.stream(), _lib.ptr(position)
     if ws.update_mode == 'fused':
+      # Did the drift kernel already evaluate the predicate for THIS tensor
+      # (same object, not modified since)?  Then update() skips its own pass.
+      tag = ws.drift_out
+      ws.c.skin_pre = 1 if (_FUSED_SKIN and tag is not None and tag[0]() is position
+                            and tag[1] == position._version) else 0
       _lib.call('jmd_nbr_update', ws.ref(), pp, st)
+      ws.c.skin_pre = 0
     else:
       _lib.call('jmd_nbr_skin_check', ws.ref(), pp, st)
       _lib.call('jmd_nbr_bin', ws.ref(), pp, 1, st)

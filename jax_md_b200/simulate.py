@@ -147,6 +147,11 @@ class _Stepper:
               _lib.ptr(P), _lib.ptr(F), _lib.ptr(mass), mass_is_array, dt_h,
               _lib.ptr(dt_dev), _lib.ptr(scale_dev), _lib.ptr(R2), _lib.ptr(P2),
               st)
+    if fused:
+      # the drift evaluated the skin predicate of R2 against this list's
+      # reference positions (csrc/jmd_integrate.cu); update(R2) may reuse it
+      import weakref
+      ws.drift_out = (weakref.ref(R2), R2._version)
     if fused and self.fused == 'pair':
       out = self.fn.launch(R2, neighbor, species, params, want_energy=False,
                            momentum=P2, mass=mass, dt_2=dt2_h, dt_dev=dt_dev,

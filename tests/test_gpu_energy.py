@@ -471,3 +471,36 @@ def test_staged_force_kernel_bitwise_equals_direct(kind, dtype):
     outs.append((E, F, st.position.clone(), st.momentum.clone(), nb.idx.clone()))
   for a, b in zip(*outs):
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('fmt', ['Dense', 'OrderedSparse'])
+def test_fused_skin_predicate_same_rebuild_decisions(fmt):
+  """The skin predicate evaluated inside the drift kernel (and reused by
+  update() when it is handed that very tensor) takes the same rebuild
+  decisions as update()'s own pass: same rebuild steps, bitwise-equal states."""
+  jmd = _jmd()
+  R, L = util.fcc(10, dtype=np.float32)
+  R = util.jitter(R, L, 0.05)
+  N = len(R)
+  d_g, s_g = jmd.space.periodic(L)
+  out = []
+  for clone in (False, True):
+    nf, efn = jmd.energy.lennard_jones_neighbor_list(
+        d_g, L, dr_threshold=0.3, format=jmd.partition.NeighborListFormat[fmt])
+    init, step = jmd.simulate.nve(efn, s_g, 5e-3)
+    Rd = _dev(R)
+    nb = nf.allocate(Rd)
+    st = init(0, Rd, kT=1.5, momenta=_dev(util.momenta(N, 3, kT=1.5)), neighbor=nb)
+    builds = []
+    for i in range(60):
+      pos = st.position.clone() if clone else st.position     # a clone is never "the drift's tensor"
+      nb = nb.update(pos)
+      builds.append(nb._ws.state_host()[4])
+      st = step(st, neighbor=nb)
+      if i == 30 and not clone:
+        st.position.add_(0.0)      # in-place touch: version bump -> update() must not trust the flags
+    out.append((builds, st.position.clone(), st.momentum.clone(), nb.idx.clone()))
+  assert out[0][0] == out[1][0]
+  assert out[0][0][-1] - out[0][0][0] >= 3, 'the run should cross several rebuilds'
+  for a, b in zip(out[0][1:], out[1][1:]):
+    assert torch.equal(a, b)
