@@ -888,6 +888,11 @@ __device__ void ph_export(const NbrP<T, DIM>& P, Smem& sm) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
     const long long kend = dense ? cap : (long long)cmax;
+    // sparse formats: entries that are not exported (past the row, or id >= row id
+    // for OrderedSparse) are marked -1 when the tile is loaded; the write phase then
+    // needs one running 32-bit output position per slot (64-bit only past 2^32 entries)
+    const bool narrow = !dense && cap < (1ll << 32);
+    unsigned pos_l = (unsigned)off_l;
     for (int k0 = 0; k0 < kend; k0 += 32) {
       const int rows = min(32, cmax - k0);       // rows of this tile that hold data
       __syncwarp();
@@ -895,6 +900,8 @@ __device__ void ph_export(const NbrP<T, DIM>& P, Smem& sm) {
         // row entries (coalesced along slots) -> atom ids (perm gather), 8 independent
         // load->gather chains in flight per lane; the tile holds ATOM IDS
         const int* src = P.nl + (size_t)k0 * P.n_pad + slot;
+        const int drop = dense ? P.n : -1;
+        const int id_limit = ordered ? a_l : 0x7fffffff;
 #pragma unroll 1
         for (int r0 = 0; r0 < rows; r0 += 8) {
           int jv[8];
@@ -902,24 +909,47 @@ __device__ void ph_export(const NbrP<T, DIM>& P, Smem& sm) {
           for (int u = 0; u < 8; ++u)     // entries past this slot's own row are garbage
             jv[u] = (k0 + r0 + u < c_l) ? __ldcs(src + (size_t)(r0 + u) * P.n_pad) : -1;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) jv[u] = jv[u] >= 0 ? __ldg(&P.perm[jv[u]]) : P.n;
+          for (int u = 0; u < 8; ++u) {
+            int v = jv[u] >= 0 ? __ldg(&P.perm[jv[u]]) : drop;
+            if (!dense && v >= id_limit) v = -1;
+            jv[u] = v;
+          }
 #pragma unroll
           for (int u = 0; u < 8; ++u) tile[r0 + u][lane] = jv[u];
         }
       }
       __syncwarp();
       const int k = k0 + lane;
+      if (dense) {
 #pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int a = __shfl_sync(0xffffffffu, a_l, r);
-        if (a < 0) break;                            // slots beyond n (uniform)
-        const int c = __shfl_sync(0xffffffffu, c_l, r);
-        const bool in_row = k < c;
-        const int v = in_row ? tile[lane][r] : P.n;
-        if (dense) {
+        for (int r = 0; r < 32; ++r) {
+          const int a = __shfl_sync(0xffffffffu, a_l, r);
+          if (a < 0) break;                            // slots beyond n (uniform)
+          const int c = __shfl_sync(0xffffffffu, c_l, r);
+          const int v = k < c ? tile[lane][r] : P.n;
           if (k < cap) P.idx[(size_t)a * cap + k] = v;
-        } else {
-          const bool keep = in_row && (!ordered || v < a);
+        }
+      } else if (narrow) {
+        const unsigned ucap = (unsigned)cap;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int a = __shfl_sync(0xffffffffu, a_l, r);
+          if (a < 0) break;
+          const int v = (lane < rows) ? tile[lane][r] : -1;
+          const unsigned b = __ballot_sync(0xffffffffu, v >= 0);
+          const unsigned base = __shfl_sync(0xffffffffu, pos_l, r);
+          const unsigned pos = base + __popc(b & lt);
+          if (v >= 0 && pos < ucap) { P.idx[pos] = v; P.idx[cap + pos] = a; }
+          if (lane == r) pos_l += __popc(b);
+        }
+      } else {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int a = __shfl_sync(0xffffffffu, a_l, r);
+          if (a < 0) break;
+          const int v = (lane < rows) ? tile[lane][r] : -1;
+          const bool keep = v >= 0;
           const unsigned b = __ballot_sync(0xffffffffu, keep);
           const long long off = __shfl_sync(0xffffffffu, off_l, r);
           const int kk = __shfl_sync(0xffffffffu, kk_l, r);

@@ -431,6 +431,7 @@ class SlabDomain:
 # ----------------------------------------------------------------------------------
 
 def bench_domain(args, world, rank, dev):
+  import time
   """Weak-scaling LJ NVE: every rank owns a slab of `cells^3` fcc cells stacked
   along x; prints the JSON line on rank 0 (bench.py contract)."""
   import json
@@ -480,10 +481,62 @@ def bench_domain(args, world, rank, dev):
   n_ghost = torch.tensor([st.n_ghost], dtype=torch.int64, device=dev)
   dist.all_reduce(n_ghost, op=dist.ReduceOp.MAX)
   ke = dom.kinetic_energy()
+  rebuilds_timed = dom.rebuilds - r0
+
+  # ---- dominant kernel (fused force + half kick) timed inside 20 more steps -------
+  ws = dom.nbrs._ws
+  pairs = int(torch.clamp(ws.t['cnt'][:st.n_own + st.n_ghost], max=ws.c.m_int).sum())
+  kernel_bytes = pairs * 20 + st.n_own * 60
+  evs = []
+  plain_force = dom._force
+
+  def timed_force(state, kick):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    plain_force(state, kick=kick)
+    b.record()
+    evs.append((a, b))
+
+  dom._force = timed_force
+  for _ in range(20):
+    st = dom.step(st)
+  torch.cuda.synchronize()
+  dom._force = plain_force
+  k_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in evs[3:]]))],
+                      dtype=torch.float64, device=dev)
+  dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
+  kb = torch.tensor([kernel_bytes], dtype=torch.int64, device=dev)
+  dist.all_reduce(kb, op=dist.ReduceOp.MAX)
+
+  # ---- end to end: pinned host state -> H2D -> init (first build) -> steps -> D2H ---
+  R_pin = torch.from_numpy(R_loc).pin_memory()
+  P_pin = Pd.cpu().pin_memory()
+  out_R = torch.empty_like(R_pin).pin_memory()
+  out_P = torch.empty_like(P_pin).pin_memory()
+  e2e_steps = args.steps
+  torch.cuda.synchronize()
+  dist.barrier()
+  t0 = time.perf_counter()
+  dom2 = SlabDomain(box, efn, bench.R_CUT, bench.SKIN, bench.DT, comm=comm)
+  st2 = dom2.init(R_pin.to(dev, non_blocking=True), P_pin.to(dev, non_blocking=True), gid)
+  for i in range(e2e_steps):
+    st2 = dom2.step(st2)
+    if (i + 1) % args.block == 0:
+      dom2.kinetic_energy()                       # global KE read back, like the example loop
+  out_R.copy_(st2.R[:N_loc], non_blocking=True)   # (slab populations drift by a few atoms;
+  out_P.copy_(st2.P[:N_loc], non_blocking=True)   #  the copy size is the initial one)
+  torch.cuda.synchronize()
+  dist.barrier()
+  e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+  dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+
   if rank == 0:
     ms_total = float(ms.item())
     N = int(n_tot.item())
     face_bytes = int(n_ghost.item()) * 12
+    peak, peak_src = bench.peaks()
+    kms = float(k_ms.item())
+    achieved = float(kb.item()) / (kms * 1e-3) / 1e9
     line = {
         'metric': 'atom-timesteps/s', 'value': N * args.steps / (ms_total * 1e-3),
         'unit': 'atom-timesteps/s', 'n_gpus': world, 'steps': args.steps,
@@ -494,12 +547,22 @@ def bench_domain(args, world, rank, dev):
                                f'skin={bench.SKIN} dt={bench.DT} kT={bench.KT} NVE, slab decomposition along x',
                    'atoms': N, 'ghost_atoms_per_gpu': int(n_ghost.item()),
                    'halo_bytes_per_step_per_gpu': face_bytes,
-                   'rebuilds_in_timed_region': dom.rebuilds - r0,
+                   'rebuilds_in_timed_region': rebuilds_timed,
+                   'loop': 'eager Python loop (one host decision per step, NCCL halo exchange)',
                    'l2_policy': 'working set exceeds L2',
                    'kinetic_energy_per_atom': ke / N},
-        'roofline': None, 'cpu_baseline': None,
-        'e2e': None,
-        'gpu_launches': int(args.steps * 5 + (dom.rebuilds - r0) * 20),
+        'roofline': {'bound': 'hbm', 'kernel': 'k_pair_force<float,3,LJ,scalar,kick> (slowest rank)',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'peak_source': peak_src, 'kernel_ms': kms,
+                     'algorithmic_bytes_per_launch': int(kb.item())},
+        'cpu_baseline': None,
+        'e2e': {'value': N * e2e_steps / float(e2e_s.item()), 'unit': 'atom-timesteps/s',
+                'h2d_bytes_per_step': 2 * N_loc * 12 * world / e2e_steps,
+                'd2h_bytes_per_step': (2 * N_loc * 12 * world + 8 * world * (e2e_steps // args.block)) / e2e_steps,
+                'steps': e2e_steps,
+                'includes': 'per rank: H2D of the slab state, domain init (first neighbour build, ghost '
+                            f'selection), {e2e_steps} steps, global KE readback every {args.block} steps, D2H of state'},
+        'gpu_launches': int(world * (args.steps * 6 + rebuilds_timed * 24)),
         'clocks': clocks,
     }
     print(json.dumps(line))

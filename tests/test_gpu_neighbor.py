@@ -330,3 +330,29 @@ def test_prefilter_equals_exact_scan_at_scale(fmt):
   assert a.max_occupancy == b.max_occupancy
   assert torch.equal(a.idx, b.idx)
   assert int(a.error.code) == int(b.error.code)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_prefilter_2d_rectangular(fmt, dtype):
+  """2-D rectangular box with >= 5 cells per side (pre-filter active): random
+  atoms, near-cutoff partners and atoms on / outside the faces."""
+  rng = np.random.default_rng(21)
+  box = np.array([31.0, 24.5], np.float32)
+  N, cut = 6000, 1.45
+  R = (rng.random((N, 2)) * box).astype(dtype)
+  m = N // 3
+  ang = rng.random(m) * 2 * np.pi
+  eps = np.finfo(dtype).eps
+  scale = 1.0 + rng.integers(-5, 6, m) * eps * rng.choice([1, 8, 64], m)
+  R[m:2 * m] = np.mod(R[:m].astype(np.float64) + (cut * scale)[:, None] *
+                      np.stack([np.cos(ang), np.sin(ang)], 1), box.astype(np.float64)).astype(dtype)
+  R[-1] = box
+  R[-2] = [0, box[1]]
+  R[-3] = [-1e-6, 3.0]
+  R[-40:-3] += box.astype(dtype)                     # unwrapped
+  nf_o, nf_g = _build_both(R, box, 1.2, 0.25, fmt)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  assert nb_g._ws.c.no_filter == 0 and min(nb_g._ws.c.fine_cps[k] for k in range(2)) >= 5
+  _assert_same(nb_o, nb_g)
