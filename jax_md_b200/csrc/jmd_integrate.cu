@@ -232,11 +232,16 @@ int launch_kick_drift(const jmd_space_t* sp, int n, const jmd_nbr_t* nb, const v
   S.species = nb ? nb->species : nullptr;
   S.ref = nullptr; S.skin_blk = nullptr; S.n_rows = 0; S.threshold_sq = T(0);
   S.nsp.init(nb ? nb->space : *sp);
-  if (nb && nb->skin_blk && nb->reference_position && nb->n == n) {
-    S.ref = (const T*)nb->reference_position;
-    S.skin_blk = nb->skin_blk;
-    S.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
-    S.threshold_sq = (T)nb->threshold_sq;
+  if (nb && nb->skin_blk && nb->reference_position) {
+    // drift over all atoms of the list, or over its owned rows (domain decomposition:
+    // ghosts are refreshed by the halo exchange and have no skin check)
+    const int rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
+    if (n == nb->n || n == rows) {
+      S.ref = (const T*)nb->reference_position;
+      S.skin_blk = nb->skin_blk;
+      S.n_rows = rows < n ? rows : n;
+      S.threshold_sq = (T)nb->threshold_sq;
+    }
   }
   k_kick_drift<T, DIM><<<(int)jmd_div_up(n > 0 ? n : 1, IB), IB, 0, s>>>(S);
   JMD_LAUNCH_CHECK();

@@ -362,8 +362,15 @@ class SlabDomain:
     needs the answer (start of the next step) the GPU is still busy with the
     force kernel and never waits for the host."""
     ws = self.nbrs._ws
-    _lib.call('jmd_nbr_skin_check', ws.ref(), _lib.ptr(st.R), _lib.stream())
-    flag = ws.t['state'][_lib.ST_REBUILD:_lib.ST_REBUILD + 1]
+    if self._drift_flags:
+      # the drift kernel just left one skin flag per 256 owned atoms (jmd_integrate.cu)
+      nblk = (st.n_own + 255) // 256
+      flag = ws.t['skin_blk'][:nblk].max().to(torch.int64).reshape(1)
+      if ws.c.always_rebuild:
+        flag = torch.ones_like(flag)
+    else:
+      _lib.call('jmd_nbr_skin_check', ws.ref(), _lib.ptr(st.R), _lib.stream())
+      flag = ws.t['state'][_lib.ST_REBUILD:_lib.ST_REBUILD + 1]
     if self.comm.world > 1:
       if self.comm.direct:
         self._flag_dev.copy_(flag)
@@ -379,6 +386,7 @@ class SlabDomain:
 
   def _take_decision(self, st):
     if not self._decision_pending:
+      self._drift_flags = False          # no drift produced these positions
       self._launch_decision(st)
     self._flag_event.synchronize()
     self._decision_pending = False
@@ -396,6 +404,7 @@ class SlabDomain:
               _lib.ptr(st.R), _lib.ptr(st.P), _lib.ptr(st.F), _lib.ptr(self.mass), 0,
               self.dt, None, None, _lib.ptr(st.R), _lib.ptr(st.P), s)
     #    the next step's rebuild decision, overlapped with steps 4-5
+    self._drift_flags = True
     self._launch_decision(st)
     # 4. halo exchange of the drifted face atoms, refresh the sorted ghost copies
     if st.n_ghost:
