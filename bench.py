@@ -187,15 +187,18 @@ def run_b200(args):
   nbrs._ws.update_mode = args.update_mode
   state = init_fn(0, Rd, kT=KT, momenta=Pd, neighbor=nbrs)
 
-  def body(i, carry):
-    state, nbrs = carry
-    nbrs = nbrs.update(state.position)
-    state = apply_fn(state, neighbor=nbrs)
-    return state, nbrs
+  def make_body(apply):
+    def body(i, carry):
+      state, nbrs = carry
+      nbrs = nbrs.update(state.position)
+      state = apply(state, neighbor=nbrs)
+      return state, nbrs
+    return body
 
+  body = make_body(apply_fn)
   loop = {'g': None}
 
-  def md_steps(state, nbrs, k):
+  def md_steps(state, nbrs, k, body=body, loop=loop):
     # the loop of examples/nve_neighbor_list.py:186-195; --loop graph runs it through
     # jax_md_b200.lax.fori_loop (the jit(lax.fori_loop) of the reference: one CUDA
     # graph of `unroll` steps, replayed), --loop eager launches step by step
@@ -233,6 +236,34 @@ def run_b200(args):
   builds = nbrs._ws.state_host()[_lib.ST_BUILDS] - builds0
   overflow = bool(nbrs.did_buffer_overflow)
   value = N * args.steps / (ms_total * 1e-3)
+
+  # ---- variant: public idx materialised lazily (lazy_idx=True; not the headline) ---
+  variants = {}
+  if not args.no_variants:
+    nf_l, efn_l = jmd.energy.lennard_jones_neighbor_list(
+        disp, L, r_onset=2.0, r_cutoff=R_CUT, dr_threshold=SKIN, format=fmt, lazy_idx=True)
+    init_l, apply_l = jmd.simulate.nve(efn_l, shift, DT)
+    nb_l = nf_l.allocate(state.position)
+    st_l = init_l(0, state.position.clone(), kT=KT, momenta=state.momentum.clone(), neighbor=nb_l)
+    body_l, loop_l = make_body(apply_l), {'g': None}
+    st_l, nb_l = md_steps(st_l, nb_l, 100, body_l, loop_l)
+    barrier()
+    b0 = nb_l._ws.state_host()[_lib.ST_BUILDS]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    st_l, nb_l = md_steps(st_l, nb_l, args.steps, body_l, loop_l)
+    b.record()
+    barrier()
+    ms_l = a.elapsed_time(b)
+    idx_l = nb_l.idx                      # first read: the export runs now
+    variants['lazy_idx'] = {
+        'value': N * args.steps / (ms_l * 1e-3), 'ms_per_step': ms_l / args.steps,
+        'rebuilds': int(nb_l._ws.state_host()[_lib.ST_BUILDS] - b0),
+        'note': 'lazy_idx=True: rebuilds inside update() leave the public idx stale on the device; '
+                'it is exported when NeighborList.idx is read (once, after the loop, here). The '
+                'headline value keeps the default: idx rewritten at every rebuild.',
+        'idx_shape_after_read': list(idx_l.shape)}
+    del nb_l, st_l, idx_l, loop_l
 
   # ---- neighbour rebuild time (one full forced rebuild) -------------------------
   ws = nbrs._ws
@@ -349,7 +380,7 @@ def run_b200(args):
                  if args.loop == 'graph' else 'eager Python loop',
                  'neighbor_overflow': overflow},
       'neighbor_rebuild_ms': rebuild_ms,
-      'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+      'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'variants': variants,
       'gpu_launches': int(args.steps * per_step),
       'clocks': clocks,
   }
@@ -370,6 +401,7 @@ def main():
   ap.add_argument('--cpu-cells', type=int, default=40)
   ap.add_argument('--cpu-steps', type=int, default=40)
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--no-variants', action='store_true')
   ap.add_argument('--loop', default='graph', choices=['eager', 'graph'])
   ap.add_argument('--unroll', type=int, default=20, help='steps per captured CUDA graph')
   ap.add_argument('--update-mode', default='fused', choices=['fused', 'gated'],

@@ -62,7 +62,8 @@ enum {
   JMD_ST_TOTAL = 3,        /* total entries in requested sparse format */
   JMD_ST_BUILDS = 4,       /* number of rebuilds executed */
   JMD_ST_SCAN_TICKET = 5,
-  JMD_ST_COUNT = 8
+  JMD_ST_EXPORT_PENDING = 8, /* public idx is stale (lazy_idx): set by a rebuild, cleared by the export */
+  JMD_ST_COUNT = 16
 };
 
 /* Neighbour-list workspace: the hidden part of partition.NeighborList
@@ -136,7 +137,9 @@ typedef struct {
    * predicate pass over the positions is skipped. */
   int32_t* skin_blk;       /* [n_pad / 256 + 1] or NULL */
   int32_t skin_pre;
-  int32_t _pad4;
+  /* 1: jmd_nbr_update leaves the public `idx` stale after a rebuild (state[EXPORT_PENDING])
+   * and jmd_nbr_export(gated = 2) materialises it on demand (NeighborList.idx read). */
+  int32_t lazy_idx;
 } jmd_nbr_t;
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */
@@ -167,6 +170,7 @@ int jmd_nbr_build(const jmd_nbr_t* nb, const void* position, int count_only,
 
 /* Export internal rows to the public idx in nb->format, update the error
  * code (partition.py:1066,1110), store reference_position, clear REBUILD. */
+/* gated: 0 run, 1 run if this update() rebuilt, 2 run if idx is stale (lazy_idx). */
 int jmd_nbr_export(const jmd_nbr_t* nb, const void* position, int gated,
                    void* stream);
 

@@ -18,7 +18,8 @@ SPACE_FREE, SPACE_PERIODIC = 0, 1
 POT_LJ, POT_SOFT_SPHERE, POT_MORSE = 0, 1, 2
 PARAM_SCALAR, PARAM_PER_ATOM, PARAM_SPECIES, PARAM_MATRIX = 0, 1, 2, 3
 ST_REBUILD, ST_MAX_CELL_OCC, ST_MAX_ROW, ST_TOTAL, ST_BUILDS = 0, 1, 2, 3, 4
-ST_COUNT = 8
+ST_EXPORT_PENDING = 8
+ST_COUNT = 16
 # jmd_dd_* info words (include/jmd_b200.h)
 (DD_N_OWN, DD_FACE_L, DD_FACE_R, DD_FROM_L, DD_FROM_R, DD_ERROR, DD_MIG_L, DD_MIG_R,
  DD_IN_L, DD_IN_R) = range(10)
@@ -57,7 +58,7 @@ class NbrT(C.Structure):
       ('fine_cell_size', C.c_double * 3), ('ref_count', C.c_void_p),
       ('brick_shift', C.c_int32), ('staged', C.c_int32), ('ref_start', C.c_void_p),
       ('nl16', C.c_void_p), ('blk_table', C.c_void_p),
-      ('skin_blk', C.c_void_p), ('skin_pre', C.c_int32), ('_pad4', C.c_int32)]
+      ('skin_blk', C.c_void_p), ('skin_pre', C.c_int32), ('lazy_idx', C.c_int32)]
 
 
 class PairT(C.Structure):

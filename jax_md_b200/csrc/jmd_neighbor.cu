@@ -29,6 +29,7 @@
 
 namespace {
 
+enum { ST_EXPORT = JMD_ST_EXPORT_PENDING };
 enum { ST_REBUILD = JMD_ST_REBUILD, ST_MAX_CELL = JMD_ST_MAX_CELL_OCC,
        ST_MAX_ROW = JMD_ST_MAX_ROW, ST_TOTAL = JMD_ST_TOTAL,
        ST_BUILDS = JMD_ST_BUILDS, ST_TICKET = JMD_ST_SCAN_TICKET,
@@ -58,6 +59,7 @@ struct NbrP {
   int cps[3];          // INTERNAL (fine) search grid
   int bs, nb[3], rotate;   // storage order: bricks of (1 << bs)^DIM cells, nb bricks per side
   int* ref_start;          // [n_ref_cells + 1] exclusive scan of the counts in REFERENCE hash order
+  int lazy_idx;            // update(): leave the public idx stale (EXPORT_PENDING) instead of exporting
   const int* skin_blk;     // per-drift-block predicate flags (jmd_nve_kick_drift)
   int skin_pre;            // skin_blk describes exactly this `position`
   int staged;              // maintain the force kernel's staging plan (blk_table, nl16)
@@ -93,6 +95,11 @@ struct Smem {
 };
 
 __device__ __forceinline__ int gtid() { return blockIdx.x * NB + threadIdx.x; }
+// gated launches: 0 always run, 1 only when this update() decided to rebuild,
+// 2 only when the public idx is stale (lazy materialisation)
+__device__ __forceinline__ bool gate_closed(const long long* state, int gated) {
+  return gated && state[gated == 2 ? (int)ST_EXPORT : (int)ST_REBUILD] == 0;
+}
 __device__ __forceinline__ int gthreads() { return gridDim.x * NB; }
 
 // Grid-wide barrier for the persistent update kernels.  They are launched with
@@ -995,6 +1002,7 @@ __device__ void ph_finalize(const NbrP<T, DIM>& P) {
     if (P.state[ST_MAX_ROW] > P.m_int) e |= JMD_ERR_NEIGHBOR_LIST_OVERFLOW;
     *P.error = (uint8_t)e;
     P.state[ST_BUILDS] += 1;
+    P.state[ST_EXPORT] = (P.lazy_idx && !P.no_public_idx) ? 1 : 0;
   }
 }
 
@@ -1010,11 +1018,11 @@ __device__ __forceinline__ int* ref_sums(const NbrP<T, DIM>& P) {
 // ---- one ordinary kernel per phase (allocate path / gated fallback) -----------------------
 enum Phase { PH_ZERO, PH_HASH, PH_SCAN1, PH_SCAN2, PH_SCAN3, PH_SCATTER, PH_RANK, PH_INVPERM,
              PH_IDENTITY, PH_PACK, PH_BUILD_RESET, PH_BUILD, PH_SP_COUNTS, PH_SP_SCAN1,
-             PH_SP_SCAN2, PH_SP_SCAN3, PH_EXPORT, PH_SP_PAD, PH_FINALIZE };
+             PH_SP_SCAN2, PH_SP_SCAN3, PH_EXPORT, PH_SP_PAD, PH_FINALIZE, PH_EXPORT_DONE };
 
 template <typename T, int DIM, int PHASE>
 __global__ void __launch_bounds__(NB, 3) k_phase(NbrP<T, DIM> P, int gated) {
-  if (gated && P.state[ST_REBUILD] == 0) return;
+  if (gate_closed(P.state, gated)) return;
   __shared__ Smem sm;
   long long* sp_sums = (long long*)P.scan_tmp;
   switch (PHASE) {
@@ -1047,6 +1055,7 @@ __global__ void __launch_bounds__(NB, 3) k_phase(NbrP<T, DIM> P, int gated) {
     case PH_EXPORT: ph_export(P, sm); break;
     case PH_SP_PAD: ph_sparse_pad(P); break;
     case PH_FINALIZE: ph_finalize(P); break;
+    case PH_EXPORT_DONE: if (gtid() == 0) P.state[ST_EXPORT] = 0; break;
   }
 }
 
@@ -1062,7 +1071,7 @@ inline int grid_for(long long work_items, int per_block, int cap_blocks) {
 // is its own kernel so that it gets its own register allocation.
 template <typename T, int DIM, int FMT, bool PERIODIC, int W, bool FILTER>
 __global__ void __launch_bounds__(NB, JMD_SCAN_MIN_BLOCKS) k_nbr_stencil_scan(NbrP<T, DIM> P, int gated) {
-  if (gated && P.state[ST_REBUILD] == 0) return;
+  if (gate_closed(P.state, gated)) return;
   constexpr int MODE = (FMT == 0 && PERIODIC) ? 1 : 0;
   // COUNT (OrderedSparse occupancy pass of allocate: no rows are written, so the
   // id-lower count has to be taken inside the candidate loop); STAGE: also emit
@@ -1077,7 +1086,7 @@ __global__ void __launch_bounds__(NB, JMD_SCAN_MIN_BLOCKS) k_nbr_stencil_scan(Nb
 
 template <typename T, int DIM>
 __global__ void __launch_bounds__(NB, 3) k_nbr_all_pairs(NbrP<T, DIM> P, int gated) {
-  if (gated && P.state[ST_REBUILD] == 0) return;
+  if (gate_closed(P.state, gated)) return;
   ph_build_all_pairs<T, DIM>(P);
 }
 
@@ -1113,7 +1122,7 @@ void launch_scan(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 
 template <typename T, int DIM>
 __global__ void __launch_bounds__(NB, JMD_EXPORT_MIN_BLOCKS) k_nbr_export(NbrP<T, DIM> P, int gated) {
-  if (gated && P.state[ST_REBUILD] == 0) return;
+  if (gate_closed(P.state, gated)) return;
   if (P.no_public_idx) return;
   __shared__ Smem sm;
   ph_export(P, sm);
@@ -1149,7 +1158,10 @@ void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 template <typename T, int DIM>
 void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   const int G = JMD_SM_COUNT * 8;
-  if (P.no_public_idx) {
+  // lazy materialisation: an update() only stores the reference positions and the
+  // error bits and marks idx stale; the export itself runs (gated == 2) when the
+  // host reads NeighborList.idx
+  if (P.no_public_idx || (P.lazy_idx && gated == 1)) {
     LAUNCH(PH_FINALIZE, grid_for((long long)P.n * DIM, NB, G));
     return;
   }
@@ -1162,7 +1174,8 @@ void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   }
   k_nbr_export<T, DIM><<<grid_for((long long)P.n, NB, 1 << 30), NB, 0, stream>>>(P, gated);
   if (P.format != JMD_DENSE) LAUNCH(PH_SP_PAD, grid_for(P.max_occupancy / 4 + 1, NB, G));
-  LAUNCH(PH_FINALIZE, grid_for((long long)P.n * DIM, NB, G));
+  if (gated == 2) LAUNCH(PH_EXPORT_DONE, 1);
+  else LAUNCH(PH_FINALIZE, grid_for((long long)P.n * DIM, NB, G));
 }
 
 // Skin predicate alone (gated mode): the last block latches the decision.
@@ -1251,7 +1264,7 @@ template <typename T, int DIM>
 __global__ void __launch_bounds__(NB, JMD_EXPORT_MIN_BLOCKS) k_update_c(NbrP<T, DIM> P) {
   if (P.state[ST_REBUILD] == 0) return;
   __shared__ Smem sm;
-  if (P.no_public_idx) { ph_finalize(P); return; }
+  if (P.no_public_idx || P.lazy_idx) { ph_finalize(P); return; }
   if (P.format != JMD_DENSE) {
     unsigned int* bar = reinterpret_cast<unsigned int*>(&P.state[ST_BARRIER]);
     unsigned int target = 0;
@@ -1289,6 +1302,7 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   if (P.bs < 0 || P.bs > 3) return JMD_EINVAL;
   P.rotate = 1;
   P.ref_start = nb->ref_start;
+  P.lazy_idx = 0;
   P.skin_blk = nb->skin_blk;
   P.skin_pre = (nb->skin_pre && nb->skin_blk) ? 1 : 0;
   P.staged = (nb->staged && nb->blk_table && nb->nl16) ? 1 : 0;
@@ -1413,6 +1427,7 @@ int jmd_nbr_update(const jmd_nbr_t* nb, const void* position, void* stream) {
     NbrP<T, DIM> P;
     int rc = fill(P, nb, position);
     if (rc) return rc;
+    P.lazy_idx = nb->lazy_idx ? 1 : 0;
     return launch_update<T, DIM>(P, (cudaStream_t)stream);
   });
 }
@@ -1464,6 +1479,7 @@ int jmd_nbr_export(const jmd_nbr_t* nb, const void* position, int gated, void* s
     NbrP<T, DIM> P;
     int rc = fill(P, nb, position);
     if (rc) return rc;
+    P.lazy_idx = (nb->lazy_idx && gated == 1) ? 1 : 0;     // gated == 1: part of an update()
     launch_export<T, DIM>(P, gated, (cudaStream_t)stream_);
     JMD_LAUNCH_CHECK();
     return 0;

@@ -174,7 +174,27 @@ class NeighborList:
   @property
   def internal_list_is_current(self) -> bool:
     """True while `idx` is the array our builder wrote (nobody swapped it)."""
-    return self._ws is not None and self._ws.t.get('idx') is self.idx
+    return self._ws is not None and self._ws.t.get('idx') is self.__dict__['idx']
+
+
+def _idx_get(self):
+  """`NeighborList.idx`.  With `lazy_idx=True` a rebuild inside update() only
+  marks the public array stale on the device; reading the attribute enqueues the
+  (device-gated) export first, so what the caller sees is always the array of
+  the current list in the requested format."""
+  v = self.__dict__['idx']
+  ws = self.__dict__.get('_ws')
+  if ws is not None and ws.c.lazy_idx and ws.t.get('idx') is v and not ws.c.no_public_idx:
+    _lib.call('jmd_nbr_export', ws.ref(), None, 2, _lib.stream())
+  return v
+
+
+def _idx_set(self, value):
+  self.__dict__['idx'] = value
+
+
+# a data descriptor on the frozen dataclass: __init__ / replace() store through it
+NeighborList.idx = property(_idx_get, _idx_set)
 
 
 @dataclasses.dataclass
@@ -340,6 +360,8 @@ def neighbor_list(displacement_or_metric,
     # exact_scan=True (static kwarg): evaluate the reference arithmetic on every
     # candidate instead of only inside the pre-filter's rounding band (testing).
     c.no_filter = 1 if static_kwargs.get('exact_scan', False) else 0
+    # lazy_idx=True (static kwarg): see NeighborList.idx
+    c.lazy_idx = 1 if static_kwargs.get('lazy_idx', False) else 0
     n_cells_buf = c.n_fine_cells
     i4 = torch.int32
     ws.buf('cell_count', (n_cells_buf + 1,), i4, 0)

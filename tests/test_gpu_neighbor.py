@@ -356,3 +356,37 @@ def test_prefilter_2d_rectangular(fmt, dtype):
   nb_g = nf_g.allocate(_dev(R))
   assert nb_g._ws.c.no_filter == 0 and min(nb_g._ws.c.fine_cps[k] for k in range(2)) >= 5
   _assert_same(nb_o, nb_g)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('mode', ['fused', 'gated'])
+def test_lazy_idx_materialises_on_read(fmt, mode):
+  """lazy_idx=True: update() leaves idx stale on the device after a rebuild and
+  reading NeighborList.idx exports it; the array read is identical to the eager one."""
+  jmd = _mods()
+  R, L = util.fcc(12, dtype=np.float32)
+  R = util.jitter(R, L, 0.05)
+  d_g, _ = jmd.space.periodic(L)
+  F = jmd.partition.NeighborListFormat[fmt]
+  rng = np.random.default_rng(3)
+  moves = [np.mod(R + rng.normal(0, s, R.shape).astype(np.float32), L).astype(np.float32)
+           for s in (0.01, 0.2, 0.02, 0.25)]
+  lists = []
+  for lazy in (False, True):
+    nf = jmd.partition.neighbor_list(d_g, L, np.float32(2.5), np.float32(0.3), format=F, lazy_idx=lazy)
+    nb = nf.allocate(_dev(R))
+    nb._ws.update_mode = mode
+    seen = [nb.idx.clone()]
+    for i, Rm in enumerate(moves):
+      nb = nb.update(_dev(Rm))
+      if lazy:
+        pending = nb._ws.state_host()[8]
+        assert pending == (1 if i in (1, 3) else 0) or i == 2   # rebuilds at the big moves
+      if i != 1:                          # skip one read: the next rebuild supersedes it
+        seen.append(nb.idx.clone())
+        if lazy:
+          assert nb._ws.state_host()[8] == 0
+    lists.append((seen, nb.reference_position.clone(), int(nb.error.code)))
+  for a, b in zip(lists[0][0], lists[1][0]):
+    assert torch.equal(a, b)
+  assert torch.equal(lists[0][1], lists[1][1]) and lists[0][2] == lists[1][2]

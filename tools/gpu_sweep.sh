@@ -1,13 +1,10 @@
 mkdir -p gpurun_out
-(time python bench.py) > gpurun_out/s20_bench.log 2>&1
-(time python bench.py --impl reference --steps 20 --warmup 3) > gpurun_out/s20_ref.log 2>&1
-(time python -c "import __graft_entry__ as g; g.smoke()") > gpurun_out/s20_smoke.log 2>&1
-tail -4 gpurun_out/s20_smoke.log
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/s21_tests.log 2>&1; tail -3 gpurun_out/s21_tests.log
+(time python bench.py --no-cpu) > gpurun_out/s21_bench.log 2>&1
 python - <<'PY'
 import json
-for f in ['gpurun_out/s20_bench.log','gpurun_out/s20_ref.log']:
-  for l in open(f):
+for l in open('gpurun_out/s21_bench.log'):
     try: d=json.loads(l)
-    except Exception: print(l[:200].rstrip()); continue
-    print(d.get('impl','b200'), d['value'], d['ms_per_step'], d.get('neighbor_rebuild_ms'), (d.get('roofline') or {}).get('kernel_ms'), d['e2e']['value'], d.get('cpu_baseline'))
+    except Exception: print(l[:300].rstrip()); continue
+    print(d['ms_per_step'], d['neighbor_rebuild_ms'], d['roofline']['kernel_ms'], d['config']['rebuilds_in_timed_region'], d['e2e']['value'], d['variants'])
 PY
