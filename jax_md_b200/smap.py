@@ -251,18 +251,118 @@ class PairNeighborListFn:
     return _Energy.apply(R, *[p for _, p in grad_params])
 
 
+class GenericPairNeighborListFn:
+  """`smap.pair_neighbor_list` (smap.py:856-979) for an ARBITRARY Python
+  `fn(dr, **params)` written with torch ops -- SURVEY.md 8(f) row 1.  The
+  neighbour list comes from the CUDA builder; the energy is composed exactly as
+  the reference composes it (gather `R[idx]` with the padding index clamped,
+  metric, `fn`, mask `idx < N`, high-precision sum / normalisation) and is
+  differentiable through `torch.autograd` (forces via `quantity.force`).  This
+  is the generic, un-fused path: the potentials of `energy.py` never take it."""
+  _jmd_fused = None
+
+  def __init__(self, fn, displacement_or_metric, species, reduce_axis,
+               ignore_unused_parameters, kwargs):
+    self.fn = fn
+    self.d = displacement_or_metric
+    self.species = species
+    self.reduce_axis = reduce_axis
+    self.ignore_unused = ignore_unused_parameters
+    self.kwargs = dict(kwargs)
+    self.kwargs.pop('fractional_coordinates', None)
+    self._is_metric = None
+
+  def _metric(self, Ra, Rb, **kw):
+    """space.canonicalize_displacement_or_metric (space.py:505-522)."""
+    if self._is_metric is None:
+      probe = self.d(Ra.reshape(-1, Ra.shape[-1])[:1], Rb.reshape(-1, Rb.shape[-1])[:1])
+      self._is_metric = probe.ndim == 1
+    out = self.d(Ra, Rb, **kw)
+    return out if self._is_metric else space.distance(out)
+
+  def _param(self, v, i, j, si, sj, R):
+    """smap.py:697-846: scalar | per-atom [N] through a combinator (default
+    mean) | [N, N] | species table [S, S]; `(combinator, per_atom)` tuples."""
+    comb = lambda a, b: 0.5 * (a + b)
+    if isinstance(v, tuple) and len(v) == 2 and callable(v[0]):
+      comb, v = v
+    if isinstance(v, (int, float)):
+      return v
+    v = torch.as_tensor(v, device=R.device) if not isinstance(v, torch.Tensor) else v.to(R.device)
+    if v.ndim == 0:
+      return v
+    if si is not None:
+      if v.ndim == 2:
+        return v[si, sj]
+      raise ValueError('Parameters with species must be scalars or [S, S] tables; found '
+                       f'shape {tuple(v.shape)}.')
+    if v.ndim == 1:
+      return comb(v[i], v[j])
+    if v.ndim == 2:
+      return v[i, j]
+    raise ValueError(f'Parameter must be a scalar, a vector or a matrix; found {v.ndim} dims.')
+
+  def __call__(self, R, neighbor=None, **dynamic_kwargs):
+    if neighbor is None:
+      raise ValueError('neighbor must be passed (positionally or as neighbor=).')
+    N = R.shape[0]
+    species = dynamic_kwargs.pop('species', self.species)
+    merged = _merge(self.kwargs, dynamic_kwargs, self.ignore_unused)
+    space_kw = {k: merged.pop(k) for k in ('perturbation',) if k in merged}
+    idx = neighbor.idx.long()
+    sparse = partition.is_sparse(neighbor.format)
+    if sparse:
+      recv, send = idx[0], idx[1]
+      mask = recv < N
+      j, i = recv.clamp(max=N - 1), send.clamp(max=N - 1)
+      dr = self._metric(R[i], R[j], **space_kw)                 # smap.py:935-937
+      norm = 1.0 if neighbor.format is partition.OrderedSparse else 2.0
+    else:
+      mask = idx < N
+      j = idx.clamp(max=N - 1)                                   # OOB gather clamps
+      i = torch.arange(N, device=R.device)[:, None].expand_as(j)
+      dr = self._metric(R[:, None, :], R[j], **space_kw)        # smap.py:938-940
+      norm = 2.0
+    si = sj = None
+    if species is not None:
+      sp = torch.as_tensor(species, device=R.device).long()
+      si, sj = sp[i], sp[j]
+    params = {k: self._param(v, i, j, si, sj, R) for k, v in merged.items()}
+    out = self.fn(dr, **params)
+    out = torch.where(mask, out, torch.zeros_like(out))
+    ra = self.reduce_axis
+    if ra is None:
+      return _hp_sum(out) / norm
+    if len(ra) == 0:
+      return out / norm
+    if not sparse:
+      return _hp_sum(out, tuple(a for a in ra)) / norm
+    if neighbor.format is partition.OrderedSparse:
+      raise ValueError('Cannot report per-particle values with an OrderedSparse neighbor list '
+                       '(smap.py:969-974).')
+    per_atom = torch.zeros(N, dtype=torch.float64, device=R.device)
+    per_atom.index_add_(0, recv[mask], out[mask].double())       # segment_sum on idx[0]
+    return per_atom.to(R.dtype) / norm
+
+
+def _hp_sum(x, axis=None):
+  if axis is None:
+    return x.sum(dtype=torch.float64).to(x.dtype)
+  return x.sum(dim=axis, dtype=torch.float64).to(x.dtype)
+
+
 def pair_neighbor_list(fn, displacement_or_metric, species=None,
                        reduce_axis=None, ignore_unused_parameters=False,
                        **kwargs):
-  """smap.py:856-979.  `fn` must be one of this package's pair potentials
-  (`energy.lennard_jones`, `energy.soft_sphere`, `energy.morse`), optionally
-  wrapped by `energy.multiplicative_isotropic_cutoff`."""
+  """smap.py:856-979.  For this package's pair potentials
+  (`energy.lennard_jones`, `energy.soft_sphere`, `energy.morse`, optionally
+  wrapped by `energy.multiplicative_isotropic_cutoff`) the mapped function is
+  the fused CUDA kernel; any other Python `fn(dr, **params)` is mapped by
+  `GenericPairNeighborListFn` (torch ops over the CUDA-built list)."""
   pot = getattr(fn, '_jmd_potential', None)
   if pot is None:
-    raise NotImplementedError(
-        'pair_neighbor_list over an arbitrary Python `fn` is row 1 of '
-        'SURVEY.md 8(f) ("next"); the fused path covers lennard_jones, '
-        'soft_sphere and morse.')
+    return GenericPairNeighborListFn(fn, displacement_or_metric, species, reduce_axis,
+                                     ignore_unused_parameters, kwargs)
   for k in kwargs:
     if callable(kwargs[k]) and not isinstance(kwargs[k], torch.Tensor):
       raise NotImplementedError('custom parameter combinators')
