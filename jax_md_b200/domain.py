@@ -18,6 +18,7 @@ Per step (host-orchestrated, one host read per step for the global decision):
   4. halo: gather-pack face positions (jmd_dd_pack) -> send/recv -> ghosts
   5. fused force + second half kick over owned rows (jmd_pair_force)
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -43,6 +44,9 @@ class RingComm:
     self.left = (self.rank - 1) % self.world
     self.right = (self.rank + 1) % self.world
     self.direct = dist.is_initialized() and dist.get_backend(group) == 'nccl'
+    # the per-step rebuild flag is all-reduced on its own communicator (own NCCL
+    # stream), so it never queues in front of the halo exchange
+    self.flag_group = dist.new_group(backend='nccl') if (self.direct and self.world > 1) else group
 
   def _stage(self, t):
     return t if (self.direct or not t.is_cuda) else t.cpu()
@@ -234,6 +238,7 @@ class SlabDomain:
     self._flag_dev = torch.zeros(1, dtype=torch.int64, device=dev)
     self._flag_host = torch.zeros(1, dtype=torch.int64).pin_memory()
     self._flag_event = torch.cuda.Event()
+    self._side_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
     self._decision_pending = False
     self._rebuild(st, first=True)
     self._force(st, kick=False)
@@ -362,26 +367,36 @@ class SlabDomain:
     needs the answer (start of the next step) the GPU is still busy with the
     force kernel and never waits for the host."""
     ws = self.nbrs._ws
-    if self._drift_flags:
-      # the drift kernel just left one skin flag per 256 owned atoms (jmd_integrate.cu)
-      nblk = (st.n_own + 255) // 256
-      flag = ws.t['skin_blk'][:nblk].max().to(torch.int64).reshape(1)
-      if ws.c.always_rebuild:
-        flag = torch.ones_like(flag)
-    else:
+    main = torch.cuda.current_stream()
+    side = self._side_stream if self.device.type == 'cuda' else None
+    if not self._drift_flags:
       _lib.call('jmd_nbr_skin_check', ws.ref(), _lib.ptr(st.R), _lib.stream())
-      flag = ws.t['state'][_lib.ST_REBUILD:_lib.ST_REBUILD + 1]
-    if self.comm.world > 1:
-      if self.comm.direct:
-        self._flag_dev.copy_(flag)
-        dist.all_reduce(self._flag_dev, op=dist.ReduceOp.MAX, group=self.comm.group)
-        self._flag_host.copy_(self._flag_dev, non_blocking=True)
-      else:                                   # gloo: staged through the host
-        self._flag_host.copy_(flag)
-        dist.all_reduce(self._flag_host, op=dist.ReduceOp.MAX, group=self.comm.group)
-    else:
-      self._flag_host.copy_(flag, non_blocking=True)
-    self._flag_event.record()
+    # The reduction of the flags, their all-reduce across ranks and the copy to the
+    # host run on a side stream: the main stream goes straight on to the halo
+    # exchange and the force kernel instead of waiting for the collective.
+    if side is not None:
+      side.wait_stream(main)
+    ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+    with ctx:
+      if self._drift_flags:
+        # the drift kernel just left one skin flag per 256 owned atoms (jmd_integrate.cu)
+        nblk = (st.n_own + 255) // 256
+        flag = ws.t['skin_blk'][:nblk].max().to(torch.int64).reshape(1)
+        if ws.c.always_rebuild:
+          flag = torch.ones_like(flag)
+      else:
+        flag = ws.t['state'][_lib.ST_REBUILD:_lib.ST_REBUILD + 1]
+      if self.comm.world > 1:
+        if self.comm.direct:
+          self._flag_dev.copy_(flag)
+          dist.all_reduce(self._flag_dev, op=dist.ReduceOp.MAX, group=self.comm.flag_group)
+          self._flag_host.copy_(self._flag_dev, non_blocking=True)
+        else:                                   # gloo: staged through the host
+          self._flag_host.copy_(flag)
+          dist.all_reduce(self._flag_host, op=dist.ReduceOp.MAX, group=self.comm.group)
+      else:
+        self._flag_host.copy_(flag, non_blocking=True)
+      self._flag_event.record()
     self._decision_pending = True
 
   def _take_decision(self, st):
@@ -390,6 +405,8 @@ class SlabDomain:
       self._launch_decision(st)
     self._flag_event.synchronize()
     self._decision_pending = False
+    if self.device.type == 'cuda':      # the side stream is idle now; order it before the next drift
+      torch.cuda.current_stream().wait_stream(self._side_stream)
     return bool(int(self._flag_host[0]) != 0)
 
   def step(self, st):
