@@ -44,6 +44,67 @@ def canonicalize_force(energy_or_force_fn):
   return force_fn
 
 
+def volume(dimension, box):
+  """quantity.py:110-121."""
+  if isinstance(box, (int, float)):
+    return float(box) ** dimension
+  b = torch.as_tensor(box) if not isinstance(box, torch.Tensor) else box
+  if b.ndim == 0:
+    return b ** dimension
+  if b.ndim == 1:
+    return torch.prod(b)
+  if b.ndim == 2:
+    return torch.linalg.det(b)
+  raise ValueError(f'Box must be either: a scalar, a vector, or a matrix. Found {box}.')
+
+
+def _dU_deps(energy_fn, position, eps0, make_perturbation, kwargs):
+  """grad of U(eps) = energy_fn(R, perturbation=...) at eps = 0 by autograd
+  (generic energy functions)."""
+  eps = eps0.clone().requires_grad_(True)
+  with torch.enable_grad():
+    U = energy_fn(position, perturbation=make_perturbation(eps), **kwargs)
+    (g,) = torch.autograd.grad(U, eps)
+  return g
+
+
+def pressure(energy_fn, position, box, kinetic_energy=0.0, **kwargs):
+  """quantity.py:202-235: P = (2 KE - dU/deps) / (dim V), eps the isotropic box
+  strain.  Fused neighbour-list energies answer from the virial their force
+  kernel accumulates; anything else differentiates through `perturbation=`."""
+  dim = position.shape[1]
+  vol_0 = volume(dim, box)
+  if getattr(energy_fn, '_jmd_fused', None) == 'pair':
+    dUdV = torch.trace(energy_fn.virial(position, **kwargs))
+  elif getattr(energy_fn, '_jmd_fused', None):
+    raise NotImplementedError('pressure of the fused many-body energies: SURVEY.md 8(f) row 2')
+  else:
+    zero = torch.zeros((), dtype=position.dtype, device=position.device)
+    dUdV = _dU_deps(energy_fn, position, zero, lambda e: 1 + e, kwargs)
+  return 1 / (dim * vol_0) * (2 * kinetic_energy - dUdV)
+
+
+def stress(energy_fn, position, box, mass=1.0, velocity=None, **kwargs):
+  """quantity.py:238-282: (sum m v v^T - dU/deps) / V, eps the box strain tensor."""
+  dim = position.shape[1]
+  vol_0 = volume(dim, box)
+  if getattr(energy_fn, '_jmd_fused', None) == 'pair':
+    dUdV = energy_fn.virial(position, **kwargs)
+  elif getattr(energy_fn, '_jmd_fused', None):
+    raise NotImplementedError('stress of the fused many-body energies: SURVEY.md 8(f) row 2')
+  else:
+    zero = torch.zeros((dim, dim), dtype=position.dtype, device=position.device)
+    eye = torch.eye(dim, dtype=position.dtype, device=position.device)
+    dUdV = _dU_deps(energy_fn, position, zero, lambda e: eye + e, kwargs)
+  VxV = 0.0
+  if velocity is not None:
+    m = _mass_like(mass, velocity)
+    if isinstance(m, torch.Tensor) and m.ndim == 2:
+      m = m[:, :, None]
+    VxV = util.high_precision_sum(m * velocity[:, None, :] * velocity[:, :, None], axis=0)
+  return 1 / vol_0 * (VxV - dUdV)
+
+
 def count_dof(position):
   """quantity.py:105-108."""
   return position.numel()

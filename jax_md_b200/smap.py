@@ -193,6 +193,22 @@ class PairNeighborListFn:
     return dict(force=force, red=red, e_atom=e_atom, dparam=dparam, modes=modes,
                 n_species=pt.n_species, keep=keep)
 
+  def virial(self, R, neighbor=None, **dynamic_kwargs):
+    """dU/d(eps_ab) at eps = 0 for the box perturbation `(I + eps)` of
+    space.py:299-300, i.e. sum over pairs of (dU/dr)/r * d_a * d_b -- the
+    quantity `quantity.pressure` / `quantity.stress` obtain in the reference by
+    differentiating through `perturbation=` (quantity.py:226-235, 268-282);
+    here it is a by-product of the fused force kernel.  -> [dim, dim]."""
+    neighbor, species, params = self._resolve(neighbor, dict(dynamic_kwargs))
+    red = self.launch(R, neighbor, species, params, True)['red']
+    v = red[_lib.RED_VIRIAL:_lib.RED_VIRIAL + 6].to(R.dtype)      # xx yy zz xy xz yz
+    dim = R.shape[1]
+    if dim == 2:
+      return torch.stack([torch.stack([v[0], v[3]]), torch.stack([v[3], v[1]])])
+    return torch.stack([torch.stack([v[0], v[3], v[4]]),
+                        torch.stack([v[3], v[1], v[5]]),
+                        torch.stack([v[4], v[5], v[2]])])
+
   def force(self, R, neighbor=None, **dynamic_kwargs):
     """-dE/dR straight from the kernel (quantity.force fast path)."""
     neighbor, species, params = self._resolve(neighbor, dict(dynamic_kwargs))

@@ -174,6 +174,10 @@ def test_jammed_soft_sphere_golden(fmt):
   nbrs = nf.allocate(R)
   np.testing.assert_allclose(float(efn(R, neighbor=nbrs)), G['jammed_energy'],
                              rtol=1e-10)
+  # tests/quantity_test.py:134-150: P = 0.06307342050945483 of the same state, here
+  # from the virial the fused force kernel accumulates (quantity.pressure)
+  P = jmd.quantity.pressure(efn, R, L, neighbor=nbrs)
+  np.testing.assert_allclose(float(P), G['jammed_pressure'], rtol=1e-9)
 
 
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
@@ -558,3 +562,32 @@ def test_generic_pair_neighbor_list_matches_fused(fmt, dtype):
     st = step(st, neighbor=nb)
   E1 = float(gen(st.position, neighbor=nb)) + float(jmd.quantity.kinetic_energy(momentum=st.momentum))
   assert abs(E1 - E0) < 2e-4 * abs(E0)
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_stress_lammps_golden_and_generic_path(dtype):
+  """tests/quantity_test.py:436-455: LAMMPS LJ (hard cutoff 2.5) energy per atom and
+  stress tensor incl. the kinetic term; the fused kernel's virial, and the same
+  numbers from the generic path (autograd through `perturbation=`)."""
+  jmd = _jmd()
+  s = np.load(os.path.join(util.GOLDEN, 'lammps_lj.npz'))
+  box = np.float32(s['box'])
+  R = _dev((s['R'] * box).astype(dtype))
+  V = _dev(s['V'].astype(dtype))
+  r = s['stress_row']
+  C = np.array([[r[0], r[3], r[4]], [r[3], r[1], r[5]], [r[4], r[5], r[2]]])
+  d, _ = jmd.space.periodic(box)
+  # list cutoff 2.5 with no skin == the hard cutoff of the LAMMPS run
+  nf = jmd.partition.neighbor_list(d, box, np.float32(2.5), np.float32(0.0), format=jmd.partition.Dense)
+  nb = nf.allocate(R)
+  fused = jmd.smap.pair_neighbor_list(jmd.energy.lennard_jones, d)
+  generic = jmd.smap.pair_neighbor_list(lambda dr, **kw: jmd.energy.lennard_jones(dr), d)
+  tol = 5e-5
+  for efn in (fused, generic):
+    np.testing.assert_allclose(float(efn(R, neighbor=nb)) / len(R), float(s['energy_per_atom']),
+                               rtol=tol, atol=tol)
+    S = jmd.quantity.stress(efn, R, box, velocity=V, neighbor=nb).cpu().numpy()
+    np.testing.assert_allclose(S, C, rtol=tol, atol=tol)
+  Pf = float(jmd.quantity.pressure(fused, R, box, neighbor=nb))
+  Pg = float(jmd.quantity.pressure(generic, R, box, neighbor=nb))
+  np.testing.assert_allclose(Pf, Pg, rtol=1e-5 if dtype == np.float32 else 1e-10)
