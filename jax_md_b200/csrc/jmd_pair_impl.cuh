@@ -25,6 +25,13 @@ constexpr int PAIR_BLOCK = JMD_PAIR_BLOCK;
 #define JMD_PAIR_BATCH 4
 #endif
 constexpr int PAIR_BATCH = JMD_PAIR_BATCH;   // row entries in flight per loop trip (power of two)
+#ifndef JMD_PAIR_IDXTMA
+#define JMD_PAIR_IDXTMA 0
+#endif
+#ifndef JMD_PAIR_IDXCH
+#define JMD_PAIR_IDXCH 16
+#endif
+constexpr int IDX_CH = JMD_PAIR_IDXCH;       // rows per TMA stage of the index stream
 #ifndef JMD_PAIR_ALWAYS_WRAP
 #define JMD_PAIR_ALWAYS_WRAP 1   /* measured: branch-free rint() form 2 % faster than the |d| > L/2 test */
 #endif
@@ -252,9 +259,10 @@ __global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_STAGED ? 4 : JMD_PAIR_MIN
   for (int i = 0; i < NV; ++i) rv[i] = 0.0;
 
   const int ai = t < Q.n ? Q.perm[t] : 0x7fffffff;
-  if (ai < Q.n_rows) {                      // ghosts (ids >= n_rows) have no row
-    const V4 pi = Q.pos_sorted[t];
-    const int cnt = min(Q.cnt[t], Q.m_int);
+  const bool valid = ai < Q.n_rows;         // ghosts (ids >= n_rows) have no row
+  {
+    const V4 pi = valid ? Q.pos_sorted[t] : V4();
+    const int cnt = valid ? min(Q.cnt[t], Q.m_int) : 0;
     const int si = (int)pi.w;
     T f[3] = {T(0), T(0), T(0)};
     T e = T(0), ds = T(0), de = T(0);
@@ -358,16 +366,84 @@ __global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_STAGED ? 4 : JMD_PAIR_MIN
     } else
 #endif
     {
+#if JMD_PAIR_IDXTMA && !JMD_PAIR_STAGED
+      // The row entries are a pure stream (read once per step) and the kernel sits on
+      // the L1 sector rate of the position gathers, so the stream is taken off the
+      // LSU/L1 path: one thread issues TMA bulk copies (cp.async.bulk) of the block's
+      // next IDX_CH rows (one contiguous 1 KB segment each) into a two-stage
+      // shared-memory ring while the block evaluates the current ones.
+      __shared__ __align__(128) int ibuf[2][IDX_CH][PAIR_BLOCK];
+      __shared__ __align__(8) unsigned long long ibar[2];
+      __shared__ int kmax_s;
+      if (threadIdx.x == 0) {
+        kmax_s = 0;
+        for (int b = 0; b < 2; ++b)
+          asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&ibar[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      {
+        int wmax = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(&kmax_s, wmax);
+      }
+      __syncthreads();
+      const int kmax = kmax_s;
+      const int nch = (kmax + IDX_CH - 1) / IDX_CH;
+      const long long blk0 = (long long)blockIdx.x * PAIR_BLOCK;
+      const int cols = (int)min((long long)PAIR_BLOCK, Q.n_pad - blk0);     // ints per row segment
+      auto issue = [&](int c) {            // thread 0: rows [c*IDX_CH, ...) -> ibuf[c & 1]
+        const int rows = min(IDX_CH, kmax - c * IDX_CH);
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&ibar[c & 1]);
+        const unsigned bytes = (unsigned)cols * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * rows) : "memory");
+        const int* src = Q.nl + (size_t)(c * IDX_CH) * np + blk0;
+        for (int r = 0; r < rows; ++r) {
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+              ::"r"((unsigned)__cvta_generic_to_shared(&ibuf[c & 1][r][0])),
+                "l"(__cvta_generic_to_global(src + (size_t)r * np)), "r"(bytes), "r"(bar)
+              : "memory");
+        }
+      };
+      if (threadIdx.x == 0 && nch > 0) issue(0);
+      for (int c = 0; c < nch; ++c) {
+        if (threadIdx.x == 0 && c + 1 < nch) issue(c + 1);   // its buffer was released by the barrier below
+        {
+          const unsigned bar = (unsigned)__cvta_generic_to_shared(&ibar[c & 1]);
+          const unsigned parity = (unsigned)(c >> 1) & 1u;
+          unsigned done = 0;
+          while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+          }
+        }
+        const int kend = min(cnt - c * IDX_CH, IDX_CH);
+        const int* rowp = &ibuf[c & 1][0][threadIdx.x];
+#pragma unroll(PAIR_BATCH)
+        for (int r = 0; r < kend; ++r) {
+          const int j = rowp[r * PAIR_BLOCK];
+          pair(j, ld_pos(&Q.pos_sorted[j]));
+        }
+        __syncthreads();
+      }
+#else
 #pragma unroll(PAIR_BATCH)
       for (int k = 0; k < cnt; ++k) {
         const int j = __ldcs(col + (size_t)k * np);        // streamed once: keep it out of L1
         pair(j, ld_pos(&Q.pos_sorted[j]));
       }
+#endif
     }
 #if JMD_PAIR_STAGED
     };   // run
     if (Q.has_cutoff) run(std::true_type()); else run(std::false_type());
 #endif
+    if (valid) {
     T* fo = Q.force + (size_t)ai * DIM;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) fo[k] = f[k];
@@ -408,6 +484,7 @@ __global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_STAGED ? 4 : JMD_PAIR_MIN
       rv[7] = 0.5 * (double)ds;
       rv[8] = 0.5 * (double)de;
     }
+    }   // valid
   }
   if (RED >= 1) {
     __shared__ double sm[NV * (PAIR_BLOCK / 32)];
