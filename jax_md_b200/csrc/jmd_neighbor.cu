@@ -45,7 +45,7 @@ enum { ST_REBUILD = JMD_ST_REBUILD, ST_MAX_CELL = JMD_ST_MAX_CELL_OCC,
 #define JMD_SCAN_UNROLL 4
 #endif
 #ifndef JMD_SCAN_MIN_BLOCKS
-#define JMD_SCAN_MIN_BLOCKS 5
+#define JMD_SCAN_MIN_BLOCKS 4
 #endif
 constexpr int NB = 256;           // threads per block, every kernel here
 constexpr int NWARP = NB / 32;
@@ -714,9 +714,10 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
       int off_end_i = (int)((unsigned)kmax * (unsigned)P.n_pad + (unsigned)slot);
       keep_in_register(off_end_i);
       const unsigned off_end = (unsigned)off_end_i;
-      for (int s0 = -w; s0 <= w; ++s0)
-      for (int s1 = -w; s1 <= w; ++s1)
-      for (int s2 = -wz; s2 <= wz; ++s2) {
+      // One stencil cell: its slot range, dirty flag and the home position shifted
+      // into its periodic image.
+      struct Cell { int start, end, dirty, s1, s2; T hs0, hs1, hs2; bool skip; };
+      auto lookup = [&](const int s0, const int s1, const int s2) -> Cell {
         const int sh[3] = {s0, s1, s2};
         float gap2 = 0.f;
         int sv[3] = {0, 0, 0};
@@ -736,10 +737,24 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
           else if (v >= P.cps[d]) { v -= P.cps[d]; hs[d] = hp[d] - P.sp.side[d]; }
           sv[d] = v;
         }
-        const int h = cell_id(P, sv);
-        if (WSTAT != 1 && gap2 > gap_limit) continue;
-        const int start = __ldg(&P.cell_start[h]);
-        const int end = __ldg(&P.cell_start[h + 1]);
+        Cell C;
+        C.s1 = s1; C.s2 = s2;
+        C.hs0 = hs[0]; C.hs1 = hs[1]; C.hs2 = hs[2];
+        C.skip = WSTAT != 1 && gap2 > gap_limit;
+        C.start = C.end = C.dirty = 0;
+        if (!C.skip) {
+          const int h = cell_id(P, sv);
+          C.start = __ldg(&P.cell_start[h]);
+          C.end = __ldg(&P.cell_start[h + 1]);
+          C.dirty = FILTER ? (__ldg(&P.cell_cursor[h]) & CELL_DIRTY) : 0;
+        }
+        return C;
+      };
+      auto scan_cell = [&](const Cell& C) {
+        if (C.skip) return;
+        const int start = C.start, end = C.end, s1 = C.s1, s2 = C.s2;
+        const T hs[3] = {C.hs0, C.hs1, C.hs2};
+        (void)s1; (void)s2;
         // staging index of a candidate = lbase + its slot (see ph_plan)
         int lbase = 0;
         if (STAGE && stage_on) {
@@ -749,7 +764,7 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
         }
         T lo_c = P.f_lo, hi_c = P.f_hi;
         if (FILTER) {
-          if (home_dirty || (__ldg(&P.cell_cursor[h]) & CELL_DIRTY)) {
+          if (home_dirty || C.dirty) {
             lo_c = T(-1);                       // a2 >= 0: never accepted unseen
             hi_c = (T)INFINITY;                 // never rejected unseen
           }
@@ -798,6 +813,27 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
             }
           }
         }
+      
+      };
+      if (WSTAT == 1) {
+        // The cell-table loads of stencil cell s+1 are issued before the candidates
+        // of cell s are scanned (27 dependent load chains per atom otherwise).
+        constexpr int NS = DIM == 3 ? 27 : 9;
+        Cell nxt = lookup(-1, -1, DIM == 3 ? -1 : 0);
+#pragma unroll 1
+        for (int si = 0; si < NS; ++si) {
+          const Cell cur = nxt;
+          if (si + 1 < NS) {
+            const int t = si + 1;
+            if (DIM == 3) nxt = lookup(t / 9 - 1, (t / 3) % 3 - 1, t % 3 - 1);
+            else nxt = lookup(t / 3 - 1, t % 3 - 1, 0);
+          }
+          scan_cell(cur);
+        }
+      } else {
+        for (int s0 = -w; s0 <= w; ++s0)
+        for (int s1 = -w; s1 <= w; ++s1)
+        for (int s2 = -wz; s2 <= wz; ++s2) scan_cell(lookup(s0, s1, s2));
       }
       if (ORDERED && !COUNT) {
         // entries whose atom id is below the row's id (OrderedSparse keeps those,
