@@ -328,10 +328,12 @@ class GenericPairNeighborListFn:
     idx = neighbor.idx.long()
     sparse = partition.is_sparse(neighbor.format)
     if sparse:
-      recv, send = idx[0], idx[1]
+      recv = idx[0]
       mask = recv < N
-      j, i = recv.clamp(max=N - 1), send.clamp(max=N - 1)
-      dr = self._metric(R[i], R[j], **space_kw)                 # smap.py:935-937
+      # entries are (idx[0], idx[1]) in that order for the metric AND the parameter
+      # lookups p[idx[0], idx[1]] (smap.py:712-725, 935-937)
+      i, j = idx[0].clamp(max=N - 1), idx[1].clamp(max=N - 1)
+      dr = self._metric(R[i], R[j], **space_kw)
       norm = 1.0 if neighbor.format is partition.OrderedSparse else 2.0
     else:
       mask = idx < N
