@@ -84,6 +84,13 @@ class PairNeighborListFn:
       t = x.detach().to(device=device, dtype=dtype).contiguous()
     else:
       t = torch.as_tensor(np.asarray(x), dtype=dtype, device=device).contiguous()
+    if t.ndim == 2 and t.dtype.is_floating_point and not bool(torch.equal(t, t.T)):
+      # The fused kernel takes the force on atom i from row i alone, which is
+      # -dE/dR_i only when p[a, b] == p[b, a]; checked once per parameter object.
+      raise NotImplementedError(
+          'asymmetric [S, S] / [N, N] parameter tables are not served by the fused '
+          'kernel; wrap the potential in a plain Python function to take the generic '
+          'smap.pair_neighbor_list path.')
     if len(self._conv) > 64:
       self._conv.clear()
     self._conv[key] = (x, t)

@@ -162,7 +162,11 @@ def pair_neighbor_list_energy(pot, displacement, R, nbrs, species=None,
   a, b, mask, rows = _entries(R, nbrs)
   dR = displacement(R[a], R[b])
   dr = space.distance(dR)
-  p = {k: _expand(v, a, b, species) for k, v in params.items()}
+  # parameter lookups: Sparse p[idx[0], idx[1]] (smap.py:712,722,794); Dense
+  # p[row, idx] (smap.py:714,725,797) -- the ROW atom comes first there, while the
+  # displacement is d(R_neigh, R_row) (map_neighbor)
+  pa, pb = (b, a) if rows is not None else (a, b)
+  p = {k: _expand(v, pa, pb, species) for k, v in params.items()}
   out = pot.energy(dr, **p) * mask
   norm = 1.0 if nbrs.format is OrderedSparse else 2.0
   if per_particle:
@@ -199,7 +203,8 @@ def pair_neighbor_list_energy(pot, displacement, R, nbrs, species=None,
       dparams[name] = 0.5 * (np.bincount(af, weights=w, minlength=N)[:N] +
                              np.bincount(bf, weights=w, minlength=N)[:N])
     else:
-      sa, sb = (species[af], species[bf]) if species is not None else (af, bf)
+      paf, pbf = pa.reshape(-1), pb.reshape(-1)
+      sa, sb = (species[paf], species[pbf]) if species is not None else (paf, pbf)
       out_t = np.zeros(pv.shape, np.float64)
       np.add.at(out_t, (sa, sb), w)
       dparams[name] = out_t

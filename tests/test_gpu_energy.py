@@ -591,3 +591,43 @@ def test_stress_lammps_golden_and_generic_path(dtype):
   Pf = float(jmd.quantity.pressure(fused, R, box, neighbor=nb))
   Pg = float(jmd.quantity.pressure(generic, R, box, neighbor=nb))
   np.testing.assert_allclose(Pf, Pg, rtol=1e-5 if dtype == np.float32 else 1e-10)
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+def test_asymmetric_species_table_orientation(fmt):
+  """smap.py:794-797: Dense looks up p[species[row], species[neighbour]], the sparse
+  formats p[species[idx[0]], species[idx[1]]].  An asymmetric table tells them apart."""
+  jmd = _jmd()
+  R, L = util.fcc(6, dtype=np.float64)
+  R = util.jitter(R, L, 0.06)
+  N = len(R)
+  sp = (np.arange(N) % 2).astype(np.int32)
+  sig = np.array([[1.0, 0.9], [1.15, 1.05]])          # sigma[0,1] != sigma[1,0]
+  d_o, _ = ospace.periodic(L)
+  d_g, _ = jmd.space.periodic(L)
+  nf_o = opart.neighbor_list(d_o, L, np.float32(1.4), np.float32(0.2), format=opart.Format[fmt])
+  nb_o = nf_o.allocate(R)
+  pot = oenergy.PairPotential('soft_sphere')
+  E_o, F_o, _ = oenergy.pair_neighbor_list_energy(pot, d_o, R, nb_o, species=sp, want_grads=True,
+                                                  sigma=sig, epsilon=np.float64(1.0), alpha=np.float64(2.0))
+  Rd = _dev(R)
+  nf_g = jmd.partition.neighbor_list(d_g, L, np.float32(1.4), np.float32(0.2),
+                                     format=jmd.partition.NeighborListFormat[fmt])
+  nb_g = nf_g.allocate(Rd)
+  fused = jmd.smap.pair_neighbor_list(jmd.energy.soft_sphere, d_g, species=_dev(sp), sigma=_dev(sig))
+  generic = jmd.smap.pair_neighbor_list(lambda dr, sigma=1.0, **kw: jmd.energy.soft_sphere(dr, sigma), d_g,
+                                        species=_dev(sp), sigma=_dev(sig))
+  np.testing.assert_allclose(float(generic(Rd, neighbor=nb_g)), E_o, rtol=1e-10)
+  F = jmd.quantity.force(generic)(Rd, neighbor=nb_g).cpu().numpy()
+  np.testing.assert_allclose(F, F_o, rtol=1e-8, atol=1e-9 * np.abs(F_o).max())
+  # the fused kernel's per-row force needs symmetric tables: it must refuse, not guess
+  with pytest.raises(NotImplementedError):
+    fused(Rd, neighbor=nb_g)
+  sym = jmd.smap.pair_neighbor_list(jmd.energy.soft_sphere, d_g, species=_dev(sp),
+                                    sigma=_dev(0.5 * (sig + sig.T)))
+  E_s, F_s, _ = oenergy.pair_neighbor_list_energy(pot, d_o, R, nb_o, species=sp, want_grads=True,
+                                                  sigma=0.5 * (sig + sig.T), epsilon=np.float64(1.0),
+                                                  alpha=np.float64(2.0))
+  np.testing.assert_allclose(float(sym(Rd, neighbor=nb_g)), E_s, rtol=1e-10)
+  np.testing.assert_allclose(jmd.quantity.force(sym)(Rd, neighbor=nb_g).cpu().numpy(), F_s,
+                             rtol=1e-8, atol=1e-9 * np.abs(F_s).max())

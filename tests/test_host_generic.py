@@ -127,3 +127,33 @@ def test_neighbor_list_dataclass_contract():
   assert int(nb.did_buffer_overflow) == 3 and int(nb.cell_size_too_small) == 0
   assert not nb.internal_list_is_current
   assert str(nb.error) == 'Partition Error: Neighbor list buffer overflow.'
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+def test_generic_path_asymmetric_species_table(fmt):
+  """smap.py:794-797 lookup orientation (Dense p[s_row, s_neigh]; sparse
+  p[s_idx0, s_idx1]) told apart by an asymmetric table; forces are the true
+  gradient (both rows of a pair contribute)."""
+  from jax_md_b200 import energy, quantity, smap, space
+  R, L = util.fcc(5, dtype=np.float64)
+  R = util.jitter(R, L, 0.06)
+  sp = (np.arange(len(R)) % 2).astype(np.int32)
+  sig = np.array([[1.0, 0.9], [1.15, 1.05]])
+  d_o, _ = ospace.periodic(L)
+  d_t, _ = space.periodic(L)
+  nb_o = opart.neighbor_list(d_o, L, np.float32(1.4), np.float32(0.2), format=opart.Format[fmt]).allocate(R)
+  E_o, F_o, _ = oenergy.pair_neighbor_list_energy(
+      oenergy.PairPotential('soft_sphere'), d_o, R, nb_o, species=sp, want_grads=True,
+      sigma=sig, epsilon=np.float64(1.0), alpha=np.float64(2.0))
+  gen = smap.pair_neighbor_list(lambda dr, sigma=1.0, **kw: energy.soft_sphere(dr, sigma), d_t,
+                                species=torch.as_tensor(sp), sigma=torch.as_tensor(sig))
+  Rt = torch.as_tensor(R)
+  nb_t = _wrap(nb_o, fmt)
+  np.testing.assert_allclose(float(gen(Rt, neighbor=nb_t)), E_o, rtol=1e-12)
+  np.testing.assert_allclose(quantity.force(gen)(Rt, neighbor=nb_t).numpy(), F_o,
+                             rtol=1e-9, atol=1e-12 * np.abs(F_o).max())
+  # and the transposed table gives a different energy (the test can tell them apart)
+  gen_T = smap.pair_neighbor_list(lambda dr, sigma=1.0, **kw: energy.soft_sphere(dr, sigma), d_t,
+                                  species=torch.as_tensor(sp), sigma=torch.as_tensor(sig.T.copy()))
+  if fmt == 'OrderedSparse':
+    assert abs(float(gen_T(Rt, neighbor=nb_t)) - E_o) > 1e-6 * abs(E_o)
