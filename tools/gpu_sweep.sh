@@ -1,14 +1,12 @@
 mkdir -p gpurun_out
-rm -f gpurun_out/s28_var.log
-for v in "" _m4; do
-  echo "== lib '$v'" >> gpurun_out/s28_var.log
-  JMD_B200_LIB=$PWD/jax_md_b200/libjmd_b200$v.so python bench.py --no-cpu --no-variants --steps 400 --warmup 300 >> gpurun_out/s28_var.log 2>&1
-done
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/s29_tests.log 2>&1; tail -3 gpurun_out/s29_tests.log
+(time python bench.py) > gpurun_out/s29_bench.log 2>&1
 python - <<'PY'
 import json
-for l in open('gpurun_out/s28_var.log'):
-    if l.startswith('=='): print(l.strip()); continue
+for l in open('gpurun_out/s29_bench.log'):
     try: d=json.loads(l)
-    except Exception: print(l[:300].rstrip()); continue
-    print(d['ms_per_step'], d['neighbor_rebuild_ms'], d['roofline']['kernel_ms'], d['config']['rebuilds_in_timed_region'])
+    except Exception: print(l[:200].rstrip()); continue
+    print(d['value'], d['ms_per_step'], d['neighbor_rebuild_ms'], d['roofline']['kernel_ms'], d['roofline']['step_frac'], d['e2e']['value'], d['variants']['lazy_idx']['ms_per_step'])
 PY
+bash tools/profile.sh r01s5 > /dev/null 2>&1
+ls gpurun_out/r01s5* | head
