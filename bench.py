@@ -370,7 +370,7 @@ def run_b200(args):
     per_step = 1 + 8 + 2 + (2 if args.format == 'Dense' else 7) + 2
   # ncu --set full of this kernel at the default workload (profiles/r01_*): DRAM
   # bytes per launch = the 4 B/pair index stream; positions stay in L2/L1
-  traffic = 356667648 if (N == 1000188 and args.format == 'OrderedSparse') else None
+  traffic = 357541632 if (N == 1000188 and args.format == 'OrderedSparse') else None
   roofline['traffic'] = traffic
   line = {
       'metric': 'atom-timesteps/s', 'value': value, 'unit': 'atom-timesteps/s',

@@ -17,8 +17,15 @@
 
 namespace {
 
+// Block size / residency of the global-gather kernel, measured on B200 (LJ, N=1M):
+// 256 threads x 4 blocks (61 regs) 0.257 ms, 128 x 8 0.261 ms, 512 x 2 0.276 ms,
+// 128 x 10 (48 regs) 0.247 ms.  The staged kernel is tied to JMD_STAGE_BLOCK.
 #ifndef JMD_PAIR_BLOCK
-#define JMD_PAIR_BLOCK 256
+#if JMD_PAIR_STAGED
+#define JMD_PAIR_BLOCK JMD_STAGE_BLOCK
+#else
+#define JMD_PAIR_BLOCK 128
+#endif
 #endif
 constexpr int PAIR_BLOCK = JMD_PAIR_BLOCK;
 #ifndef JMD_PAIR_BATCH
@@ -36,7 +43,7 @@ constexpr int IDX_CH = JMD_PAIR_IDXCH;       // rows per TMA stage of the index 
 #define JMD_PAIR_ALWAYS_WRAP 1   /* measured: branch-free rint() form 2 % faster than the |d| > L/2 test */
 #endif
 #ifndef JMD_PAIR_MIN_BLOCKS
-#define JMD_PAIR_MIN_BLOCKS 1
+#define JMD_PAIR_MIN_BLOCKS 10
 #endif
 
 template <typename T, int DIM>
@@ -205,7 +212,10 @@ __device__ __forceinline__ T lookup(const PairP<T, DIM>& Q, int k, int ai, int a
 template <int RED> struct RedN { static constexpr int value = RED == 0 ? 1 : (RED == 1 ? 4 : 13); };
 
 template <typename T, int DIM, int POT, bool SCALAR, int RED, bool KICK>
-__global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_STAGED ? 4 : JMD_PAIR_MIN_BLOCKS) JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
+// (the register cap of JMD_PAIR_MIN_BLOCKS residency is for the f32 force / kick
+// variants; energy + virial + parameter-gradient and f64 variants need more registers)
+__global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_STAGED ? 4 : ((sizeof(T) == 4 && RED < 2) ? JMD_PAIR_MIN_BLOCKS : 4))
+JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
   using V4 = typename Vec4<T>::type;
 #if JMD_PAIR_STAGED
   // Stage the positions of every atom in the 3^d stencils of this block's home

@@ -437,8 +437,8 @@ def test_fori_loop_cuda_graph_matches_eager(kind):
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
 def test_staged_force_kernel_bitwise_equals_direct(kind, dtype):
   """The shared-memory staged force kernel (16-bit staging rows) evaluates the
-  same pairs in the same order as the global-gather kernel: forces, energies and
-  the fused half kick are bitwise equal.  N=13500: 1-2 row segments per block,
+  same pairs in the same order as the global-gather kernel: forces and the fused
+  half kick (hence trajectories) are bitwise equal, energies to summation order.  N=13500: 1-2 row segments per block,
   x wrap pieces, partially filled last block."""
   jmd = _jmd()
   R, L = util.fcc(15, dtype=dtype)
@@ -473,7 +473,10 @@ def test_staged_force_kernel_bitwise_equals_direct(kind, dtype):
       nb = nb.update(st.position)
       st = step(st, neighbor=nb)
     outs.append((E, F, st.position.clone(), st.momentum.clone(), nb.idx.clone()))
-  for a, b in zip(*outs):
+  # per-atom results are bitwise equal; the total energy is a block-wise f64 sum and
+  # the two kernels use different block sizes (256 staged / 128 gather)
+  np.testing.assert_allclose(float(outs[0][0]), float(outs[1][0]), rtol=1e-13)
+  for a, b in zip(outs[0][1:], outs[1][1:]):
     assert torch.equal(a, b)
 
 

@@ -1,12 +1,5 @@
 mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -x -q) > gpurun_out/s29_tests.log 2>&1; tail -3 gpurun_out/s29_tests.log
-(time python bench.py) > gpurun_out/s29_bench.log 2>&1
-python - <<'PY'
-import json
-for l in open('gpurun_out/s29_bench.log'):
-    try: d=json.loads(l)
-    except Exception: print(l[:200].rstrip()); continue
-    print(d['value'], d['ms_per_step'], d['neighbor_rebuild_ms'], d['roofline']['kernel_ms'], d['roofline']['step_frac'], d['e2e']['value'], d['variants']['lazy_idx']['ms_per_step'])
-PY
-bash tools/profile.sh r01s5 > /dev/null 2>&1
-ls gpurun_out/r01s5* | head
+CMD="python bench.py --steps 40 --warmup 10 --no-cpu --no-variants --kernel-reps 2"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01s6_launches.csv $CMD > gpurun_out/r01s6_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pair_force -s 12 -c 1 -f -o gpurun_out/r01s6_force $CMD > gpurun_out/r01s6_force.log 2>&1
+ls gpurun_out/r01s6*
