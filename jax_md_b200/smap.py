@@ -156,6 +156,13 @@ class PairNeighborListFn:
           'jax_md_b200.partition; this list has a foreign `idx`.')
     species = dynamic_kwargs.pop('species', self.species)
     params = _merge(self.kwargs, dynamic_kwargs, self.ignore_unused)
+    if params.pop('perturbation', None) is not None:
+      # space.py:299-300 scales the displacement; the fused kernel has no such input.
+      # Its derivative at the identity (all the reference uses it for) is `virial()`.
+      raise NotImplementedError(
+          'perturbation= is not an input of the fused kernel: use quantity.pressure / '
+          'quantity.stress (served from its virial) or a plain Python potential (generic '
+          'smap.pair_neighbor_list path).')
     return neighbor, species, params
 
   def _species_tensor(self, species, device):
