@@ -211,6 +211,44 @@ def pair_neighbor_list_energy(pot, displacement, R, nbrs, species=None,
   return E, (-grad).astype(R.dtype), dparams
 
 
+def pair_virial(pot, displacement, R, nbrs, species=None, **params):
+  """dU/d(eps_ab) at eps = 0 for the box strain `perturbation=(I + eps)` of
+  space.py:299-300: sum over list entries of (dU/dr)/r * dR_a * dR_b / norm -- what
+  quantity.pressure / quantity.stress (quantity.py:202-282) obtain by autodiff."""
+  N, dim = R.shape
+  a, b, mask, rows = _entries(R, nbrs)
+  dR = displacement(R[a], R[b])
+  dr = space.distance(dR)
+  pa, pb = (b, a) if rows is not None else (a, b)
+  p = {k: _expand(v, pa, pb, species) for k, v in params.items()}
+  dU_dr = pot.grads(dr, **p)[0]
+  norm = 1.0 if nbrs.format is OrderedSparse else 2.0
+  with np.errstate(invalid='ignore', divide='ignore'):
+    coef = np.where(mask & (dr > 0), dU_dr / np.where(dr > 0, dr, 1), 0) / norm
+  dRf = dR.reshape(-1, dim).astype(np.float64)
+  return np.einsum('e,ea,eb->ab', coef.reshape(-1).astype(np.float64), dRf, dRf)
+
+
+def pressure(pot, displacement, R, box, nbrs, kinetic_energy=0.0, species=None, **params):
+  """quantity.py:202-235 for a scalar / vector box."""
+  dim = R.shape[1]
+  vol = float(box) ** dim if np.ndim(box) == 0 else float(np.prod(box))
+  W = pair_virial(pot, displacement, R, nbrs, species=species, **params)
+  return (2.0 * kinetic_energy - np.trace(W)) / (dim * vol)
+
+
+def stress(pot, displacement, R, box, nbrs, mass=1.0, velocity=None, species=None, **params):
+  """quantity.py:238-282."""
+  dim = R.shape[1]
+  vol = float(box) ** dim if np.ndim(box) == 0 else float(np.prod(box))
+  W = pair_virial(pot, displacement, R, nbrs, species=species, **params)
+  VxV = 0.0
+  if velocity is not None:
+    V = np.asarray(velocity, np.float64)
+    VxV = np.einsum('n,na,nb->ab', np.broadcast_to(np.asarray(mass, np.float64), (len(V),)), V, V)
+  return (VxV - W) / vol
+
+
 def pair_energy_bruteforce(pot, displacement, R, species=None, **params):
   """smap.pair (smap.py:548-691) O(N^2) total energy, for cross-checks."""
   N = R.shape[0]

@@ -292,3 +292,30 @@ def test_fire_descent_reduces_force():
   for _ in range(150):
     st = step(st)
   assert np.abs(st.force).max() < 0.05 * f0
+
+
+def test_pressure_and_stress_goldens():
+  """Reference tests/quantity_test.py:134-150 (jammed soft spheres, P =
+  0.06307342050945483) and :436-455 (LAMMPS LJ stress incl. the kinetic term)."""
+  s = np.load(os.path.join(util.GOLDEN, 'jammed_state.npz'))
+  R = s['real_position']
+  L = float(s['box'][0, 0])
+  d, _ = ospace.periodic(L)
+  nb = opart.neighbor_list(d, L, np.float64(np.max(s['sigma'])), np.float64(0.0),
+                           format=opart.Dense).allocate(R)
+  pot = oenergy.PairPotential('soft_sphere')
+  P = oenergy.pressure(pot, d, R, L, nb, species=s['species'], sigma=s['sigma'],
+                       epsilon=np.float64(1.0), alpha=np.float64(2.0))
+  np.testing.assert_allclose(P, G['jammed_pressure'], rtol=1e-9)
+
+  s = np.load(os.path.join(util.GOLDEN, 'lammps_lj.npz'))
+  box = np.float32(s['box'])
+  R = (s['R'] * box).astype(np.float64)
+  r = s['stress_row']
+  C = np.array([[r[0], r[3], r[4]], [r[3], r[1], r[5]], [r[4], r[5], r[2]]])
+  d, _ = ospace.periodic(box)
+  for fmt in (opart.Dense, opart.Sparse, opart.OrderedSparse):
+    nb = opart.neighbor_list(d, box, np.float32(2.5), np.float32(0.0), format=fmt).allocate(R)
+    S = oenergy.stress(oenergy.PairPotential('lj'), d, R, box, nb, velocity=s['V'],
+                       sigma=np.float64(1.0), epsilon=np.float64(1.0))
+    np.testing.assert_allclose(S, C, rtol=5e-5, atol=5e-5)
