@@ -155,8 +155,10 @@ class PairNeighborListFn:
           'The fused kernels read the internal rows of a NeighborList built by '
           'jax_md_b200.partition; this list has a foreign `idx`.')
     species = dynamic_kwargs.pop('species', self.species)
+    perturbation = dynamic_kwargs.pop('perturbation', self.kwargs.get('perturbation'))
     params = _merge(self.kwargs, dynamic_kwargs, self.ignore_unused)
-    if params.pop('perturbation', None) is not None:
+    params.pop('perturbation', None)
+    if perturbation is not None:
       # space.py:299-300 scales the displacement; the fused kernel has no such input.
       # Its derivative at the identity (all the reference uses it for) is `virial()`.
       raise NotImplementedError(
