@@ -214,7 +214,8 @@ template <int RED> struct RedN { static constexpr int value = RED == 0 ? 1 : (RE
 template <typename T, int DIM, int POT, bool SCALAR, int RED, bool KICK>
 // (the register cap of JMD_PAIR_MIN_BLOCKS residency is for the f32 force / kick
 // variants; energy + virial + parameter-gradient and f64 variants need more registers)
-__global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_STAGED ? 4 : ((sizeof(T) == 4 && RED < 2) ? JMD_PAIR_MIN_BLOCKS : 4))
+__global__ void __launch_bounds__(PAIR_BLOCK, JMD_PAIR_STAGED ? ((sizeof(T) == 4 && RED < 2) ? 4 : 2)
+                                                            : ((sizeof(T) == 4 && RED < 2) ? JMD_PAIR_MIN_BLOCKS : 4))
 JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
   using V4 = typename Vec4<T>::type;
 #if JMD_PAIR_STAGED
