@@ -75,3 +75,32 @@ def test_space_struct_values():
   d3, _ = space.periodic(10.1)
   st = space.space_struct(d3._jmd_space, 3, torch.float64)
   assert st.side[0] == 10.1 and st.half[0] == float(np.float32(10.1) * np.float32(0.5))
+
+
+def test_ctypes_layout_equals_the_c_compiler_layout(tmp_path):
+  """Every field of the ctypes mirrors sits at the offset gcc gives the header's
+  structs (guards the descriptor against silent drift when fields are added)."""
+  import subprocess
+  from jax_md_b200 import _lib
+  structs = {'jmd_space_t': _lib.SpaceT, 'jmd_nbr_t': _lib.NbrT, 'jmd_pair_t': _lib.PairT,
+             'jmd_sw_t': _lib.SwT}
+  lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "jmd_b200.h"', 'int main(void) {']
+  for cname, ct in structs.items():
+    lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+    for fname, _ in ct._fields_:
+      if fname.startswith('_pad'):
+        continue
+      lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+  lines += ['  return 0;', '}']
+  src = tmp_path / 'layout.c'
+  src.write_text('\n'.join(lines))
+  exe = tmp_path / 'layout'
+  subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+  out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+  got = dict(l.split() for l in out.splitlines())
+  for cname, ct in structs.items():
+    assert int(got[cname]) == ctypes.sizeof(ct), cname
+    for fname, _ in ct._fields_:
+      if fname.startswith('_pad'):
+        continue
+      assert int(got[f'{cname}.{fname}']) == getattr(ct, fname).offset, f'{cname}.{fname}'
