@@ -140,6 +140,20 @@ typedef struct {
   /* 1: jmd_nbr_update leaves the public `idx` stale after a rebuild (state[EXPORT_PENDING])
    * and jmd_nbr_export(gated = 2) materialises it on demand (NeighborList.idx read). */
   int32_t lazy_idx;
+  /* Warp-per-cell candidate scan (csrc/jmd_nbr_cellscan.cuh), used when cell_scan != 0
+   * and the search grid is the reference grid: one warp owns a home cell, tests the
+   * concatenated candidate stream of its 3^d stencil 32 candidates at a time and leaves
+   * one accept bit per test in cs_bits [n_cells][cs_batches][cs_chunks][32] (cs_batches =
+   * ceil(cell_capacity / 32) groups of home atoms, cs_chunks = ceil(3^d * cell_capacity /
+   * 32)); jmd_nbr_export expands the masks into the rows and the public idx.  cs_lb:
+   * [n / 2048 + 2] look-back words of the sparse offsets scan.  With cell_scan the rows
+   * of `nl` are complete after jmd_nbr_export, not after jmd_nbr_build. */
+  int32_t cell_scan;
+  int32_t cs_chunks;
+  int32_t cs_batches;
+  int32_t _pad2;
+  uint32_t* cs_bits;
+  uint64_t* cs_lb;
 } jmd_nbr_t;
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */

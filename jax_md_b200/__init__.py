@@ -8,6 +8,6 @@ reached through the C ABI in include/jmd_b200.h.  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
 from . import dataclasses, util, space, partition, smap, energy, quantity  # noqa: F401
-from . import simulate, minimize, lax  # noqa: F401
+from . import simulate, minimize, lax, units  # noqa: F401
 
 __version__ = '0.1.0'

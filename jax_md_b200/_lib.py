@@ -58,7 +58,9 @@ class NbrT(C.Structure):
       ('fine_cell_size', C.c_double * 3), ('ref_count', C.c_void_p),
       ('brick_shift', C.c_int32), ('staged', C.c_int32), ('ref_start', C.c_void_p),
       ('nl16', C.c_void_p), ('blk_table', C.c_void_p),
-      ('skin_blk', C.c_void_p), ('skin_pre', C.c_int32), ('lazy_idx', C.c_int32)]
+      ('skin_blk', C.c_void_p), ('skin_pre', C.c_int32), ('lazy_idx', C.c_int32),
+      ('cell_scan', C.c_int32), ('cs_chunks', C.c_int32), ('cs_batches', C.c_int32),
+      ('_pad2', C.c_int32), ('cs_bits', C.c_void_p), ('cs_lb', C.c_void_p)]
 
 
 class PairT(C.Structure):

@@ -1,0 +1,481 @@
+// Warp-cooperative candidate scan ("cell scan") -- included by jmd_neighbor.cu inside
+// its anonymous namespace, after NbrP / exact_keep / publish_counts.
+//
+// Replaces partition.py:911-1032 (candidate gather, distance mask, cumsum compaction)
+// and the export to the public formats for lists whose cells hold enough atoms to keep
+// a warp busy.  One WARP owns one home cell (all of the reference's 3^d stencil):
+//
+//   k_nbr_cell_test    lanes run over the CONCATENATED candidate stream of the stencil
+//                      cells (reference order: stencil cells x-slowest, slot order
+//                      inside a cell), 32 candidates per chunk, each candidate shifted
+//                      once into the home cell's periodic image.  Home atoms are
+//                      broadcast from shared memory; one FSETP + one VOTE.BALLOT per
+//                      (chunk, home atom) yields the accept mask of that home atom over
+//                      the chunk.  The masks -- one bit per candidate test -- go to
+//                      `cs_bits`; row lengths (cnt, cnt_lower) and the occupancy
+//                      statistics are final after this kernel.  The reference's exact
+//                      arithmetic runs only for chunks that saw a candidate inside the
+//                      rounding band around cutoff^2 or a "dirty" cell.
+//   k_nbr_offsets      (sparse formats) exclusive scan of the per-atom entry counts in
+//                      atom-id order: single pass, decoupled look-back.
+//   k_nbr_cell_expand  expands the masks into rows staged in shared memory ([k][lane],
+//                      padded), then writes the internal transposed list coalesced and
+//                      the public idx (Dense rows / sparse segments at their offsets)
+//                      from the same staged rows; also stores the reference positions
+//                      and the error bits (partition.py:1066,1110).
+//
+// The candidate ORDER is the reference's, so `idx` stays element-exact.
+#pragma once
+
+constexpr int CS_WARPS = 4;                 // home cells per block
+enum { ST_LB_TILE = 9, ST_CS_TICKET = 10 }; // state[] slots used by the offsets scan / expand finalize
+enum { CS_ROWS = 1, CS_IDX = 2, CS_FINALIZE = 4 };
+
+template <typename T>
+struct CsWarpSmem {
+  int pre[32];        // exclusive prefix of the stencil cells' atom counts (entries >= NS: total)
+  int cstart[32];     // first slot of stencil cell s
+  int sdirty[32];     // stencil cell holds an irregular atom (exact test)
+  T shift[3][32];     // image shift added to the candidates of stencil cell s
+  typename Vec4<T>::type home[32];   // home atoms of the current batch: x y z id
+  uint2 bits[32];     // .x accept mask of home atom h over the current chunk; .y the same
+                      // restricted to candidates with a smaller atom id (OrderedSparse)
+  int rank[32];       // (expand) slot of the chunk's candidate j
+};
+
+__device__ __forceinline__ int id_of(float w) { return __float_as_int(w); }
+__device__ __forceinline__ int id_of(double w) { return (int)w; }            // exact below 2^53
+__device__ __forceinline__ float id_as(float, int id) { return __int_as_float(id); }
+__device__ __forceinline__ double id_as(double, int id) { return (double)id; }
+
+// Stencil of `cell` in the reference's order; returns the candidate total.
+template <typename T, int DIM>
+__device__ __forceinline__ int cs_setup(const NbrP<T, DIM>& P, int cell, int lane, CsWarpSmem<T>& sm) {
+  constexpr int NS = DIM == 3 ? 27 : 9;
+  int cc[3];
+  cell_coords(P, cell, cc);
+  int cnt = 0, start = 0, dirty = 0;
+  T sh[3] = {T(0), T(0), T(0)};
+  if (lane < NS) {
+    int s3[3];
+    if (DIM == 3) { s3[0] = lane / 9 - 1; s3[1] = (lane / 3) % 3 - 1; s3[2] = lane % 3 - 1; }
+    else { s3[0] = lane / 3 - 1; s3[1] = lane % 3 - 1; s3[2] = 0; }
+    int sv[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      int v = cc[d] + s3[d];
+      // a stencil cell beyond a face is the periodic image of the cell at the other end:
+      // its atoms are moved by -side / +side so that home - candidate is the minimum image
+      if (v < 0) { v += P.cps[d]; sh[d] = -P.sp.side[d]; }
+      else if (v >= P.cps[d]) { v -= P.cps[d]; sh[d] = P.sp.side[d]; }
+      sv[d] = v;
+    }
+    const int h = cell_id(P, sv);
+    start = __ldg(&P.cell_start[h]);
+    cnt = __ldg(&P.cell_start[h + 1]) - start;
+    dirty = __ldg(&P.cell_cursor[h]) & CELL_DIRTY;
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  sm.pre[lane] = incl - cnt;             // lanes >= NS: the total
+  sm.cstart[lane] = start;
+  sm.sdirty[lane] = dirty;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) sm.shift[d][lane] = sh[d];
+  return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// largest s with pre[s] <= t (pre non-decreasing, 32 entries)
+__device__ __forceinline__ int cs_find(const int* pre, int t) {
+  int s = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1)
+    if (pre[s + step] <= t) s += step;
+  return s;
+}
+
+template <typename T, int DIM, int MODE, bool ORDERED, bool PERIODIC, bool FILTER>
+__global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_test(NbrP<T, DIM> P, int gated) {
+  if (gate_closed(P.state, gated)) return;
+  using V4 = typename Vec4<T>::type;
+  constexpr int NS = DIM == 3 ? 27 : 9;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ CsWarpSmem<T> smem[CS_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  CsWarpSmem<T>& sm = smem[w];
+  const int cell = blockIdx.x * CS_WARPS + w;
+  // the offsets scan of this rebuild starts from cleared look-back words
+  {
+    const int tiles = (P.n + SCAN_TILE - 1) / SCAN_TILE + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tiles; i += gridDim.x * blockDim.x) P.cs_lb[i] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.state[ST_LB_TILE] = 0;
+  }
+  long long my_k = 0, my_tot = 0;
+  const V4* __restrict__ const pos = P.pos_sorted;
+  int hs = 0, he = 0;
+  if (cell < P.n_cells) { hs = P.cell_start[cell]; he = P.cell_start[cell + 1]; }
+  if (he > hs) {
+    const bool home_dirty = FILTER ? (__ldg(&P.cell_cursor[cell]) & CELL_DIRTY) != 0 : false;
+    const int total = cs_setup<T, DIM>(P, cell, lane, sm);
+    __syncwarp();
+    const int nchunks = min((total + 31) >> 5, P.cs_chunks);
+    const T c2 = P.cutoff_sq;
+    const T bw = P.f_hi - c2;               // half width of the rounding band (2 * band)
+    T hh[3], qq[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { hh[d] = d < DIM ? P.sp.half[d] : T(0); qq[d] = d < DIM ? P.sp.quarter[d] : T(0); }
+    const int self_pre = sm.pre[NS / 2];    // the centre stencil cell is the home cell itself
+    for (int hb = hs; hb < he; hb += 32) {  // home atoms, 32 at a time
+      const int batch = (hb - hs) >> 5;
+      const int nh = min(32, he - hb);
+      const int slot = hb + lane;
+      if (batch >= P.cs_batches) {          // more atoms than cell_capacity: CELL_LIST_OVERFLOW is flagged
+        if (lane < nh) { P.cnt[slot] = 0; P.cnt_lower[slot] = 0; }
+        continue;
+      }
+      int hid = 0x7fffffff;
+      V4 hv = make_v4<T>(T(0), T(0), T(0), T(0));
+      if (lane < nh) { hv = pos[slot]; hid = P.perm[slot]; }
+      const bool has_row = hid < P.n_rows;
+      __syncwarp();
+      sm.home[lane] = make_v4<T>(hv.x, hv.y, hv.z, id_as(T(0), hid));
+      __syncwarp();
+      int k = 0, kl = 0;
+      if (__any_sync(FULL, has_row)) {
+        unsigned* const gb = P.cs_bits + ((size_t)cell * P.cs_batches + batch) * ((size_t)P.cs_chunks * 32);
+        for (int q = 0; q < nchunks; ++q) {
+          const int t = q * 32 + lane;
+          const bool valid = t < total;
+          const int s = cs_find(sm.pre, valid ? t : 0);
+          const int rank = sm.cstart[s] + (t - sm.pre[s]);
+          V4 cv = make_v4<T>(T(0), T(0), T(0), T(0));
+          int cid = 0x7fffffff;
+          bool lane_exact = false;
+          // invalid lanes sit far away: never accepted, never inside the band
+          T cx = T(1e18), cy = T(1e18), cz = T(0);
+          if (valid) {
+            cv = pos[rank];
+            if (ORDERED) cid = __ldg(&P.perm[rank]);
+            lane_exact = FILTER ? (home_dirty || sm.sdirty[s] != 0) : true;
+            cx = cv.x + sm.shift[0][s];
+            cy = cv.y + sm.shift[1][s];
+            if (DIM == 3) cz = cv.z + sm.shift[2][s];
+          }
+          bool band = false;
+          if (FILTER) {
+            // common path: contracted arithmetic on the image-shifted candidate; one
+            // compare and one ballot per (chunk, home atom)
+#pragma unroll 4
+            for (int h = 0; h < nh; ++h) {
+              const V4 hp = sm.home[h];
+              const T ax = hp.x - cx, ay = hp.y - cy;
+              T a2 = ax * ax + ay * ay;
+              if (DIM == 3) { const T az = hp.z - cz; a2 += az * az; }
+              const bool keep = a2 < c2;
+              band = band || (fabs(a2 - c2) <= bw);
+              const unsigned b = __ballot_sync(FULL, keep);
+              if (ORDERED) {
+                const unsigned bl = __ballot_sync(FULL, keep && cid < id_of(hp.w));
+                if (lane == 0) sm.bits[h] = make_uint2(b, bl);
+              } else {
+                if (lane == 0) sm.bits[h].x = b;
+              }
+            }
+          }
+          if (!FILTER || __any_sync(FULL, band || lane_exact)) {
+            // rare: a candidate inside the rounding band or a dirty cell -- the
+            // reference's exact op sequence decides those pairs
+#pragma unroll 1
+            for (int h = 0; h < nh; ++h) {
+              const V4 hp = sm.home[h];
+              const T ax = hp.x - cx, ay = hp.y - cy;
+              T a2 = ax * ax + ay * ay;
+              if (DIM == 3) { const T az = hp.z - cz; a2 += az * az; }
+              bool keep = a2 < c2;
+              if (valid && (lane_exact || fabs(a2 - c2) <= bw)) {
+                const T hp3[3] = {hp.x, hp.y, hp.z};
+                keep = exact_keep<T, DIM, MODE, PERIODIC>(P, hp3, cv, hh, qq, c2);
+              }
+              keep = keep && valid;
+              const unsigned b = __ballot_sync(FULL, keep);
+              if (ORDERED) {
+                const unsigned bl = __ballot_sync(FULL, keep && cid < id_of(hp.w));
+                if (lane == 0) sm.bits[h] = make_uint2(b, bl);
+              } else {
+                if (lane == 0) sm.bits[h].x = b;
+              }
+            }
+          }
+          __syncwarp();
+          unsigned m = 0u, ml = 0u;
+          if (lane < nh) {
+            if (ORDERED) { const uint2 mm = sm.bits[lane]; m = mm.x; ml = mm.y; }
+            else m = sm.bits[lane].x;
+          }
+          __syncwarp();
+          if (P.mask_self) {                 // partition.py:953-958
+            const int t_self = self_pre + (slot - hs);
+            if ((t_self >> 5) == q) m &= ~(1u << (t_self & 31));
+          }
+          if (!has_row) { m = 0u; ml = 0u; }
+          gb[q * 32 + lane] = m;
+          k += __popc(m);
+          kl += __popc(ml);
+        }
+      }
+      if (lane < nh) {
+        P.cnt[slot] = k;
+        P.cnt_lower[slot] = kl;
+        my_k = k > my_k ? k : my_k;
+        my_tot += ORDERED ? kl : k;
+      }
+    }
+  }
+  publish_counts(P.state, my_k, my_tot);
+}
+
+// ---- sparse offsets: exclusive scan of the per-atom entry counts (atom-id order) ----
+// single pass, decoupled look-back; tiles are handed out by an atomic counter so a
+// tile only ever waits for tiles that already run.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(NB) k_nbr_offsets(NbrP<T, DIM> P, int gated) {
+  if (gate_closed(P.state, gated)) return;
+  __shared__ long long sscan[NWARP];
+  __shared__ int s_tile;
+  __shared__ long long s_prefix;
+  constexpr unsigned long long F_AGG = 1ull << 62, F_PRE = 2ull << 62, MASK = (1ull << 62) - 1ull;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd((unsigned long long*)&P.state[ST_LB_TILE], 1ull);
+  __syncthreads();
+  const int tile = s_tile;
+  const long long base = (long long)tile * SCAN_TILE;
+  const bool ordered = P.format == JMD_ORDERED_SPARSE;
+  int v[8];
+  long long s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long a = base + (long long)threadIdx.x * 8 + j;
+    int x = 0;
+    if (a < P.n) {
+      const int t = P.inv_perm[a];
+      x = ordered ? P.cnt_lower[t] : min(P.cnt[t], P.m_int);
+    }
+    v[j] = x;
+    s += x;
+  }
+  long long tot;
+  long long e = block_excl_scan<long long>(s, &tot, sscan);
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = P.cs_lb;
+    long long run = 0;
+    if (tile > 0) {
+      st[tile] = F_AGG | (unsigned long long)tot;
+      __threadfence();
+      int p = tile - 1;
+      while (true) {
+        unsigned long long x;
+        do { x = st[p]; } while ((x >> 62) == 0ull);
+        run += (long long)(x & MASK);
+        if ((x >> 62) == 2ull) break;
+        --p;
+      }
+    }
+    __threadfence();
+    st[tile] = F_PRE | (unsigned long long)(run + tot);
+    s_prefix = run;
+  }
+  __syncthreads();
+  e += s_prefix;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long a = base + (long long)threadIdx.x * 8 + j;
+    if (a < P.n) P.offsets[a] = e;
+    e += v[j];
+    if (a == (long long)P.n - 1) P.offsets[P.n] = e;
+  }
+  if (P.n == 0 && tile == 0 && threadIdx.x == 0) P.offsets[0] = 0;
+}
+
+// ---- expansion of the accept masks into rows + public idx ------------------------------
+template <typename T, int DIM>
+__global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_expand(NbrP<T, DIM> P, int gated, int flags) {
+  if (gate_closed(P.state, gated)) return;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ int cs_tiles[];          // per warp: [m_int][33] staged rows (slots)
+  __shared__ CsWarpSmem<T> smem[CS_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  CsWarpSmem<T>& sm = smem[w];
+  int* const tile = cs_tiles + (size_t)w * P.m_int * 33;
+  const int cell = blockIdx.x * nwarps + w;
+  const bool rows = (flags & CS_ROWS) != 0;
+  const bool pub = (flags & CS_IDX) != 0 && !P.no_public_idx && P.idx != nullptr;
+  const bool fin = (flags & CS_FINALIZE) != 0;
+  const bool dense = P.format == JMD_DENSE;
+  const bool ordered = P.format == JMD_ORDERED_SPARSE;
+  const long long cap = P.max_occupancy;
+  int hs = 0, he = 0;
+  if (cell < P.n_cells) { hs = P.cell_start[cell]; he = P.cell_start[cell + 1]; }
+  if (he > hs) {
+    const int total = cs_setup<T, DIM>(P, cell, lane, sm);
+    __syncwarp();
+    const int nchunks = min((total + 31) >> 5, P.cs_chunks);
+    for (int hb = hs; hb < he; hb += 32) {
+      const int batch = (hb - hs) >> 5;
+      const int nh = min(32, he - hb);
+      const int slot = hb + lane;
+      int hid = 0x7fffffff, c_l = 0;
+      if (lane < nh) {
+        hid = P.perm[slot];
+        c_l = batch < P.cs_batches ? min(P.cnt[slot], P.m_int) : 0;
+        if (fin) {                           // partition.py:1128: reference_position = position
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) P.ref[(size_t)hid * DIM + d] = P.position[(size_t)hid * DIM + d];
+        }
+      }
+      if (batch >= P.cs_batches) continue;
+      int cmax = c_l;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+      const unsigned* const gb = P.cs_bits + ((size_t)cell * P.cs_batches + batch) * ((size_t)P.cs_chunks * 32);
+      int k = 0;
+      for (int q = 0; q < (cmax > 0 ? nchunks : 0); ++q) {
+        const int t = q * 32 + lane;
+        const int s = cs_find(sm.pre, t < total ? t : 0);
+        __syncwarp();
+        sm.rank[lane] = sm.cstart[s] + (t - sm.pre[s]);
+        __syncwarp();
+        unsigned m = c_l > 0 ? __ldcs(gb + q * 32 + lane) : 0u;
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          if (k < P.m_int) tile[k * 33 + lane] = sm.rank[j];
+          ++k;
+        }
+      }
+      __syncwarp();
+      if (rows) {
+        // internal transposed list: row kk of the cell's home atoms is contiguous
+        for (int kk = 0; kk < cmax; ++kk)
+          if (kk < c_l) P.nl[(size_t)kk * P.n_pad + slot] = tile[kk * 33 + lane];
+      }
+      if (pub) {
+        for (int h = 0; h < nh; ++h) {
+          const int a = __shfl_sync(FULL, hid, h);
+          const int c = __shfl_sync(FULL, c_l, h);
+          if (a >= P.n) continue;
+          if (dense) {
+            // Dense: idx[a, k] in candidate order, padded with N (partition.py:960-980, 1105)
+            for (long long k0 = 0; k0 < cap; k0 += 32) {
+              const long long kk = k0 + lane;
+              int v = P.n;
+              if (kk < c) v = __ldg(&P.perm[tile[(int)kk * 33 + h]]);
+              if (kk < cap) P.idx[(size_t)a * cap + kk] = v;
+            }
+          } else {
+            // Sparse: idx[0] = receivers, idx[1] = senders, ordered by sender then
+            // candidate order; OrderedSparse keeps receiver id < sender id (:1010-1032)
+            long long pos0 = P.offsets[a];
+            for (int k0 = 0; k0 < c; k0 += 32) {
+              const int kk = k0 + lane;
+              int v = -1;
+              if (kk < c) v = __ldg(&P.perm[tile[kk * 33 + h]]);
+              const bool keep = v >= 0 && (!ordered || v < a);
+              const unsigned b = __ballot_sync(FULL, keep);
+              const long long pos = pos0 + __popc(b & ((1u << lane) - 1u));
+              if (keep && pos < cap) { P.idx[pos] = v; P.idx[cap + pos] = a; }
+              pos0 += __popc(b);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (pub && !dense) {
+    // pad the tail of the sparse arrays with N (partition.py:1024)
+    const long long start = P.offsets[P.n];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = start + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < cap; p += stride) {
+      P.idx[p] = P.n;
+      P.idx[cap + p] = P.n;
+    }
+  }
+  // last block: error bits / counters (ph_finalize), look-back words for the next scan
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd((unsigned long long*)&P.state[ST_CS_TICKET], 1ull);
+    if (t == (unsigned long long)gridDim.x - 1ull) {
+      P.state[ST_CS_TICKET] = 0;
+      if (fin) {
+        unsigned e = *P.error;
+        if (P.state[ST_MAX_CELL] > P.cell_capacity) e |= JMD_ERR_CELL_LIST_OVERFLOW;
+        const long long occ = dense ? P.state[ST_MAX_ROW] : P.state[ST_TOTAL];
+        if (occ > P.max_occupancy) e |= JMD_ERR_NEIGHBOR_LIST_OVERFLOW;
+        if (P.state[ST_MAX_ROW] > P.m_int) e |= JMD_ERR_NEIGHBOR_LIST_OVERFLOW;
+        *P.error = (uint8_t)e;
+        P.state[ST_BUILDS] += 1;
+        P.state[ST_EXPORT] = (P.lazy_idx && !P.no_public_idx) ? 1 : 0;
+      } else if (pub) {
+        P.state[ST_EXPORT] = 0;
+      }
+    }
+  }
+}
+
+// shared memory of one expand block, or 0 if the staged rows do not fit
+template <typename T, int DIM>
+inline size_t cs_expand_smem(const NbrP<T, DIM>& P, int* warps) {
+  const size_t per_warp = (size_t)P.m_int * 33 * sizeof(int);
+  int nw = CS_WARPS;
+  while (nw > 1 && nw * per_warp > 96 * 1024) nw >>= 1;
+  *warps = nw;
+  return nw * per_warp <= 96 * 1024 ? nw * per_warp : 0;
+}
+
+template <typename T, int DIM, int FMT, bool PERIODIC>
+void launch_cell_test_f(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+  constexpr int MODE = (FMT == 0 && PERIODIC) ? 1 : 0;
+  const int grid = (P.n_cells + CS_WARPS - 1) / CS_WARPS;
+  if (PERIODIC && P.filter)
+    k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, PERIODIC><<<grid, CS_WARPS * 32, 0, stream>>>(P, gated);
+  else
+    k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, false><<<grid, CS_WARPS * 32, 0, stream>>>(P, gated);
+}
+
+template <typename T, int DIM>
+void launch_cell_test(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+  const int fmt = P.format == JMD_DENSE ? 0 : (P.format == JMD_SPARSE ? 1 : 2);
+  if (P.sp.periodic) {
+    if (fmt == 0) launch_cell_test_f<T, DIM, 0, true>(P, gated, stream);
+    else if (fmt == 1) launch_cell_test_f<T, DIM, 1, true>(P, gated, stream);
+    else launch_cell_test_f<T, DIM, 2, true>(P, gated, stream);
+  } else {
+    if (fmt == 2) launch_cell_test_f<T, DIM, 2, false>(P, gated, stream);
+    else launch_cell_test_f<T, DIM, 1, false>(P, gated, stream);
+  }
+}
+
+template <typename T, int DIM>
+int launch_cell_expand(const NbrP<T, DIM>& P, int gated, int flags, cudaStream_t stream) {
+  int nw = CS_WARPS;
+  const size_t bytes = cs_expand_smem(P, &nw);
+  if (bytes == 0) return JMD_EINVAL;
+  static int optin[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !optin[dev]) {
+    cudaFuncSetAttribute(k_nbr_cell_expand<T, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (dev < 64) optin[dev] = 1;
+  }
+  const bool pub = (flags & CS_IDX) != 0 && !P.no_public_idx && P.idx != nullptr;
+  if (pub && P.format != JMD_DENSE)
+    k_nbr_offsets<T, DIM><<<(P.n + SCAN_TILE - 1) / SCAN_TILE + (P.n == 0 ? 1 : 0), NB, 0, stream>>>(P, gated);
+  const int grid = (P.n_cells + nw - 1) / nw;
+  k_nbr_cell_expand<T, DIM><<<grid, nw * 32, bytes, stream>>>(P, gated, flags);
+  return 0;
+}

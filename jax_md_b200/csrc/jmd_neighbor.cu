@@ -68,6 +68,10 @@ struct NbrP {
   unsigned short* nl16;
   int ref_cps[3], n_ref_cells, sw;   // reference grid (capacity flag only), stencil half width
   int count_only, two_sided, rev_only, n_rows, no_public_idx;
+  // warp-per-cell scan (jmd_nbr_cellscan.cuh)
+  int cellscan, cs_chunks, cs_batches;
+  unsigned* cs_bits;               // [n_cells][cs_batches][cs_chunks][32] accept masks
+  unsigned long long* cs_lb;       // look-back words of the sparse offsets scan
   long long n_pad, max_occupancy;
   T cell_size[DIM];    // fine cell size
   T ref_cell_size[DIM];
@@ -1050,6 +1054,8 @@ __device__ __forceinline__ int* ref_sums(const NbrP<T, DIM>& P) {
   return P.scan_tmp + (P.n_cells / SCAN_TILE + 2);     // behind the storage-order tile sums
 }
 
+#include "jmd_nbr_cellscan.cuh"
+
 // ---- one ordinary kernel per phase (allocate path / gated fallback) -----------------------
 enum Phase { PH_ZERO, PH_HASH, PH_SCAN1, PH_SCAN2, PH_SCAN3, PH_SCATTER, PH_RANK, PH_INVPERM,
              PH_IDENTITY, PH_PACK, PH_BUILD_RESET, PH_BUILD, PH_SP_COUNTS, PH_SP_SCAN1,
@@ -1138,6 +1144,10 @@ void launch_scan_wf(const NbrP<T, DIM>& P, int gated, int grid, cudaStream_t str
 
 template <typename T, int DIM>
 void launch_scan(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
+  if (P.cellscan) {
+    launch_cell_test<T, DIM>(P, gated, stream);
+    return;
+  }
   if (!P.use_cells) {
     k_nbr_all_pairs<T, DIM><<<grid_for((long long)P.n * 32, NB, JMD_SM_COUNT * 16), NB, 0, stream>>>(P, gated);
     return;
@@ -1193,6 +1203,14 @@ void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 template <typename T, int DIM>
 void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   const int G = JMD_SM_COUNT * 8;
+  if (P.cellscan) {
+    // the rows are expanded from the accept masks here, together with the public idx
+    int flags = CS_ROWS | CS_IDX | CS_FINALIZE;
+    if (P.no_public_idx || (P.lazy_idx && gated == 1)) flags = CS_ROWS | CS_FINALIZE;
+    else if (gated == 2) flags = CS_IDX;
+    launch_cell_expand<T, DIM>(P, gated, flags, stream);
+    return;
+  }
   // lazy materialisation: an update() only stores the reference positions and the
   // error bits and marks idx stale; the export itself runs (gated == 2) when the
   // host reads NeighborList.idx
@@ -1342,6 +1360,11 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   P.skin_pre = (nb->skin_pre && nb->skin_blk) ? 1 : 0;
   P.staged = (nb->staged && nb->blk_table && nb->nl16) ? 1 : 0;
   P.stage_cap = JMD_STAGE_BYTES / (int)sizeof(typename Vec4<T>::type);
+  P.cs_bits = (unsigned*)nb->cs_bits;
+  P.cs_lb = (unsigned long long*)nb->cs_lb;
+  P.cs_chunks = nb->cs_chunks;
+  P.cs_batches = nb->cs_batches;
+  P.cellscan = 0;
   P.blk_table = nb->blk_table;
   P.nl16 = nb->nl16;
   P.sw = nb->stencil_w > 0 ? nb->stencil_w : 1;
@@ -1363,6 +1386,10 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   }
   // the stencil scan addresses nl with 32-bit element offsets
   if ((unsigned long long)nb->m_int * (unsigned long long)nb->n_pad >= (1ull << 32)) return JMD_EINVAL;
+  // warp-per-cell scan: reference grid in the reference's storage order only
+  if (nb->cell_scan && nb->use_cells && P.bs == 0 && P.sw == 1 && P.rotate && !P.staged && P.cs_bits && P.cs_lb &&
+      P.cs_chunks > 0 && P.cs_batches > 0 && (size_t)nb->m_int * 33 * sizeof(int) <= 96 * 1024)
+    P.cellscan = 1;
   P.count_only = 0;
   P.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;
   P.no_public_idx = nb->no_public_idx;
@@ -1441,6 +1468,11 @@ int launch_update(NbrP<T, DIM>& P, cudaStream_t stream) {
   if ((rc = coop_grid(k_update<T, DIM>, cache_a, &grid))) return rc;
   k_update<T, DIM><<<grid, NB, 0, stream>>>(P);
   launch_scan<T, DIM>(P, 1, stream);
+  if (P.cellscan) {
+    launch_export<T, DIM>(P, 1, stream);
+    JMD_LAUNCH_CHECK();
+    return 0;
+  }
   if (P.format == JMD_DENSE) {
     k_update_c<T, DIM><<<grid_for(P.n, NB, 1 << 30), NB, 0, stream>>>(P);
   } else {

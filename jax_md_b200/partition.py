@@ -249,6 +249,36 @@ def _host_scalar(x):
   return x
 
 
+_CELL_SCAN = os.environ.get('JMD_CELL_SCAN', '1') != '0'
+_CELL_SCAN_MIN_OCCUPANCY = float(os.environ.get('JMD_CELL_SCAN_MIN_OCC', '8'))
+
+
+def _enable_cell_scan(ws, cl_capacity, static_kwargs):
+  """Warp-per-cell candidate scan (csrc/jmd_nbr_cellscan.cuh): one warp tests the
+  concatenated candidate stream of a home cell's 3^d stencil, 32 candidates at a
+  time.  It pays when a cell holds enough atoms to fill the lanes (LJ liquid: ~20
+  per cell); sparse cells (2-D soft spheres: ~2) keep the thread-per-atom scan.
+  `cell_scan=True/False` (static kwarg) overrides the occupancy heuristic."""
+  c = ws.c
+  c.cell_scan = 0
+  stage = static_kwargs.get('stage_positions', os.environ.get('JMD_STAGE', '0') != '0')
+  if not ws.use_cells or ws.fine != 1 or c.brick_shift != 0 or stage:
+    return
+  want = static_kwargs.get('cell_scan')
+  if want is None:
+    want = _CELL_SCAN and ws.n_capacity / max(ws.n_cells_ref, 1) >= _CELL_SCAN_MIN_OCCUPANCY
+  if not want:
+    return
+  c.cs_batches = -(-max(cl_capacity, 1) // 32)
+  c.cs_chunks = -(-(3 ** ws.dim) * max(cl_capacity, 1) // 32)
+  words = ws.n_cells_ref * c.cs_batches * c.cs_chunks * 32
+  if words * 4 > 8 << 30:
+    return
+  ws.buf('cs_bits', (max(words, 1),), torch.int32)
+  ws.buf('cs_lb', (ws.n_capacity // 2048 + 4,), torch.int64, 0)
+  c.cell_scan = 1
+
+
 def neighbor_list(displacement_or_metric,
                   box,
                   r_cutoff,
@@ -384,6 +414,8 @@ def neighbor_list(displacement_or_metric,
     # skin predicate fused into the drift kernel (simulate._Stepper.step)
     ws.buf('skin_blk', (c.n_pad // 256 + 1,), i4, 0)
     ws.drift_out = None            # (weakref to the drift's position tensor, its version)
+    ws.n_cells_ref = n_cells
+    ws.fine = fine
     ws.cell_size_host = cell_size
     ws.use_cells = use_cells
     return ws
@@ -411,6 +443,7 @@ def neighbor_list(displacement_or_metric,
       cl_capacity = int(max_cell * capacity_multiplier) + extra_capacity
       c.cell_capacity = cl_capacity
       width = 3 ** dim * cl_capacity
+      _enable_cell_scan(ws, cl_capacity, static_kwargs)
       # cells are stored in the reference's slot order, which depends on the
       # capacity (slot = rank mod capacity, partition.py:441): bin again.
       _lib.call('jmd_nbr_bin', ws.ref(), pp, 0, st)
