@@ -283,11 +283,12 @@ int jmd_scale_momentum(int dtype, int64_t count, void* momentum,
  * chain = [xi[cl] | p_xi[cl] | Q[cl] | KE] of the position dtype.  ke_red:
  * NULL -> use the chain's own KE, else the double KE slot written by the
  * force+kick kernel (simulate.py:662).  Writes the product of the sub-step
- * momentum scales to scale_out (position dtype). */
+ * momentum scales to scale_out (position dtype).  chain_out: where the updated
+ * chain goes (NULL or == chain: in place); the reference returns a new chain. */
 int jmd_nhc_half_step(int dtype, int chain_length, int chain_steps, int sy_steps,
                       double dt, double tau, int64_t dof, const void* kT_dev,
-                      void* chain, const double* ke_red, void* scale_out,
-                      void* stream);
+                      const void* chain, void* chain_out, const double* ke_red,
+                      void* scale_out, void* stream);
 
 /* FIRE momentum mixing + schedule (minimize.py:190-224) from red[FF,PP,FP].
  * fire_in/out = [dt, alpha] (position dtype), n_pos int32; out of place so

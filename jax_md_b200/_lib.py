@@ -104,7 +104,7 @@ _SIGNATURES = {
                            _P, _P, _I, _D, _P, _P, _P, _P, _P],
     'jmd_kick_reduce': [_I, _I, _I, _P, _P, _P, _I, _D, _P, _P, _P, _P],
     'jmd_scale_momentum': [_I, _L, _P, _P, _P],
-    'jmd_nhc_half_step': [_I, _I, _I, _I, _D, _D, _L, _P, _P, _P, _P, _P],
+    'jmd_nhc_half_step': [_I, _I, _I, _I, _D, _D, _L, _P, _P, _P, _P, _P, _P],
     'jmd_fire_mix': [_I, _L, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D,
                      _D, _P],
 }

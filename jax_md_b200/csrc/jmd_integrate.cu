@@ -123,8 +123,12 @@ __constant__ double SY7[7] = {0.784513610477560, 0.235573213359357, -1.177679984
 // chain layout (T): xi[cl] | p_xi[cl] | Q[cl] | KE | scale
 template <typename T>
 __global__ void k_nhc_half_step(int cl, int chain_steps, int sy_steps, T dt, T tau, long long dof,
-                                const T* kT_dev, T* chain, const double* ke_red, T* scale_out) {
+                                const T* kT_dev, const T* chain_in, T* chain, const double* ke_red, T* scale_out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // out of place: the caller's previous chain state stays intact (the reference returns a
+  // fresh NoseHooverChain every step, simulate.py:492-507)
+  if (chain_in != chain)
+    for (int m = 0; m < 3 * cl + 1; ++m) chain[m] = chain_in[m];
   T* xi = chain;
   T* p_xi = chain + cl;
   T* Q = chain + 2 * cl;
@@ -297,18 +301,19 @@ int jmd_scale_momentum(int dtype, int64_t count, void* momentum, const void* sca
 }
 
 int jmd_nhc_half_step(int dtype, int chain_length, int chain_steps, int sy_steps, double dt, double tau,
-                      int64_t dof, const void* kT_dev, void* chain, const double* ke_red, void* scale_out,
-                      void* stream) {
+                      int64_t dof, const void* kT_dev, const void* chain, void* chain_out, const double* ke_red,
+                      void* scale_out, void* stream) {
   if (!kT_dev || !chain || !scale_out || chain_length < 2) return JMD_EINVAL;
+  if (!chain_out) chain_out = (void*)chain;
   if (sy_steps != 1 && sy_steps != 3 && sy_steps != 5 && sy_steps != 7) return JMD_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == JMD_F32)
     k_nhc_half_step<float><<<1, 32, 0, s>>>(chain_length, chain_steps, sy_steps, (float)dt, (float)tau, dof,
-                                            (const float*)kT_dev, (float*)chain, ke_red, (float*)scale_out);
+                                            (const float*)kT_dev, (const float*)chain, (float*)chain_out, ke_red, (float*)scale_out);
   else if (dtype == JMD_F64)
     k_nhc_half_step<double><<<1, 32, 0, s>>>(chain_length, chain_steps, sy_steps, (double)(float)dt,
-                                             (double)(float)tau, dof, (const double*)kT_dev, (double*)chain,
-                                             ke_red, (double*)scale_out);
+                                             (double)(float)tau, dof, (const double*)kT_dev, (const double*)chain,
+                                             (double*)chain_out, ke_red, (double*)scale_out);
   else return JMD_EINVAL;
   JMD_LAUNCH_CHECK();
   return 0;

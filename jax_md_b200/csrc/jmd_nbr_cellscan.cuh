@@ -300,16 +300,35 @@ __global__ void __launch_bounds__(NB) k_nbr_offsets(NbrP<T, DIM> P, int gated) {
 }
 
 // ---- expansion of the accept masks into rows + public idx ------------------------------
+// Lanes are home atoms.  Every lane walks ITS OWN accept masks (staged in shared memory)
+// one set bit per iteration, so iteration i yields entry i of every row at once: the
+// store into the transposed internal list nl[i][slot] is coalesced without any staging.
+// For the public idx 32 iterations are parked in a 32 x 33 tile, turned into atom ids by
+// independent perm gathers, and flushed row by row (coalesced along the row; Dense rows
+// directly, sparse segments through a ballot compaction at their offsets).
+constexpr int CS_OFF_BITS = 11;              // cells up to 2047 atoms (cell_capacity is checked on the host side)
+
+// per-warp dynamic shared memory of the expand kernel
+__host__ __device__ inline size_t cs_expand_warp_bytes(int cs_chunks) {
+  return (size_t)cs_chunks * 32 * sizeof(unsigned)             // masks   [chunk][lane]
+         + (size_t)cs_chunks * 32 * sizeof(unsigned short)     // codes   [stream position]
+         + (size_t)32 * 33 * sizeof(int);                      // id tile [iteration][lane]
+}
+
 template <typename T, int DIM>
 __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_expand(NbrP<T, DIM> P, int gated, int flags) {
   if (gate_closed(P.state, gated)) return;
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ int cs_tiles[];          // per warp: [m_int][33] staged rows (slots)
+  extern __shared__ __align__(16) unsigned char cs_dyn[];
   __shared__ CsWarpSmem<T> smem[CS_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   CsWarpSmem<T>& sm = smem[w];
-  int* const tile = cs_tiles + (size_t)w * P.m_int * 33;
+  unsigned char* const mine = cs_dyn + (size_t)w * cs_expand_warp_bytes(P.cs_chunks);
+  unsigned* const bits_s = reinterpret_cast<unsigned*>(mine);
+  int* const tile = reinterpret_cast<int*>(mine + (size_t)P.cs_chunks * 32 * sizeof(unsigned));
+  unsigned short* const codes_s =
+      reinterpret_cast<unsigned short*>(mine + (size_t)P.cs_chunks * 32 * sizeof(unsigned) + 32 * 33 * sizeof(int));
   const int cell = blockIdx.x * nwarps + w;
   const bool rows = (flags & CS_ROWS) != 0;
   const bool pub = (flags & CS_IDX) != 0 && !P.no_public_idx && P.idx != nullptr;
@@ -323,14 +342,23 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_expand(NbrP<T, DIM> 
     const int total = cs_setup<T, DIM>(P, cell, lane, sm);
     __syncwarp();
     const int nchunks = min((total + 31) >> 5, P.cs_chunks);
+    // codes of the whole candidate stream: stencil cell << 11 | position inside the cell
+    for (int q = 0; q < nchunks; ++q) {
+      const int t = q * 32 + lane;
+      const int s = cs_find(sm.pre, t < total ? t : 0);
+      const int off = max(0, min(t - sm.pre[s], (1 << CS_OFF_BITS) - 1));
+      codes_s[t] = (unsigned short)((s << CS_OFF_BITS) | off);
+    }
     for (int hb = hs; hb < he; hb += 32) {
       const int batch = (hb - hs) >> 5;
       const int nh = min(32, he - hb);
       const int slot = hb + lane;
       int hid = 0x7fffffff, c_l = 0;
+      long long off_l = 0;
       if (lane < nh) {
         hid = P.perm[slot];
         c_l = batch < P.cs_batches ? min(P.cnt[slot], P.m_int) : 0;
+        if (pub && !dense && hid < P.n) off_l = P.offsets[hid];
         if (fin) {                           // partition.py:1128: reference_position = position
 #pragma unroll
           for (int d = 0; d < DIM; ++d) P.ref[(size_t)hid * DIM + d] = P.position[(size_t)hid * DIM + d];
@@ -340,59 +368,63 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_expand(NbrP<T, DIM> 
       int cmax = c_l;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+      // this batch's masks: coalesced global -> shared
       const unsigned* const gb = P.cs_bits + ((size_t)cell * P.cs_batches + batch) * ((size_t)P.cs_chunks * 32);
-      int k = 0;
-      for (int q = 0; q < (cmax > 0 ? nchunks : 0); ++q) {
-        const int t = q * 32 + lane;
-        const int s = cs_find(sm.pre, t < total ? t : 0);
-        __syncwarp();
-        sm.rank[lane] = sm.cstart[s] + (t - sm.pre[s]);
-        __syncwarp();
-        unsigned m = c_l > 0 ? __ldcs(gb + q * 32 + lane) : 0u;
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          if (k < P.m_int) tile[k * 33 + lane] = sm.rank[j];
-          ++k;
-        }
+      __syncwarp();
+      if (cmax > 0) {
+#pragma unroll 4
+        for (int q = 0; q < nchunks; ++q) bits_s[q * 32 + lane] = __ldcs(gb + q * 32 + lane);
       }
       __syncwarp();
-      if (rows) {
-        // internal transposed list: row kk of the cell's home atoms is contiguous
-        for (int kk = 0; kk < cmax; ++kk)
-          if (kk < c_l) P.nl[(size_t)kk * P.n_pad + slot] = tile[kk * 33 + lane];
-      }
-      if (pub) {
-        for (int h = 0; h < nh; ++h) {
-          const int a = __shfl_sync(FULL, hid, h);
-          const int c = __shfl_sync(FULL, c_l, h);
-          if (a >= P.n) continue;
-          if (dense) {
-            // Dense: idx[a, k] in candidate order, padded with N (partition.py:960-980, 1105)
-            for (long long k0 = 0; k0 < cap; k0 += 32) {
-              const long long kk = k0 + lane;
-              int v = P.n;
-              if (kk < c) v = __ldg(&P.perm[tile[(int)kk * 33 + h]]);
+      int q = -1;
+      unsigned m = 0u;
+      // Dense rows are written out to their full width (padding N), sparse ones to cmax
+      const int imax = (pub && dense) ? (int)cap : cmax;
+      for (int i0 = 0; i0 < imax; i0 += 32) {
+#pragma unroll 1
+        for (int ii = 0; ii < 32; ++ii) {
+          const int i = i0 + ii;
+          if (i < c_l) {
+            while (m == 0u && q + 1 < nchunks) { ++q; m = bits_s[q * 32 + lane]; }
+            const int j = m ? __ffs(m) - 1 : 0;
+            m &= m - 1u;
+            const unsigned code = codes_s[q * 32 + j];
+            const int rank = sm.cstart[code >> CS_OFF_BITS] + (int)(code & ((1u << CS_OFF_BITS) - 1u));
+            if (rows) P.nl[(size_t)i * P.n_pad + slot] = rank;       // coalesced over the lanes
+            tile[ii * 33 + lane] = rank;
+          }
+        }
+        if (pub) {
+          // slots -> atom ids, own column: independent gathers
+#pragma unroll 8
+          for (int ii = 0; ii < 32; ++ii)
+            if (i0 + ii < c_l) tile[ii * 33 + lane] = __ldg(&P.perm[tile[ii * 33 + lane]]);
+          __syncwarp();
+          const int kk = i0 + lane;
+          for (int h = 0; h < nh; ++h) {
+            const int a = __shfl_sync(FULL, hid, h);
+            const int c = __shfl_sync(FULL, c_l, h);
+            if (a >= P.n) continue;
+            if (dense) {
+              // Dense: idx[a, k] in candidate order, padded with N (partition.py:960-980, 1105)
+              const int v = kk < c ? tile[lane * 33 + h] : P.n;
               if (kk < cap) P.idx[(size_t)a * cap + kk] = v;
-            }
-          } else {
-            // Sparse: idx[0] = receivers, idx[1] = senders, ordered by sender then
-            // candidate order; OrderedSparse keeps receiver id < sender id (:1010-1032)
-            long long pos0 = P.offsets[a];
-            for (int k0 = 0; k0 < c; k0 += 32) {
-              const int kk = k0 + lane;
-              int v = -1;
-              if (kk < c) v = __ldg(&P.perm[tile[kk * 33 + h]]);
+            } else {
+              // Sparse: idx[0] = receivers, idx[1] = senders, ordered by sender then
+              // candidate order; OrderedSparse keeps receiver id < sender id (:1010-1032)
+              if (i0 >= c) continue;
+              const long long pos0 = __shfl_sync(FULL, off_l, h);
+              const int v = kk < c ? tile[lane * 33 + h] : -1;
               const bool keep = v >= 0 && (!ordered || v < a);
               const unsigned b = __ballot_sync(FULL, keep);
               const long long pos = pos0 + __popc(b & ((1u << lane) - 1u));
               if (keep && pos < cap) { P.idx[pos] = v; P.idx[cap + pos] = a; }
-              pos0 += __popc(b);
+              if (lane == h) off_l += __popc(b);
             }
           }
+          __syncwarp();
         }
       }
-      __syncwarp();
     }
   }
   if (pub && !dense) {
@@ -404,7 +436,7 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_expand(NbrP<T, DIM> 
       P.idx[cap + p] = P.n;
     }
   }
-  // last block: error bits / counters (ph_finalize), look-back words for the next scan
+  // last block: error bits / counters (ph_finalize)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -427,14 +459,15 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_expand(NbrP<T, DIM> 
   }
 }
 
-// shared memory of one expand block, or 0 if the staged rows do not fit
+// shared memory of one expand block, or 0 if it does not fit
+constexpr size_t CS_SMEM_MAX = 96 * 1024;
 template <typename T, int DIM>
 inline size_t cs_expand_smem(const NbrP<T, DIM>& P, int* warps) {
-  const size_t per_warp = (size_t)P.m_int * 33 * sizeof(int);
+  const size_t per_warp = cs_expand_warp_bytes(P.cs_chunks);
   int nw = CS_WARPS;
-  while (nw > 1 && nw * per_warp > 96 * 1024) nw >>= 1;
+  while (nw > 1 && nw * per_warp > CS_SMEM_MAX) nw >>= 1;
   *warps = nw;
-  return nw * per_warp <= 96 * 1024 ? nw * per_warp : 0;
+  return nw * per_warp <= CS_SMEM_MAX ? nw * per_warp : 0;
 }
 
 template <typename T, int DIM, int FMT, bool PERIODIC>
@@ -469,7 +502,10 @@ int launch_cell_expand(const NbrP<T, DIM>& P, int gated, int flags, cudaStream_t
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 64 || !optin[dev]) {
-    cudaFuncSetAttribute(k_nbr_cell_expand<T, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    // the full shared-memory carve-out: residency is bounded by the staged rows
+    cudaFuncSetAttribute(k_nbr_cell_expand<T, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_MAX);
+    cudaFuncSetAttribute(k_nbr_cell_expand<T, DIM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     if (dev < 64) optin[dev] = 1;
   }
   const bool pub = (flags & CS_IDX) != 0 && !P.no_public_idx && P.idx != nullptr;

@@ -36,8 +36,8 @@ def _flatten(obj, leaves, path=()):
     return ('list', [_flatten(o, leaves) for o in obj])
   if isinstance(obj, dict):
     return ('dict', {k: _flatten(v, leaves) for k, v in obj.items()})
-  if _dc.is_dataclass(obj) and not isinstance(obj, type) and not hasattr(obj, '_ws') \
-      and not hasattr(obj, '_buf'):       # in-place objects are carried by identity
+  if _dc.is_dataclass(obj) and not isinstance(obj, type) and not hasattr(obj, '_ws'):
+    # (a NeighborList -- `_ws` -- is updated in place and carried by identity)
     fields = {}
     for f in _dc.fields(obj):
       if f.metadata.get('static', False):

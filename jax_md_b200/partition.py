@@ -8,6 +8,7 @@ libjmd_b200.so (csrc/jmd_neighbor.cu).  `allocate` syncs with the device to
 read occupancies, as the reference does (partition.py:249,1094); `update` never
 syncs and is CUDA-graph capturable.
 """
+import copy as _copy
 import ctypes as C
 import logging
 import os
@@ -413,7 +414,8 @@ def neighbor_list(displacement_or_metric,
     ws.buf('state', (_lib.ST_COUNT,), torch.int64, 0)
     # skin predicate fused into the drift kernel (simulate._Stepper.step)
     ws.buf('skin_blk', (c.n_pad // 256 + 1,), i4, 0)
-    ws.drift_out = None            # (weakref to the drift's position tensor, its version)
+    ws.drift_out = None            # (weakref to the drift's position tensor, its version, update epoch)
+    ws.update_epoch = 0            # bumped by every update(): drift flags older than that are stale
     ws.n_cells_ref = n_cells
     ws.fine = fine
     ws.cell_size_host = cell_size
@@ -519,12 +521,15 @@ def neighbor_list(displacement_or_metric,
       raise ValueError('position shape/dtype differs from the allocated list')
     position = position.contiguous()
     st, pp = _lib.stream(), _lib.ptr(position)
+    # Did the drift kernel already evaluate the predicate for THIS tensor (same
+    # object, not modified since) against THIS list's current reference positions
+    # (no other update() ran in between)?  Then update() skips its own pass.
+    tag, ws.drift_out = ws.drift_out, None
+    fused_skin = (_FUSED_SKIN and tag is not None and tag[0]() is position
+                  and tag[1] == position._version and tag[2] == ws.update_epoch)
+    ws.update_epoch += 1
     if ws.update_mode == 'fused':
-      # Did the drift kernel already evaluate the predicate for THIS tensor
-      # (same object, not modified since)?  Then update() skips its own pass.
-      tag = ws.drift_out
-      ws.c.skin_pre = 1 if (_FUSED_SKIN and tag is not None and tag[0]() is position
-                            and tag[1] == position._version) else 0
+      ws.c.skin_pre = 1 if fused_skin else 0
       _lib.call('jmd_nbr_update', ws.ref(), pp, st)
       ws.c.skin_pre = 0
     else:
@@ -532,7 +537,9 @@ def neighbor_list(displacement_or_metric,
       _lib.call('jmd_nbr_bin', ws.ref(), pp, 1, st)
       _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 1, st)
       _lib.call('jmd_nbr_export', ws.ref(), pp, 1, st)
-    return neighbors
+    # partition.py:1107-1117 returns a new NeighborList; the buffers behind it are
+    # this list's own, rewritten in place (like jit with donated arguments)
+    return _copy.copy(neighbors)       # (not replace(): reading .idx would materialise a lazy idx)
 
   return NeighborListFns(allocate_fn, update_fn)
 

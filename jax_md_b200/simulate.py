@@ -151,7 +151,7 @@ class _Stepper:
       # the drift evaluated the skin predicate of R2 against this list's
       # reference positions (csrc/jmd_integrate.cu); update(R2) may reuse it
       import weakref
-      ws.drift_out = (weakref.ref(R2), R2._version)
+      ws.drift_out = (weakref.ref(R2), R2._version, ws.update_epoch)
     if fused and self.fused == 'pair':
       out = self.fn.launch(R2, neighbor, species, params, want_energy=False,
                            momentum=P2, mass=mass, dt_2=dt2_h, dt_dev=dt_dev,
@@ -200,20 +200,34 @@ def nve(energy_or_force_fn, shift_fn, dt=1e-3, **sim_kwargs):
 
 @dataclasses.dataclass
 class NoseHooverChain:
-  """simulate.py:350-374.  The fields are views into one device buffer laid
-  out [xi | p_xi | Q | KE] that the single-thread chain kernel updates."""
-  position: Any
-  momentum: Any
-  mass: Any
+  """simulate.py:350-374.  The chain lives in ONE device buffer laid out
+  [xi | p_xi | Q | KE] (what the single-thread chain kernel reads and writes);
+  `position`, `momentum`, `mass` and `kinetic_energy` are views of it.  Every
+  `apply_fn` writes a NEW buffer, so earlier states keep their own chain."""
+  _buf: Any
   tau: Any
-  kinetic_energy: Any
   degrees_of_freedom: int = dataclasses.static_field()
-  _buf: Any = dataclasses.static_field(default=None)
+  _cl: int = dataclasses.static_field(default=0)
+
+  @property
+  def position(self):
+    return self._buf[0:self._cl]
+
+  @property
+  def momentum(self):
+    return self._buf[self._cl:2 * self._cl]
+
+  @property
+  def mass(self):
+    return self._buf[2 * self._cl:3 * self._cl]
+
+  @property
+  def kinetic_energy(self):
+    return self._buf[3 * self._cl]
 
 
 def _make_chain(buf, cl, tau, dof):
-  return NoseHooverChain(buf[0:cl], buf[cl:2 * cl], buf[2 * cl:3 * cl], tau,
-                         buf[3 * cl], dof, buf)
+  return NoseHooverChain(buf, tau, dof, cl)
 
 
 @dataclasses.dataclass
@@ -252,12 +266,12 @@ def nvt_nose_hoover(energy_or_force_fn, shift_fn, dt, kT, chain_length=5,
       kT_cache[key] = t
     return t
 
-  def _half_step(state_chain, kT_t, R, ke_red):
+  def _half_step(buf_in, buf_out, dof, kT_t, R, ke_red):
     dtc = _lib.dtype_code(R.dtype)
     scale = torch.empty((1,), dtype=R.dtype, device=R.device)
     _lib.call('jmd_nhc_half_step', dtc, chain_length, chain_steps, sy_steps,
-              float(dt_f), float(tau), int(state_chain.degrees_of_freedom),
-              _lib.ptr(kT_t), _lib.ptr(state_chain._buf),
+              float(dt_f), float(tau), int(dof),
+              _lib.ptr(kT_t), _lib.ptr(buf_in), _lib.ptr(buf_out),
               None if ke_red is None else
               (ke_red.data_ptr() + 8 * _lib.RED_KINETIC),
               _lib.ptr(scale), _lib.stream())
@@ -276,7 +290,8 @@ def nvt_nose_hoover(energy_or_force_fn, shift_fn, dt, kT, chain_length=5,
     P = P.contiguous()
     KE = quantity.kinetic_energy(momentum=P, mass=m)
     buf = torch.zeros(3 * chain_length + 1, dtype=R.dtype, device=R.device)
-    Q = f32(_kT) * (tau ** f32(2))                         # simulate.py:440-442
+    kT_h = float(_kT.detach().cpu()) if isinstance(_kT, torch.Tensor) else _kT
+    Q = f32(kT_h) * (tau ** f32(2))                        # simulate.py:440-442
     buf[2 * chain_length:3 * chain_length] = float(Q)
     buf[2 * chain_length] = float(f32(Q * f32(dof)))
     buf[3 * chain_length] = KE
@@ -288,15 +303,18 @@ def nvt_nose_hoover(energy_or_force_fn, shift_fn, dt, kT, chain_length=5,
     R = state.position
     kT_t = _kT_dev(_kT, R)
     chain = state.chain
+    dof = chain.degrees_of_freedom
+    buf = torch.empty_like(chain._buf)       # the new state's chain (the old one stays intact)
     # update_mass + first half step on the carried KE (simulate.py:654-658)
-    s1 = _half_step(chain, kT_t, R, None)
+    s1 = _half_step(chain._buf, buf, dof, kT_t, R, None)
     R2, P2, F2 = stepper.step(R, state.momentum, state.force, state.mass,
                               kwargs, scale_dev=s1)
     # chain.KE = KE(p) from the fused reduction, second half step (:660-665)
-    s2 = _half_step(chain, kT_t, R, stepper.red(R))
+    s2 = _half_step(buf, buf, dof, kT_t, R, stepper.red(R))
     _lib.call('jmd_scale_momentum', _lib.dtype_code(R.dtype), P2.numel(),
               _lib.ptr(P2), _lib.ptr(s2), _lib.stream())
-    return state.set(position=R2, momentum=P2, force=F2)
+    return state.set(position=R2, momentum=P2, force=F2,
+                     chain=_make_chain(buf, chain_length, chain.tau, dof))
 
   apply_fn._stepper = stepper
   return init_fn, apply_fn

@@ -76,8 +76,11 @@ class PairNeighborListFn:
 
   # -- parameter canonicalisation (smap.py:697-846) ---------------------------
   def _tensor(self, x, dtype, device):
-    key = (id(x), dtype)
-    hit = self._conv.get(key)
+    # converted copies are cached per tensor object AND version (in-place edits make a
+    # new entry); NumPy inputs can be mutated without notice, so they are never cached
+    cacheable = isinstance(x, torch.Tensor)
+    key = (id(x), dtype, x._version if cacheable else None)
+    hit = self._conv.get(key) if cacheable else None
     if hit is not None and hit[0] is x:
       return hit[1]
     if isinstance(x, torch.Tensor):
@@ -93,7 +96,8 @@ class PairNeighborListFn:
           'smap.pair_neighbor_list path.')
     if len(self._conv) > 64:
       self._conv.clear()
-    self._conv[key] = (x, t)
+    if cacheable:
+      self._conv[key] = (x, t)
     return t
 
   def _pair_struct(self, R, species, params, sparse=False):
@@ -240,6 +244,12 @@ class PairNeighborListFn:
     grad_params = [(n, params[n]) for n in ('sigma', 'epsilon')
                    if isinstance(params.get(n), torch.Tensor)
                    and params[n].requires_grad]
+    if torch.is_grad_enabled():
+      for n, v in params.items():
+        if n not in ('sigma', 'epsilon') and isinstance(v, torch.Tensor) and v.requires_grad:
+          raise NotImplementedError(
+              f'd(energy)/d({n}) is not produced by the fused kernel (only positions, sigma and '
+              'epsilon are); use a plain Python potential for the generic smap.pair_neighbor_list path.')
     needs_grad = torch.is_grad_enabled() and (R.requires_grad or grad_params)
     if not needs_grad:
       out = self.launch(R, neighbor, species, params, True, per_atom)
