@@ -141,19 +141,23 @@ typedef struct {
    * and jmd_nbr_export(gated = 2) materialises it on demand (NeighborList.idx read). */
   int32_t lazy_idx;
   /* Warp-per-cell candidate scan (csrc/jmd_nbr_cellscan.cuh), used when cell_scan != 0
-   * and the search grid is the reference grid: one warp owns a home cell, tests the
-   * concatenated candidate stream of its 3^d stencil 32 candidates at a time and leaves
-   * one accept bit per test in cs_bits [n_cells][cs_batches][cs_chunks][32] (cs_batches =
+   * and the search grid is the reference grid: one warp owns a home cell and tests the
+   * concatenated candidate stream of its 3^d stencil 32 candidates at a time (cs_batches =
    * ceil(cell_capacity / 32) groups of home atoms, cs_chunks = ceil(3^d * cell_capacity /
-   * 32)); jmd_nbr_export expands the masks into the rows and the public idx.  cs_lb:
-   * [n / 2048 + 2] look-back words of the sparse offsets scan.  With cell_scan the rows
-   * of `nl` are complete after jmd_nbr_export, not after jmd_nbr_build. */
+   * 32) chunks of candidates).  cs_lb: [n / 2048 + 2] look-back words of the sparse
+   * offsets scan.  cs_bits is reserved (must be NULL). */
   int32_t cell_scan;
   int32_t cs_chunks;
   int32_t cs_batches;
   int32_t _pad2;
   uint32_t* cs_bits;
   uint64_t* cs_lb;
+  /* Device-resident atom counts {n, n_rows} (or NULL): when set, jmd_nve_kick_drift,
+   * jmd_pair_force and the jmd_dd_comm_* kernels take the counts from here instead of the
+   * host fields, so a captured CUDA graph of the step stays valid when a rebuild of the
+   * domain decomposition changes the local atom count (grids are sized for `n`, which
+   * then is the capacity). */
+  const int32_t* n_dev;
 } jmd_nbr_t;
 
 /* ---- neighbour list (replaces partition.py:349-471, 911-1154) ------------- */
@@ -314,10 +318,13 @@ enum {
   JMD_DD_MIG_R = 7,
   JMD_DD_IN_L = 8,    /* atoms that arrived from the left / right */
   JMD_DD_IN_R = 9,
+  JMD_DD_N_LOC = 10,  /* owned + ghost atoms; {N_LOC, N_ROWS} is the jmd_nbr_t.n_dev pair */
+  JMD_DD_N_ROWS = 11, /* == N_OWN */
   JMD_DD_INFO_COUNT = 16
 };
 #define JMD_DD_ELIST 1 /* a selection list exceeded its capacity */
 #define JMD_DD_ECAP 2  /* owned + ghost atoms exceed the array capacity */
+#define JMD_DD_ETIMEOUT 4 /* a peer's halo / flag did not arrive (spin-wait timed out) */
 
 /* For atoms i < n (i < min(n, *n_dev) when n_dev != NULL, so the count can stay on the
  * device): d = (pos[i, axis] - lo) wrapped into [-L/2, L/2).  Appends i to
@@ -360,6 +367,63 @@ int jmd_dd_pack_counted(int dtype, int ncomp, int cap, const int32_t* idx,
 int jmd_dd_place(int dtype, int dim, int cap_total, int cap_list, const int32_t* counters,
                  const void* recv_l, const void* recv_r, void* R, int32_t* info,
                  void* stream);
+
+/* Ordered variant of jmd_dd_select: the lists come out sorted by atom index (single
+ * pass, decoupled look-back), so ghost order and hence summation order are reproducible.
+ * scratch: uint64[n / 2048 + 2] look-back words + 1 tile counter, zeroed by the call. */
+int jmd_dd_select_ordered(int dtype, int dim, int n, const int32_t* n_dev, const void* position,
+                          int axis, double lo, double L, double thr_a, double thr_b,
+                          int32_t* list_a, int32_t* list_b, int32_t* counters, int cap,
+                          uint64_t* scratch, void* stream);
+
+/* ---- per-step exchange over NVLink peer memory (CUDA IPC; one process per GPU) --------
+ * Every rank owns one "shared block" (jmd_p2p_alloc) that its ring neighbours map
+ * (jmd_p2p_open): two parities x two sides of landing rows for ghost positions, a signal
+ * word per side and one rebuild-flag word per rank.  A step is then two kernels with no
+ * host involvement and no NCCL call, so it can live inside a CUDA graph:
+ *   jmd_dd_comm_push  gathers the face atoms and STORES them straight into the
+ *                     neighbours' landing rows through the peer mapping, then releases
+ *                     the neighbours' signal words; writes this rank's rebuild flag (OR
+ *                     of the drift's skin flags) into every rank's flag word.
+ *   jmd_dd_comm_wait  waits for both signals, copies the landed rows behind the owned
+ *                     atoms and into the cell-sorted float4 array; block 0 ORs all
+ *                     ranks' flags and publishes (epoch << 1 | any) to a mapped host word,
+ *                     which the host polls while the force kernel still runs.
+ * Spin-waits give up after ~8 s and set JMD_DD_ETIMEOUT in info[JMD_DD_ERROR]. */
+int jmd_p2p_alloc(int64_t bytes, void** ptr, uint8_t* handle64);
+int jmd_p2p_open(const uint8_t* handle64, void** ptr);
+int jmd_p2p_close(void* ptr);
+int jmd_p2p_free(void* ptr);
+int jmd_host_flag_alloc(uint64_t** host_ptr, uint64_t** dev_ptr);   /* mapped pinned word */
+int jmd_host_flag_free(uint64_t* host_ptr);
+
+typedef struct {
+  int32_t dtype, dim;
+  int32_t rank, world;
+  int32_t cap_list;            /* rows per landing buffer */
+  int32_t always_rebuild;
+  const int32_t* face_l;       /* [cap_list] owned-atom indices sent to the left neighbour */
+  const int32_t* face_r;
+  const int32_t* face_counts;  /* [2] device-resident list lengths */
+  int32_t* info;               /* JMD_DD_* words */
+  uint64_t* epoch;             /* [1] device step counter */
+  unsigned int* ticket;        /* [2] zero-initialised scratch */
+  const int32_t* skin_blk;     /* drift's skin flags (jmd_nbr_t.skin_blk) */
+  /* this rank's shared block: */
+  void* land;                  /* [2][2][cap_list][dim]: parity, side (0 = from left) */
+  uint64_t* signal;            /* [2] epoch of the last complete push from the left / right */
+  uint64_t* flags;             /* [2 parities][world] (epoch << 1 | flag), slot r written by rank r */
+  /* peers: */
+  void* peer_land_l;           /* left neighbour's `land` (we are ITS right side) */
+  void* peer_land_r;
+  uint64_t* peer_signal_l;     /* left neighbour's `signal` */
+  uint64_t* peer_signal_r;
+  uint64_t* const* peer_flags; /* device array [world] of every rank's `flags` */
+  uint64_t* host_flag;         /* device address of the mapped host word */
+} jmd_dd_t;
+
+int jmd_dd_comm_push(const jmd_dd_t* dd, const void* R, void* stream);
+int jmd_dd_comm_wait(const jmd_dd_t* dd, const jmd_nbr_t* nb, void* R, void* stream);
 
 const char* jmd_version(void);
 

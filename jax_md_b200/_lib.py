@@ -22,9 +22,9 @@ ST_EXPORT_PENDING = 8
 ST_COUNT = 16
 # jmd_dd_* info words (include/jmd_b200.h)
 (DD_N_OWN, DD_FACE_L, DD_FACE_R, DD_FROM_L, DD_FROM_R, DD_ERROR, DD_MIG_L, DD_MIG_R,
- DD_IN_L, DD_IN_R) = range(10)
+ DD_IN_L, DD_IN_R, DD_N_LOC, DD_N_ROWS) = range(12)
 DD_INFO_COUNT = 16
-DD_ELIST, DD_ECAP = 1, 2
+DD_ELIST, DD_ECAP, DD_ETIMEOUT = 1, 2, 4
 RED_ENERGY, RED_KINETIC, RED_VIRIAL = 0, 1, 2
 RED_DSIGMA, RED_DEPSILON, RED_FF, RED_PP, RED_FP = 8, 9, 10, 11, 12
 RED_COUNT = 16
@@ -60,7 +60,8 @@ class NbrT(C.Structure):
       ('nl16', C.c_void_p), ('blk_table', C.c_void_p),
       ('skin_blk', C.c_void_p), ('skin_pre', C.c_int32), ('lazy_idx', C.c_int32),
       ('cell_scan', C.c_int32), ('cs_chunks', C.c_int32), ('cs_batches', C.c_int32),
-      ('_pad2', C.c_int32), ('cs_bits', C.c_void_p), ('cs_lb', C.c_void_p)]
+      ('_pad2', C.c_int32), ('cs_bits', C.c_void_p), ('cs_lb', C.c_void_p),
+      ('n_dev', C.c_void_p)]
 
 
 class PairT(C.Structure):
@@ -71,6 +72,21 @@ class PairT(C.Structure):
               ('r_onset', C.c_double), ('r_cutoff', C.c_double),
               ('r_onset2', C.c_double), ('r_cutoff2', C.c_double),
               ('switch_denom', C.c_double)]
+
+
+class DdT(C.Structure):
+  """jmd_dd_t: per-step peer-memory exchange of the domain decomposition."""
+  _fields_ = [('dtype', C.c_int32), ('dim', C.c_int32), ('rank', C.c_int32),
+              ('world', C.c_int32), ('cap_list', C.c_int32),
+              ('always_rebuild', C.c_int32),
+              ('face_l', C.c_void_p), ('face_r', C.c_void_p),
+              ('face_counts', C.c_void_p), ('info', C.c_void_p),
+              ('epoch', C.c_void_p), ('ticket', C.c_void_p),
+              ('skin_blk', C.c_void_p), ('land', C.c_void_p),
+              ('signal', C.c_void_p), ('flags', C.c_void_p),
+              ('peer_land_l', C.c_void_p), ('peer_land_r', C.c_void_p),
+              ('peer_signal_l', C.c_void_p), ('peer_signal_r', C.c_void_p),
+              ('peer_flags', C.c_void_p), ('host_flag', C.c_void_p)]
 
 
 class SwT(C.Structure):
@@ -96,6 +112,15 @@ _SIGNATURES = {
     'jmd_dd_compact': [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'jmd_dd_pack_counted': [_I, _I, _I, _P, _P, _P, _P, _P],
     'jmd_dd_place': [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    'jmd_dd_select_ordered': [_I, _I, _I, _P, _P, _I, _D, _D, _D, _D, _P, _P, _P, _I, _P, _P],
+    'jmd_p2p_alloc': [_L, C.POINTER(C.c_void_p), _P],
+    'jmd_p2p_open': [_P, C.POINTER(C.c_void_p)],
+    'jmd_p2p_close': [_P],
+    'jmd_p2p_free': [_P],
+    'jmd_host_flag_alloc': [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)],
+    'jmd_host_flag_free': [_P],
+    'jmd_dd_comm_push': [C.POINTER(DdT), _P, _P],
+    'jmd_dd_comm_wait': [C.POINTER(DdT), C.POINTER(NbrT), _P, _P],
     'jmd_pair_force': [C.POINTER(NbrT), C.POINTER(PairT), _P, _P, _P, _P, _P,
                        _P, _P, _I, _D, _P, _I, _P],
     'jmd_sw_force': [C.POINTER(NbrT), C.POINTER(SwT), _P, _P, _P, _P, _P, _P, _I,

@@ -2,6 +2,7 @@
 // and gather-pack of halo and migration payloads.  The exchange itself is NCCL
 // send/recv issued by the host on the same stream (jax_md_b200/domain.py).
 #include <cuda_runtime.h>
+#include <string.h>
 #include "jmd_common.cuh"
 
 namespace {
@@ -182,8 +183,256 @@ __global__ void k_dd_place(int dim, int cap_total, int cap_list, const int* coun
     info[JMD_DD_FACE_R] = min(counters[1], cap_list);
     info[JMD_DD_FROM_L] = ok ? nl : 0;
     info[JMD_DD_FROM_R] = ok ? nr : 0;
+    info[JMD_DD_N_LOC] = n_own + (ok ? nl + nr : 0);
+    info[JMD_DD_N_ROWS] = n_own;
     info[JMD_DD_ERROR] |= (ok ? 0 : JMD_DD_ECAP) | ((counters[0] > cap_list || counters[1] > cap_list) ? JMD_DD_ELIST : 0);
   }
+}
+
+// ---- ordered selection (single pass, decoupled look-back) -----------------------------
+// Tiles of 2048 atoms handed out by an atomic counter; a tile's running prefix packs both
+// list counts into one 64-bit look-back word: [2 flag | 31 count_b | 31 count_a].
+template <typename T>
+__global__ void __launch_bounds__(256) k_dd_select_ordered(int dim, int n, const int* n_dev, const T* pos, int axis,
+                                                           T lo, T L, T thr_a, T thr_b, int* list_a, int* list_b,
+                                                           int* counters, int cap, unsigned long long* lb,
+                                                           int tiles) {
+  if (n_dev) n = min(n, *n_dev);
+  __shared__ int s_tile;
+  __shared__ unsigned long long s_pre;
+  __shared__ unsigned long long wsum[8];
+  constexpr unsigned long long F_AGG = 1ull << 62, F_PRE = 2ull << 62, MASK = (1ull << 62) - 1ull;
+  unsigned long long* counter = lb + tiles;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(counter, 1ull);
+  __syncthreads();
+  const int tile = s_tile;
+  const T half = L * T(0.5);
+  const int base = tile * 2048 + threadIdx.x * 8;
+  unsigned fa = 0, fb = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = base + j;
+    if (i < n) {
+      T d = pos[(size_t)i * dim + axis] - lo;
+      if (d >= half) d -= L;
+      else if (d < -half) d += L;
+      if (d < thr_a) fa |= 1u << j;
+      if (d >= thr_b) fb |= 1u << j;
+    }
+  }
+  // exclusive scan of (count_a, count_b) packed as a | b << 31 over the block
+  const unsigned long long mine = (unsigned long long)__popc(fa) | ((unsigned long long)__popc(fb) << 31);
+  unsigned long long incl = mine;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  unsigned long long wbase = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < w) wbase += wsum[k];
+    tot += wsum[k];
+  }
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = lb;
+    unsigned long long run = 0;
+    if (tile > 0) {
+      st[tile] = F_AGG | tot;
+      int p = tile - 1;
+      while (true) {
+        unsigned long long x;
+        do { x = st[p]; } while ((x >> 62) == 0ull);
+        run += x & MASK;
+        if ((x >> 62) == 2ull) break;
+        --p;
+      }
+    }
+    __threadfence();
+    st[tile] = F_PRE | (run + tot);
+    s_pre = run;
+    if (tile == tiles - 1) {            // totals (entries beyond `cap` are counted, not stored)
+      const unsigned long long all = run + tot;
+      counters[0] = (int)(all & 0x7fffffffull);
+      counters[1] = (int)((all >> 31) & 0x7fffffffull);
+    }
+  }
+  __syncthreads();
+  const unsigned long long excl = s_pre + wbase + incl - mine;
+  int pa = (int)(excl & 0x7fffffffull), pb = (int)((excl >> 31) & 0x7fffffffull);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (fa & (1u << j)) { if (pa < cap) list_a[pa] = base + j; ++pa; }
+    if (fb & (1u << j)) { if (pb < cap) list_b[pb] = base + j; ++pb; }
+  }
+}
+
+// ---- per-step exchange through peer memory ---------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spins until *p >= want (or *p >> 1 >= want for flag words); false on timeout (~8 s)
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want, int shift,
+                                           unsigned long long* last) {
+  const long long t0 = clock64();
+  unsigned long long v;
+  while (((v = ld_acquire_sys(p)) >> shift) < want) {
+    if (clock64() - t0 > 16000000000ll) { *last = v; return false; }   // ~8 s
+    __nanosleep(64);
+  }
+  *last = v;
+  return true;
+}
+
+template <typename T>
+struct DdP {
+  int dim, rank, world, cap_list, always_rebuild;
+  const int *face_l, *face_r, *face_counts;
+  int* info;
+  unsigned long long* epoch;
+  unsigned int* ticket;
+  const int* skin_blk;
+  T* land;
+  unsigned long long *signal, *flags;
+  T *peer_land_l, *peer_land_r;
+  unsigned long long *peer_signal_l, *peer_signal_r;
+  unsigned long long* const* peer_flags;
+  unsigned long long* host_flag;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_dd_comm_push(DdP<T> D, const T* R) {
+  const unsigned long long ep = *D.epoch + 1ull;
+  const int parity = (int)(ep & 1ull);
+  const int dim = D.dim;
+  const size_t side_rows = (size_t)D.cap_list * dim;
+  // face atoms -> the neighbours' landing rows (we are the left neighbour's RIGHT side and
+  // the right neighbour's LEFT side)
+  const int nl = min(D.face_counts[0], D.cap_list), nr = min(D.face_counts[1], D.cap_list);
+  const long long total = (long long)(nl + nr) * dim;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int k = (int)(e / dim), c = (int)(e % dim);
+    if (k < nl) {
+      T* dst = D.peer_land_l + ((size_t)parity * 2 + 1) * side_rows;
+      dst[(size_t)k * dim + c] = R[(size_t)D.face_l[k] * dim + c];
+    } else {
+      T* dst = D.peer_land_r + ((size_t)parity * 2 + 0) * side_rows;
+      dst[(size_t)(k - nl) * dim + c] = R[(size_t)D.face_r[k - nl] * dim + c];
+    }
+  }
+  // this rank's rebuild flag -> every rank's flag word (block 0)
+  if (blockIdx.x == 0) {
+    const int n_own = D.info[JMD_DD_N_OWN];
+    const int nblk = (n_own + 255) / 256;
+    int moved = D.always_rebuild;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) moved |= (D.skin_blk[b] != 0);
+    const int any = __syncthreads_or(moved);
+    // (flag words are double-buffered by step parity like the landing rows: a rank that
+    // runs one step ahead never overwrites a word a slower rank still has to read)
+    if (threadIdx.x < D.world)
+      st_release_sys(D.peer_flags[threadIdx.x] + (size_t)parity * D.world + D.rank,
+                     (ep << 1) | (unsigned long long)(any ? 1 : 0));
+  }
+  // release the neighbours' signals once every block's rows are out
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&D.ticket[0], 1u);
+    if (t == gridDim.x - 1) {
+      D.ticket[0] = 0u;
+      __threadfence_system();
+      st_release_sys(D.peer_signal_l + 1, ep);
+      st_release_sys(D.peer_signal_r + 0, ep);
+    }
+  }
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) k_dd_comm_wait(DdP<T> D, T* R, typename Vec4<T>::type* pos_sorted,
+                                                      const int* inv_perm) {
+  const unsigned long long ep = *D.epoch + 1ull;
+  const int parity = (int)(ep & 1ull);
+  __shared__ int ok_s;
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    bool ok = spin_until(D.signal + 0, ep, 0, &v);
+    ok = spin_until(D.signal + 1, ep, 0, &v) && ok;
+    ok_s = ok ? 1 : 0;
+    if (!ok) atomicOr(&D.info[JMD_DD_ERROR], JMD_DD_ETIMEOUT);
+  }
+  __syncthreads();
+  const int n_own = D.info[JMD_DD_N_OWN], nl = D.info[JMD_DD_FROM_L], nr = D.info[JMD_DD_FROM_R];
+  const size_t side_rows = (size_t)D.cap_list * DIM;
+  const T* from_l = D.land + ((size_t)parity * 2 + 0) * side_rows;
+  const T* from_r = D.land + ((size_t)parity * 2 + 1) * side_rows;
+  if (ok_s) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nl + nr; k += stride) {
+      const T* src = k < nl ? from_l + (size_t)k * DIM : from_r + (size_t)(k - nl) * DIM;
+      T r[3] = {T(0), T(0), T(0)};
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) {
+        r[c] = src[c];
+        R[(size_t)(n_own + k) * DIM + c] = r[c];
+      }
+      if (pos_sorted) {
+        typename Vec4<T>::type v;
+        v.x = r[0]; v.y = r[1]; v.z = r[2]; v.w = T(0);
+        pos_sorted[inv_perm[n_own + k]] = v;
+      }
+    }
+  }
+  // global rebuild decision -> mapped host word (block 0); last block advances the epoch
+  if (blockIdx.x == 0) {
+    int any = 0;
+    if (threadIdx.x < D.world) {
+      unsigned long long v = 0;
+      if (!spin_until(D.flags + (size_t)parity * D.world + threadIdx.x, ep, 1, &v))
+        atomicOr(&D.info[JMD_DD_ERROR], JMD_DD_ETIMEOUT);
+      any = (int)(v & 1ull);
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) {
+      st_release_sys(D.host_flag, (ep << 1) | (unsigned long long)(any ? 1 : 0));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&D.ticket[1], 1u);
+    if (t == gridDim.x - 1) {
+      D.ticket[1] = 0u;
+      *D.epoch = ep;
+    }
+  }
+}
+
+template <typename T>
+int fill_dd(DdP<T>& D, const jmd_dd_t* dd) {
+  if (!dd || dd->world < 1 || dd->world > 256 || dd->cap_list < 1) return JMD_EINVAL;
+  if (!dd->face_l || !dd->face_r || !dd->face_counts || !dd->info || !dd->epoch || !dd->ticket || !dd->land ||
+      !dd->signal || !dd->flags || !dd->peer_land_l || !dd->peer_land_r || !dd->peer_signal_l ||
+      !dd->peer_signal_r || !dd->peer_flags || !dd->host_flag || !dd->skin_blk)
+    return JMD_EINVAL;
+  D.dim = dd->dim; D.rank = dd->rank; D.world = dd->world; D.cap_list = dd->cap_list;
+  D.always_rebuild = dd->always_rebuild;
+  D.face_l = dd->face_l; D.face_r = dd->face_r; D.face_counts = dd->face_counts; D.info = dd->info;
+  D.epoch = (unsigned long long*)dd->epoch; D.ticket = dd->ticket; D.skin_blk = dd->skin_blk;
+  D.land = (T*)dd->land; D.signal = (unsigned long long*)dd->signal; D.flags = (unsigned long long*)dd->flags;
+  D.peer_land_l = (T*)dd->peer_land_l; D.peer_land_r = (T*)dd->peer_land_r;
+  D.peer_signal_l = (unsigned long long*)dd->peer_signal_l; D.peer_signal_r = (unsigned long long*)dd->peer_signal_r;
+  D.peer_flags = (unsigned long long* const*)dd->peer_flags;
+  D.host_flag = (unsigned long long*)dd->host_flag;
+  return 0;
 }
 
 inline int blocks_for(long long n) {
@@ -292,6 +541,101 @@ int jmd_dd_place(int dtype, int dim, int cap_total, int cap_list, const int32_t*
     k_dd_place<double><<<g, 256, 0, s>>>(dim, cap_total, cap_list, counters, (const double*)recv_l,
                                          (const double*)recv_r, (double*)R, info);
   else return JMD_EINVAL;
+  JMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int jmd_dd_select_ordered(int dtype, int dim, int n, const int32_t* n_dev, const void* position, int axis, double lo,
+                          double L, double thr_a, double thr_b, int32_t* list_a, int32_t* list_b,
+                          int32_t* counters, int cap, uint64_t* scratch, void* stream) {
+  if (!position || !list_a || !list_b || !counters || !scratch || axis < 0 || axis >= dim || n < 0) return JMD_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tiles = n / 2048 + 1;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(uint64_t) * (tiles + 1), s);
+  if (e != cudaSuccess) return (int)e;
+  if (dtype == JMD_F32)
+    k_dd_select_ordered<float><<<tiles, 256, 0, s>>>(dim, n, n_dev, (const float*)position, axis, (float)lo, (float)L,
+                                                     (float)thr_a, (float)thr_b, list_a, list_b, counters, cap,
+                                                     (unsigned long long*)scratch, tiles);
+  else if (dtype == JMD_F64)
+    k_dd_select_ordered<double><<<tiles, 256, 0, s>>>(dim, n, n_dev, (const double*)position, axis, lo, L, thr_a,
+                                                      thr_b, list_a, list_b, counters, cap,
+                                                      (unsigned long long*)scratch, tiles);
+  else return JMD_EINVAL;
+  JMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int jmd_p2p_alloc(int64_t bytes, void** ptr, uint8_t* handle64) {
+  if (!ptr || !handle64 || bytes <= 0) return JMD_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(*ptr, 0, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int jmd_p2p_open(const uint8_t* handle64, void** ptr) {
+  if (!ptr || !handle64) return JMD_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int jmd_p2p_close(void* ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : 0; }
+int jmd_p2p_free(void* ptr) { return ptr ? (int)cudaFree(ptr) : 0; }
+
+int jmd_host_flag_alloc(uint64_t** host_ptr, uint64_t** dev_ptr) {
+  if (!host_ptr || !dev_ptr) return JMD_EINVAL;
+  cudaError_t e = cudaHostAlloc((void**)host_ptr, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e != cudaSuccess) return (int)e;
+  memset(*host_ptr, 0, 64);
+  return (int)cudaHostGetDevicePointer((void**)dev_ptr, *host_ptr, 0);
+}
+
+int jmd_host_flag_free(uint64_t* host_ptr) { return host_ptr ? (int)cudaFreeHost(host_ptr) : 0; }
+
+int jmd_dd_comm_push(const jmd_dd_t* dd, const void* R, void* stream) {
+  if (!dd || !R) return JMD_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = blocks_for((long long)dd->cap_list * dd->dim * 2);
+  int rc;
+  if (dd->dtype == JMD_F32) {
+    DdP<float> D;
+    if ((rc = fill_dd(D, dd))) return rc;
+    k_dd_comm_push<float><<<g, 256, 0, s>>>(D, (const float*)R);
+  } else if (dd->dtype == JMD_F64) {
+    DdP<double> D;
+    if ((rc = fill_dd(D, dd))) return rc;
+    k_dd_comm_push<double><<<g, 256, 0, s>>>(D, (const double*)R);
+  } else return JMD_EINVAL;
+  JMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int jmd_dd_comm_wait(const jmd_dd_t* dd, const jmd_nbr_t* nb, void* R, void* stream) {
+  if (!dd || !R) return JMD_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = blocks_for((long long)dd->cap_list * 2);
+  int rc;
+#define JMD_WAIT(T, DIM)                                                                              \
+  {                                                                                                   \
+    DdP<T> D;                                                                                         \
+    if ((rc = fill_dd(D, dd))) return rc;                                                             \
+    k_dd_comm_wait<T, DIM><<<g, 256, 0, s>>>(D, (T*)R, nb ? (typename Vec4<T>::type*)nb->pos_sorted : nullptr, \
+                                             nb ? nb->inv_perm : nullptr);                            \
+  }
+  if (dd->dtype == JMD_F32 && dd->dim == 3) JMD_WAIT(float, 3)
+  else if (dd->dtype == JMD_F32 && dd->dim == 2) JMD_WAIT(float, 2)
+  else if (dd->dtype == JMD_F64 && dd->dim == 3) JMD_WAIT(double, 3)
+  else if (dd->dtype == JMD_F64 && dd->dim == 2) JMD_WAIT(double, 2)
+  else return JMD_EINVAL;
+#undef JMD_WAIT
   JMD_LAUNCH_CHECK();
   return 0;
 }

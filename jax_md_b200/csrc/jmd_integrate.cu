@@ -31,6 +31,7 @@ struct StepP {
   int n_rows;
   T threshold_sq;
   Space<T, DIM> nsp;       // the neighbour list's metric
+  const int* n_dev;        // {n, n_rows} on the device (domain decomposition): drift the owned rows
 };
 
 template <typename T>
@@ -43,6 +44,7 @@ template <typename T, int DIM>
 __global__ void __launch_bounds__(IB) k_kick_drift(StepP<T, DIM> S) {
   const int a = blockIdx.x * IB + threadIdx.x;
   bool moved = false;
+  if (S.n_dev) { S.n = S.n_dev[1]; S.n_rows = S.n_dev[1]; }
   if (a < S.n) {
     T dt = S.dt, dt_2 = S.dt_2;
     if (S.dt_dev) {
@@ -236,7 +238,12 @@ int launch_kick_drift(const jmd_space_t* sp, int n, const jmd_nbr_t* nb, const v
   S.species = nb ? nb->species : nullptr;
   S.ref = nullptr; S.skin_blk = nullptr; S.n_rows = 0; S.threshold_sq = T(0);
   S.nsp.init(nb ? nb->space : *sp);
-  if (nb && nb->skin_blk && nb->reference_position) {
+  S.n_dev = nb ? nb->n_dev : nullptr;
+  if (nb && nb->n_dev && nb->skin_blk && nb->reference_position) {
+    S.ref = (const T*)nb->reference_position;
+    S.skin_blk = nb->skin_blk;
+    S.threshold_sq = (T)nb->threshold_sq;
+  } else if (nb && nb->skin_blk && nb->reference_position) {
     // drift over all atoms of the list, or over its owned rows (domain decomposition:
     // ghosts are refreshed by the halo exchange and have no skin check)
     const int rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;

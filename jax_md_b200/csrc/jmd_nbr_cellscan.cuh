@@ -11,25 +11,27 @@
 //                      once into the home cell's periodic image.  Home atoms are
 //                      broadcast from shared memory; one FSETP + one VOTE.BALLOT per
 //                      (chunk, home atom) yields the accept mask of that home atom over
-//                      the chunk.  The masks -- one bit per candidate test -- go to
-//                      `cs_bits`; row lengths (cnt, cnt_lower) and the occupancy
-//                      statistics are final after this kernel.  The reference's exact
-//                      arithmetic runs only for chunks that saw a candidate inside the
-//                      rounding band around cutoff^2 or a "dirty" cell.
+//                      the chunk; after the chunk every lane (= home atom) appends the
+//                      set bits of its mask to its row of the transposed internal list.
+//                      The reference's exact arithmetic runs only for chunks that saw a
+//                      candidate inside the rounding band around cutoff^2 or a "dirty"
+//                      cell.
 //   k_nbr_offsets      (sparse formats) exclusive scan of the per-atom entry counts in
 //                      atom-id order: single pass, decoupled look-back.
-//   k_nbr_cell_expand  expands the masks into rows staged in shared memory ([k][lane],
-//                      padded), then writes the internal transposed list coalesced and
-//                      the public idx (Dense rows / sparse segments at their offsets)
-//                      from the same staged rows; also stores the reference positions
-//                      and the error bits (partition.py:1066,1110).
+// The export to the public idx is jmd_neighbor.cu's tile-transposing ph_export.
+//
+// Measured on B200 (LJ, N = 1M, profiles/r02_*): the test kernel needs 0.47 warp
+// instructions per candidate test against 1.1 for the thread-per-atom scan.  Two
+// variants that kept the accept masks in global memory and expanded them in a second
+// kernel (rows staged in shared memory as 16-bit codes; a lock-step per-lane walk with
+// coalesced row stores) were measured at 0.73 ms and 1.05 ms for the expansion alone and
+// dropped.
 //
 // The candidate ORDER is the reference's, so `idx` stays element-exact.
 #pragma once
 
 constexpr int CS_WARPS = 4;                 // home cells per block
 enum { ST_LB_TILE = 9, ST_CS_TICKET = 10 }; // state[] slots used by the offsets scan / expand finalize
-enum { CS_ROWS = 1, CS_IDX = 2, CS_FINALIZE = 4 };
 
 template <typename T>
 struct CsWarpSmem {
@@ -146,7 +148,6 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_test(NbrP<T, DIM> P,
       __syncwarp();
       int k = 0, kl = 0;
       if (__any_sync(FULL, has_row)) {
-        unsigned* const gb = P.cs_bits + ((size_t)cell * P.cs_batches + batch) * ((size_t)P.cs_chunks * 32);
         for (int q = 0; q < nchunks; ++q) {
           const int t = q * 32 + lane;
           const bool valid = t < total;
@@ -222,9 +223,21 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_test(NbrP<T, DIM> P,
             if ((t_self >> 5) == q) m &= ~(1u << (t_self & 31));
           }
           if (!has_row) { m = 0u; ml = 0u; }
-          gb[q * 32 + lane] = m;
-          k += __popc(m);
           kl += __popc(ml);
+          if (P.count_only) {
+            k += __popc(m);
+          } else {
+            // append the accepted candidates to this lane's row (candidate order)
+            sm.rank[lane] = rank;
+            __syncwarp();
+            while (m) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1u;
+              if (k < P.m_int) P.nl[(size_t)k * P.n_pad + slot] = sm.rank[j];
+              ++k;
+            }
+            __syncwarp();
+          }
         }
       }
       if (lane < nh) {
@@ -299,177 +312,6 @@ __global__ void __launch_bounds__(NB) k_nbr_offsets(NbrP<T, DIM> P, int gated) {
   if (P.n == 0 && tile == 0 && threadIdx.x == 0) P.offsets[0] = 0;
 }
 
-// ---- expansion of the accept masks into rows + public idx ------------------------------
-// Lanes are home atoms.  Every lane walks ITS OWN accept masks (staged in shared memory)
-// one set bit per iteration, so iteration i yields entry i of every row at once: the
-// store into the transposed internal list nl[i][slot] is coalesced without any staging.
-// For the public idx 32 iterations are parked in a 32 x 33 tile, turned into atom ids by
-// independent perm gathers, and flushed row by row (coalesced along the row; Dense rows
-// directly, sparse segments through a ballot compaction at their offsets).
-constexpr int CS_OFF_BITS = 11;              // cells up to 2047 atoms (cell_capacity is checked on the host side)
-
-// per-warp dynamic shared memory of the expand kernel
-__host__ __device__ inline size_t cs_expand_warp_bytes(int cs_chunks) {
-  return (size_t)cs_chunks * 32 * sizeof(unsigned)             // masks   [chunk][lane]
-         + (size_t)cs_chunks * 32 * sizeof(unsigned short)     // codes   [stream position]
-         + (size_t)32 * 33 * sizeof(int);                      // id tile [iteration][lane]
-}
-
-template <typename T, int DIM>
-__global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_expand(NbrP<T, DIM> P, int gated, int flags) {
-  if (gate_closed(P.state, gated)) return;
-  constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) unsigned char cs_dyn[];
-  __shared__ CsWarpSmem<T> smem[CS_WARPS];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
-  CsWarpSmem<T>& sm = smem[w];
-  unsigned char* const mine = cs_dyn + (size_t)w * cs_expand_warp_bytes(P.cs_chunks);
-  unsigned* const bits_s = reinterpret_cast<unsigned*>(mine);
-  int* const tile = reinterpret_cast<int*>(mine + (size_t)P.cs_chunks * 32 * sizeof(unsigned));
-  unsigned short* const codes_s =
-      reinterpret_cast<unsigned short*>(mine + (size_t)P.cs_chunks * 32 * sizeof(unsigned) + 32 * 33 * sizeof(int));
-  const int cell = blockIdx.x * nwarps + w;
-  const bool rows = (flags & CS_ROWS) != 0;
-  const bool pub = (flags & CS_IDX) != 0 && !P.no_public_idx && P.idx != nullptr;
-  const bool fin = (flags & CS_FINALIZE) != 0;
-  const bool dense = P.format == JMD_DENSE;
-  const bool ordered = P.format == JMD_ORDERED_SPARSE;
-  const long long cap = P.max_occupancy;
-  int hs = 0, he = 0;
-  if (cell < P.n_cells) { hs = P.cell_start[cell]; he = P.cell_start[cell + 1]; }
-  if (he > hs) {
-    const int total = cs_setup<T, DIM>(P, cell, lane, sm);
-    __syncwarp();
-    const int nchunks = min((total + 31) >> 5, P.cs_chunks);
-    // codes of the whole candidate stream: stencil cell << 11 | position inside the cell
-    for (int q = 0; q < nchunks; ++q) {
-      const int t = q * 32 + lane;
-      const int s = cs_find(sm.pre, t < total ? t : 0);
-      const int off = max(0, min(t - sm.pre[s], (1 << CS_OFF_BITS) - 1));
-      codes_s[t] = (unsigned short)((s << CS_OFF_BITS) | off);
-    }
-    for (int hb = hs; hb < he; hb += 32) {
-      const int batch = (hb - hs) >> 5;
-      const int nh = min(32, he - hb);
-      const int slot = hb + lane;
-      int hid = 0x7fffffff, c_l = 0;
-      long long off_l = 0;
-      if (lane < nh) {
-        hid = P.perm[slot];
-        c_l = batch < P.cs_batches ? min(P.cnt[slot], P.m_int) : 0;
-        if (pub && !dense && hid < P.n) off_l = P.offsets[hid];
-        if (fin) {                           // partition.py:1128: reference_position = position
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) P.ref[(size_t)hid * DIM + d] = P.position[(size_t)hid * DIM + d];
-        }
-      }
-      if (batch >= P.cs_batches) continue;
-      int cmax = c_l;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-      // this batch's masks: coalesced global -> shared
-      const unsigned* const gb = P.cs_bits + ((size_t)cell * P.cs_batches + batch) * ((size_t)P.cs_chunks * 32);
-      __syncwarp();
-      if (cmax > 0) {
-#pragma unroll 4
-        for (int q = 0; q < nchunks; ++q) bits_s[q * 32 + lane] = __ldcs(gb + q * 32 + lane);
-      }
-      __syncwarp();
-      int q = -1;
-      unsigned m = 0u;
-      // Dense rows are written out to their full width (padding N), sparse ones to cmax
-      const int imax = (pub && dense) ? (int)cap : cmax;
-      for (int i0 = 0; i0 < imax; i0 += 32) {
-#pragma unroll 1
-        for (int ii = 0; ii < 32; ++ii) {
-          const int i = i0 + ii;
-          if (i < c_l) {
-            while (m == 0u && q + 1 < nchunks) { ++q; m = bits_s[q * 32 + lane]; }
-            const int j = m ? __ffs(m) - 1 : 0;
-            m &= m - 1u;
-            const unsigned code = codes_s[q * 32 + j];
-            const int rank = sm.cstart[code >> CS_OFF_BITS] + (int)(code & ((1u << CS_OFF_BITS) - 1u));
-            if (rows) P.nl[(size_t)i * P.n_pad + slot] = rank;       // coalesced over the lanes
-            tile[ii * 33 + lane] = rank;
-          }
-        }
-        if (pub) {
-          // slots -> atom ids, own column: independent gathers
-#pragma unroll 8
-          for (int ii = 0; ii < 32; ++ii)
-            if (i0 + ii < c_l) tile[ii * 33 + lane] = __ldg(&P.perm[tile[ii * 33 + lane]]);
-          __syncwarp();
-          const int kk = i0 + lane;
-          for (int h = 0; h < nh; ++h) {
-            const int a = __shfl_sync(FULL, hid, h);
-            const int c = __shfl_sync(FULL, c_l, h);
-            if (a >= P.n) continue;
-            if (dense) {
-              // Dense: idx[a, k] in candidate order, padded with N (partition.py:960-980, 1105)
-              const int v = kk < c ? tile[lane * 33 + h] : P.n;
-              if (kk < cap) P.idx[(size_t)a * cap + kk] = v;
-            } else {
-              // Sparse: idx[0] = receivers, idx[1] = senders, ordered by sender then
-              // candidate order; OrderedSparse keeps receiver id < sender id (:1010-1032)
-              if (i0 >= c) continue;
-              const long long pos0 = __shfl_sync(FULL, off_l, h);
-              const int v = kk < c ? tile[lane * 33 + h] : -1;
-              const bool keep = v >= 0 && (!ordered || v < a);
-              const unsigned b = __ballot_sync(FULL, keep);
-              const long long pos = pos0 + __popc(b & ((1u << lane) - 1u));
-              if (keep && pos < cap) { P.idx[pos] = v; P.idx[cap + pos] = a; }
-              if (lane == h) off_l += __popc(b);
-            }
-          }
-          __syncwarp();
-        }
-      }
-    }
-  }
-  if (pub && !dense) {
-    // pad the tail of the sparse arrays with N (partition.py:1024)
-    const long long start = P.offsets[P.n];
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long p = start + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < cap; p += stride) {
-      P.idx[p] = P.n;
-      P.idx[cap + p] = P.n;
-    }
-  }
-  // last block: error bits / counters (ph_finalize)
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long t = atomicAdd((unsigned long long*)&P.state[ST_CS_TICKET], 1ull);
-    if (t == (unsigned long long)gridDim.x - 1ull) {
-      P.state[ST_CS_TICKET] = 0;
-      if (fin) {
-        unsigned e = *P.error;
-        if (P.state[ST_MAX_CELL] > P.cell_capacity) e |= JMD_ERR_CELL_LIST_OVERFLOW;
-        const long long occ = dense ? P.state[ST_MAX_ROW] : P.state[ST_TOTAL];
-        if (occ > P.max_occupancy) e |= JMD_ERR_NEIGHBOR_LIST_OVERFLOW;
-        if (P.state[ST_MAX_ROW] > P.m_int) e |= JMD_ERR_NEIGHBOR_LIST_OVERFLOW;
-        *P.error = (uint8_t)e;
-        P.state[ST_BUILDS] += 1;
-        P.state[ST_EXPORT] = (P.lazy_idx && !P.no_public_idx) ? 1 : 0;
-      } else if (pub) {
-        P.state[ST_EXPORT] = 0;
-      }
-    }
-  }
-}
-
-// shared memory of one expand block, or 0 if it does not fit
-constexpr size_t CS_SMEM_MAX = 96 * 1024;
-template <typename T, int DIM>
-inline size_t cs_expand_smem(const NbrP<T, DIM>& P, int* warps) {
-  const size_t per_warp = cs_expand_warp_bytes(P.cs_chunks);
-  int nw = CS_WARPS;
-  while (nw > 1 && nw * per_warp > CS_SMEM_MAX) nw >>= 1;
-  *warps = nw;
-  return nw * per_warp <= CS_SMEM_MAX ? nw * per_warp : 0;
-}
-
 template <typename T, int DIM, int FMT, bool PERIODIC>
 void launch_cell_test_f(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   constexpr int MODE = (FMT == 0 && PERIODIC) ? 1 : 0;
@@ -493,25 +335,3 @@ void launch_cell_test(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   }
 }
 
-template <typename T, int DIM>
-int launch_cell_expand(const NbrP<T, DIM>& P, int gated, int flags, cudaStream_t stream) {
-  int nw = CS_WARPS;
-  const size_t bytes = cs_expand_smem(P, &nw);
-  if (bytes == 0) return JMD_EINVAL;
-  static int optin[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 64 || !optin[dev]) {
-    // the full shared-memory carve-out: residency is bounded by the staged rows
-    cudaFuncSetAttribute(k_nbr_cell_expand<T, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_MAX);
-    cudaFuncSetAttribute(k_nbr_cell_expand<T, DIM>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-    if (dev < 64) optin[dev] = 1;
-  }
-  const bool pub = (flags & CS_IDX) != 0 && !P.no_public_idx && P.idx != nullptr;
-  if (pub && P.format != JMD_DENSE)
-    k_nbr_offsets<T, DIM><<<(P.n + SCAN_TILE - 1) / SCAN_TILE + (P.n == 0 ? 1 : 0), NB, 0, stream>>>(P, gated);
-  const int grid = (P.n_cells + nw - 1) / nw;
-  k_nbr_cell_expand<T, DIM><<<grid, nw * 32, bytes, stream>>>(P, gated, flags);
-  return 0;
-}

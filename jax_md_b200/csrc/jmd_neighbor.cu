@@ -1173,6 +1173,38 @@ __global__ void __launch_bounds__(NB, JMD_EXPORT_MIN_BLOCKS) k_nbr_export(NbrP<T
   ph_export(P, sm);
 }
 
+// export + sparse tail padding + (fin) reference positions / error bits in one launch;
+// the last block to finish does the scalar part of ph_finalize
+template <typename T, int DIM>
+__global__ void __launch_bounds__(NB, JMD_EXPORT_MIN_BLOCKS) k_nbr_export_fin(NbrP<T, DIM> P, int gated, int fin) {
+  if (gate_closed(P.state, gated)) return;
+  __shared__ Smem sm;
+  ph_export(P, sm);
+  if (P.format != JMD_DENSE) ph_sparse_pad(P);
+  if (fin) {
+    const long long total = (long long)P.n * DIM;
+    for (long long i = gtid(); i < total; i += gthreads()) P.ref[i] = P.position[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd((unsigned long long*)&P.state[ST_CS_TICKET], 1ull);
+    if (t == (unsigned long long)gridDim.x - 1ull) {
+      P.state[ST_CS_TICKET] = 0;
+      if (fin) {
+        unsigned e = *P.error;
+        if (P.use_cells && P.state[ST_MAX_CELL] > P.cell_capacity) e |= JMD_ERR_CELL_LIST_OVERFLOW;
+        const long long occ = P.format == JMD_DENSE ? P.state[ST_MAX_ROW] : P.state[ST_TOTAL];
+        if (occ > P.max_occupancy) e |= JMD_ERR_NEIGHBOR_LIST_OVERFLOW;
+        if (P.state[ST_MAX_ROW] > P.m_int) e |= JMD_ERR_NEIGHBOR_LIST_OVERFLOW;
+        *P.error = (uint8_t)e;
+        P.state[ST_BUILDS] += 1;
+      }
+      P.state[ST_EXPORT] = 0;
+    }
+  }
+}
+
 #define LAUNCH(PH, grid) k_phase<T, DIM, PH><<<(grid), NB, 0, stream>>>(P, gated)
 
 template <typename T, int DIM>
@@ -1203,12 +1235,12 @@ void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 template <typename T, int DIM>
 void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   const int G = JMD_SM_COUNT * 8;
-  if (P.cellscan) {
-    // the rows are expanded from the accept masks here, together with the public idx
-    int flags = CS_ROWS | CS_IDX | CS_FINALIZE;
-    if (P.no_public_idx || (P.lazy_idx && gated == 1)) flags = CS_ROWS | CS_FINALIZE;
-    else if (gated == 2) flags = CS_IDX;
-    launch_cell_expand<T, DIM>(P, gated, flags, stream);
+  if (P.cellscan && !(P.no_public_idx || (P.lazy_idx && gated == 1))) {
+    // cell-scan lists: look-back offsets + one export kernel that also pads the sparse
+    // tail, stores the reference positions and sets the error bits (no grid barrier)
+    if (P.format != JMD_DENSE)
+      k_nbr_offsets<T, DIM><<<(P.n + SCAN_TILE - 1) / SCAN_TILE + (P.n == 0 ? 1 : 0), NB, 0, stream>>>(P, gated);
+    k_nbr_export_fin<T, DIM><<<grid_for((long long)P.n, NB, 1 << 30), NB, 0, stream>>>(P, gated, gated == 2 ? 0 : 1);
     return;
   }
   // lazy materialisation: an update() only stores the reference positions and the
@@ -1387,9 +1419,8 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   // the stencil scan addresses nl with 32-bit element offsets
   if ((unsigned long long)nb->m_int * (unsigned long long)nb->n_pad >= (1ull << 32)) return JMD_EINVAL;
   // warp-per-cell scan: reference grid in the reference's storage order only
-  if (nb->cell_scan && nb->use_cells && P.bs == 0 && P.sw == 1 && P.rotate && !P.staged && P.cs_bits && P.cs_lb &&
-      P.cs_chunks > 0 && P.cs_batches > 0 && nb->cell_capacity < (1 << CS_OFF_BITS) &&
-      cs_expand_warp_bytes(P.cs_chunks) <= CS_SMEM_MAX)
+  if (nb->cell_scan && nb->use_cells && P.bs == 0 && P.sw == 1 && P.rotate && !P.staged && P.cs_lb &&
+      P.cs_chunks > 0 && P.cs_batches > 0)
     P.cellscan = 1;
   P.count_only = 0;
   P.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;

@@ -95,6 +95,7 @@ struct PairP {
   // shared-memory staging (jmd_common.cuh)
   const unsigned short* nl16;
   const int* blk_table;
+  const int* n_dev;         // {n, n_rows} on the device (domain decomposition), or NULL
 };
 
 // read-only (non-coherent) 16/32-byte position gathers
@@ -277,6 +278,7 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
 #endif
   constexpr bool WANT_E = RED == 2;
   constexpr int NV = RedN<RED>::value;
+  if (Q.n_dev) { Q.n = Q.n_dev[0]; Q.n_rows = Q.n_dev[1]; }
   const int t = blockIdx.x * PAIR_BLOCK + threadIdx.x;
   double rv[NV];
 #pragma unroll
@@ -677,6 +679,7 @@ int JMD_PAIR_LAUNCHER(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, vo
   Q.dt_dev = (const T*)dt_dev;
   Q.idx = nullptr; Q.idx_m = 0; Q.position = nullptr; Q.species = nullptr;
   Q.nl16 = nb->nl16; Q.blk_table = nb->blk_table;
+  Q.n_dev = nb->n_dev;
   const bool kick = momentum != nullptr;
   if ((kick || want_e) && (!red || !partials)) return JMD_EINVAL;
   if (kick && !mass) return JMD_EINVAL;

@@ -1,6 +1,5 @@
 """Slab domain decomposition of the short-range MD step over the GPUs of one
-node.  One process per GPU, `torch.distributed` (NCCL over
-NVLink; gloo with host staging for tests).
+node.  One process per GPU.
 
 The reference has no API for this (its only multi-device code is the TPU voxel
 prototype, jax_md/tpu.py:481-525,1498-1555), so this module is additive.  The
@@ -10,16 +9,26 @@ so the same neighbour-list and force kernels run on it; rows, forces and skin
 checks exist for owned atoms only (`jmd_nbr_t.n_rows`), hence no reverse
 (force) communication.
 
-Per step (host-orchestrated, one host read per step for the global decision):
-  1. skin predicate on owned atoms  -> all-reduce(MAX) of the rebuild flag
-  2. if rebuild: migrate atoms that left the slab (ring send/recv), re-select
-     the face atoms, exchange ghost positions, rebuild the local neighbour list
-  3. kick + drift of owned atoms (jmd_nve_kick_drift)
-  4. halo: gather-pack face positions (jmd_dd_pack) -> send/recv -> ghosts
-  5. fused force + second half kick over owned rows (jmd_pair_force)
+A step is FOUR kernels and no host work besides one CUDA-graph launch:
+  jmd_nve_kick_drift   half kick + drift of the owned atoms; leaves the skin flags
+  jmd_dd_comm_push     gathers the face atoms and stores them straight into the ring
+                       neighbours' landing rows through CUDA-IPC peer mappings (NVLink),
+                       releases their signal words; broadcasts this rank's rebuild flag
+  jmd_dd_comm_wait     waits for both neighbours' rows, copies them behind the owned atoms
+                       and into the cell-sorted float4 array; ORs all ranks' flags and
+                       publishes the global decision to a mapped host word
+  jmd_pair_force       forces on the owned rows + second half kick
+All counts the kernels need live on the device (`jmd_nbr_t.n_dev`, `info`), so the
+captured graph stays valid across rebuilds.  The host polls the decision word while the
+force kernel is still running; only a rebuild (every ~8 steps) is host-driven:
+atom migration and ghost re-selection (ordered select kernels, fixed-capacity messages
+that carry their counts, `torch.distributed` send/recv), one host read of the new
+counts, then the local neighbour-list rebuild.
 """
 import contextlib
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -158,7 +167,8 @@ class SlabDomain:
   function (`smap.PairNeighborListFn`) built with the GLOBAL periodic space."""
 
   def __init__(self, box, energy_fn, r_cutoff, dr_threshold, dt, comm=None,
-               axis=0, mass=1.0, capacity_factor=1.3, capacity_multiplier=1.25):
+               axis=0, mass=1.0, capacity_factor=1.3, capacity_multiplier=1.25,
+               transport=None, use_graph=True):
     _lib.require_cuda()
     self.comm = comm or RingComm()
     self.box = np.asarray(box, np.float64).reshape(-1)
@@ -186,6 +196,20 @@ class SlabDomain:
     self.nbrs = None
     self.rebuilds = 0
     self._lists = None
+    # the halo carries positions only: per-atom species / parameters would need their own
+    # exchange: refuse them instead of silently treating ghosts as species 0
+    if getattr(energy_fn, 'species', None) is not None:
+      raise NotImplementedError('SlabDomain: energy functions with species are not supported')
+    for k, v in getattr(energy_fn, 'kwargs', {}).items():
+      if isinstance(v, (torch.Tensor, np.ndarray)) and getattr(v, 'ndim', 0) > 0:
+        raise NotImplementedError(f'SlabDomain: per-atom / table parameter {k!r} is not supported')
+    self.transport = transport or os.environ.get('JMD_DD_TRANSPORT', 'p2p')
+    self.use_graph = use_graph and os.environ.get('JMD_DD_GRAPH', '1') != '0'
+    self._graph = None
+    self._epoch = 0
+    self._pending = None
+    self._peer = None
+    self._warm = 0
 
   # -- setup ------------------------------------------------------------------------
   def init(self, R_own, P_own, gid_own=None):
@@ -228,6 +252,7 @@ class SlabDomain:
     self.info = torch.zeros(_lib.DD_INFO_COUNT, **i32)
     self.info_host = torch.zeros(_lib.DD_INFO_COUNT, dtype=torch.int32).pin_memory()
     self.mig_scratch = torch.empty(6 * self.cap_mig, **i32)
+    self.sel_scratch = torch.zeros(self.cap // 2048 + 4, dtype=torch.int64, device=dev)
     t = dict(dtype=dt, device=dev)
     self.mig_pay = [torch.zeros((self.cap_mig, 3 * self.dim), **t) for _ in range(4)]     # out l, r; in l, r
     self.mig_gid = [torch.zeros(self.cap_mig + 1, dtype=torch.int64, device=dev) for _ in range(4)]
@@ -241,22 +266,102 @@ class SlabDomain:
     self._side_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
     self._decision_pending = False
     self._rebuild(st, first=True)
+    if self.transport == 'p2p':
+      self._setup_peers(st)
     self._force(st, kick=False)
     return st
 
+  # -- peer-memory exchange (CUDA IPC) --------------------------------------------------
+  def _setup_peers(self, st):
+    """One shared block per rank: landing rows [2 parities][2 sides][cap_list][dim], two
+    signal words, one flag word per rank.  Handles go round with all_gather_object; the
+    neighbours' blocks are mapped with cudaIpcOpenMemHandle (NVLink peer access)."""
+    W, r = self.comm.world, self.comm.rank
+    item = 4 if self.dtype == torch.float32 else 8
+    land_bytes = 2 * 2 * self.cap_list * self.dim * item
+    land_bytes = (land_bytes + 255) // 256 * 256
+    total = land_bytes + 256 + 2 * 8 * max(W, 32)
+    ptr = C.c_void_p()
+    handle = (C.c_uint8 * 64)()
+    _lib.call('jmd_p2p_alloc', total, C.byref(ptr), handle)
+    base = ptr.value
+    handles = [None] * W
+    if W > 1:
+      dist.all_gather_object(handles, bytes(handle), group=self.comm.group)
+    else:
+      handles[0] = bytes(handle)
+    mapped = {r: base}
+
+    def peer(rank):
+      if rank not in mapped:
+        q = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handles[rank])
+        _lib.call('jmd_p2p_open', buf, C.byref(q))
+        mapped[rank] = q.value
+      return mapped[rank]
+    flags_ptrs = torch.tensor([peer(k) + land_bytes + 256 for k in range(W)], dtype=torch.int64,
+                              device=self.device)
+    host = C.c_void_p()
+    hdev = C.c_void_p()
+    _lib.call('jmd_host_flag_alloc', C.byref(host), C.byref(hdev))
+    self._host_flag = C.c_uint64.from_address(host.value)
+    ws = self.nbrs._ws
+    dd = _lib.DdT()
+    dd.dtype, dd.dim, dd.rank, dd.world = self.dtc, self.dim, r, W
+    dd.cap_list = self.cap_list
+    dd.always_rebuild = int(ws.c.always_rebuild)
+    dd.face_l, dd.face_r = self.list_a.data_ptr(), self.list_b.data_ptr()
+    dd.face_counts = self.counters.data_ptr()
+    dd.info = self.info.data_ptr()
+    self._epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+    self._ticket = torch.zeros(2, dtype=torch.int32, device=self.device)
+    dd.epoch, dd.ticket = self._epoch_dev.data_ptr(), self._ticket.data_ptr()
+    dd.skin_blk = ws.t['skin_blk'].data_ptr()
+    dd.land, dd.signal, dd.flags = base, base + land_bytes, base + land_bytes + 256
+    left, right = peer(self.comm.left), peer(self.comm.right)
+    dd.peer_land_l, dd.peer_land_r = left, right
+    dd.peer_signal_l, dd.peer_signal_r = left + land_bytes, right + land_bytes
+    dd.peer_flags = flags_ptrs.data_ptr()
+    dd.host_flag = hdev.value
+    self._peer = dict(dd=dd, base=base, mapped=mapped, flags_ptrs=flags_ptrs, host=host.value)
+    # the step kernels take their counts from the device ({N_LOC, N_ROWS} of `info`); the
+    # descriptor they get carries the CAPACITY as n, so their grids never change and one
+    # captured graph serves every rebuild
+    nb = _lib.NbrT.from_buffer_copy(ws.c)
+    nb.n = self.cap
+    nb.n_rows = 0
+    nb.n_dev = self.info.data_ptr() + 4 * _lib.DD_N_LOC
+    self._nb_step = nb
+    self._epoch = 0
+    if W > 1:
+      dist.barrier(group=self.comm.group)      # every block is mapped before the first push
+
+  def close(self):
+    """Unmaps the peers' blocks and frees this rank's (call on every rank)."""
+    if self._peer is None:
+      return
+    torch.cuda.synchronize()
+    if self.comm.world > 1:
+      dist.barrier(group=self.comm.group)
+    for rank, q in self._peer['mapped'].items():
+      if rank != self.comm.rank:
+        _lib.call('jmd_p2p_close', C.c_void_p(q))
+    if self.comm.world > 1:
+      dist.barrier(group=self.comm.group)
+    _lib.call('jmd_p2p_free', C.c_void_p(self._peer['base']))
+    _lib.call('jmd_host_flag_free', C.c_void_p(self._peer['host']))
+    self._peer = None
+    self._graph = None
+
   # -- pieces -----------------------------------------------------------------------
   def _select(self, st, thr_a, thr_b, list_a, list_b, counters):
-    """Sorted int32 indices of owned atoms with d < thr_a / d >= thr_b into the
-    fixed-capacity lists (padding: INT32_MAX); counts stay on the device."""
-    counters.zero_()
-    list_a.fill_(_INT_MAX)
-    list_b.fill_(_INT_MAX)
-    _lib.call('jmd_dd_select', self.dtc, self.dim, self.cap, _lib.ptr(self.info), _lib.ptr(st.R),
+    """Ascending int32 indices of owned atoms with d < thr_a / d >= thr_b into the
+    fixed-capacity lists; counts stay on the device.  One ordered-select kernel
+    (look-back scan): the atom order, hence the summation order, is reproducible."""
+    _lib.call('jmd_dd_select_ordered', self.dtc, self.dim, self.cap, _lib.ptr(self.info), _lib.ptr(st.R),
               self.axis, float(self.lo), float(self.box[self.axis]), float(thr_a), float(thr_b),
-              _lib.ptr(list_a), _lib.ptr(list_b), _lib.ptr(counters), list_a.numel(), _lib.stream())
-    # sorted lists make the atom order (hence the summation order) reproducible
-    list_a.copy_(torch.sort(list_a).values)
-    list_b.copy_(torch.sort(list_b).values)
+              _lib.ptr(list_a), _lib.ptr(list_b), _lib.ptr(counters), list_a.numel(),
+              _lib.ptr(self.sel_scratch), _lib.stream())
 
   def _migrate(self, st):
     """Atoms that left [lo, lo + width) move to the neighbouring rank (device
@@ -295,6 +400,8 @@ class SlabDomain:
       raise RuntimeError('domain decomposition list capacity exceeded')
     if info[_lib.DD_ERROR] & _lib.DD_ECAP:
       raise RuntimeError('slab capacity exceeded; raise capacity_factor')
+    if info[_lib.DD_ERROR] & _lib.DD_ETIMEOUT:
+      raise RuntimeError('a neighbour rank\'s halo or rebuild flag never arrived (peer exchange timed out)')
     st.n_own = info[_lib.DD_N_OWN]
     n_from_l, n_from_r = info[_lib.DD_FROM_L], info[_lib.DD_FROM_R]
     st.n_ghost = n_from_l + n_from_r
@@ -334,10 +441,17 @@ class SlabDomain:
       st.n_ghost = 0
       self._lists = None
     n_loc = st.n_own + st.n_ghost
+    if self.comm.world == 1:
+      # no ghost exchange ran: publish the counts the step kernels read
+      self.info[_lib.DD_N_OWN] = st.n_own
+      self.info[_lib.DD_N_LOC] = n_loc
+      self.info[_lib.DD_N_ROWS] = st.n_own
+      self.info[_lib.DD_FROM_L] = 0
+      self.info[_lib.DD_FROM_R] = 0
+      self.counters.zero_()
     Rl = st.R[:n_loc]
     if self.nbrs is None:
-      self.nbrs = self.neighbor_fn.allocate(Rl, n_capacity=self.cap, n_rows=st.n_own,
-                                            no_public_idx=True)
+      self._allocate(st, Rl)
     else:
       ws = self.nbrs._ws
       ws.c.n, ws.c.n_rows = n_loc, st.n_own
@@ -346,7 +460,35 @@ class SlabDomain:
       _lib.call('jmd_nbr_bin', ws.ref(), pp, 0, s)
       _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 0, s)
       _lib.call('jmd_nbr_export', ws.ref(), pp, 0, s)
+      # capacity overflow of the local list (density drifts through migration): caught at
+      # the NEXT rebuild's host read (`_ghosts`), see _check_list
     self.rebuilds += 1
+
+  def _allocate(self, st, Rl, extra=0):
+    self.nbrs = self.neighbor_fn.allocate(Rl, extra_capacity=extra, n_capacity=self.cap,
+                                          n_rows=st.n_own, no_public_idx=True)
+    self._graph = None
+    if self._peer is not None:
+      ws = self.nbrs._ws
+      nb = _lib.NbrT.from_buffer_copy(ws.c)
+      nb.n, nb.n_rows = self.cap, 0
+      nb.n_dev = self.info.data_ptr() + 4 * _lib.DD_N_LOC
+      self._nb_step = nb
+      self._peer['dd'].skin_blk = ws.t['skin_blk'].data_ptr()
+
+  def check_list(self, st):
+    """Host check of the local neighbour list's error bits (one sync): on overflow the
+    list is re-allocated with more head-room from the current positions and the step
+    graph is captured again.  Called from the bench / user loop every block of steps,
+    like the reference's `did_buffer_overflow` check (partition.py:840-854)."""
+    code = int(self.nbrs.error.code)
+    if code & 3:
+      n_loc = st.n_own + st.n_ghost
+      self._extra = getattr(self, '_extra', 0) + 8
+      self._allocate(st, st.R[:n_loc], extra=self._extra)
+      self._force(st, kick=False)
+      return True
+    return False
 
   def _force(self, st, kick):
     ws = self.nbrs._ws
@@ -360,6 +502,69 @@ class SlabDomain:
               self.dt_2, None, 0, _lib.stream())
 
   # -- the step ---------------------------------------------------------------------
+  def _step_kernels(self, st):
+    """drift -> push (halo + flag) -> wait (unpack + decision) -> force; device-side
+    counts only, capturable."""
+    s = _lib.stream()
+    nb = C.byref(self._nb_step)
+    dd = C.byref(self._peer['dd'])
+    _lib.call('jmd_nve_kick_drift', C.byref(self.sp), self.dtc, self.cap, nb,
+              _lib.ptr(st.R), _lib.ptr(st.P), _lib.ptr(st.F), _lib.ptr(self.mass), 0,
+              self.dt, None, None, _lib.ptr(st.R), _lib.ptr(st.P), s)
+    _lib.call('jmd_dd_comm_push', dd, _lib.ptr(st.R), s)
+    _lib.call('jmd_dd_comm_wait', dd, nb, _lib.ptr(st.R), s)
+    fn = self.energy_fn
+    _, species, params = fn._resolve(self.nbrs, {})
+    pt, keep, _ = fn._pair_struct(st.R, species, params, False)
+    _lib.call('jmd_pair_force', nb, C.byref(pt), _lib.ptr(st.F), None,
+              _lib.ptr(self.red), None, _lib.ptr(self.partials), _lib.ptr(st.P),
+              _lib.ptr(self.mass), 0, self.dt_2, None, 0, s)
+
+  def _poll(self, epoch, timeout=20.0):
+    """Global rebuild decision of step `epoch` from the mapped host word (written by
+    jmd_dd_comm_wait, i.e. BEFORE that step's force kernel runs)."""
+    t0 = time.perf_counter()
+    flag = self._host_flag
+    while True:
+      v = flag.value
+      if (v >> 1) >= epoch:
+        return bool(v & 1)
+      if time.perf_counter() - t0 > timeout:
+        raise RuntimeError(f'domain decomposition: no decision for step {epoch} '
+                           f'(host word {v}); a peer rank stalled?')
+
+  def _step_p2p(self, st):
+    # NeighborList.update semantics (partition.py:1146) with a GLOBAL decision taken on
+    # the positions the last step produced
+    if self._pending is None and self._epoch > 0:
+      self._pending = self._poll(self._epoch)
+    if self._pending:
+      self._rebuild(st)
+    self._pending = None
+    if self.use_graph and self.device.type == 'cuda' and self._warm >= 2:
+      if self._graph is None:
+        self._capture(st)
+      self._graph.replay()
+    else:
+      self._step_kernels(st)      # the first steps run eagerly (lazy kernel loading
+      self._warm += 1             # must not happen inside a capture)
+    self._epoch += 1
+    return st
+
+  def _capture(self, st):
+    """Captures the four step kernels once; every count they need is device-resident,
+    so the graph survives rebuilds (it is dropped only when the list is re-allocated)."""
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      self._step_kernels(st)
+    self._graph = g
+
+  def step(self, st):
+    if self._peer is not None:
+      return self._step_p2p(st)
+    return self._step_nccl(st)
+
   def _launch_decision(self, st):
     """Skin predicate on the CURRENT owned positions -> global OR -> pinned host
     flag (asynchronously).  Enqueued right after the drift, i.e. before the halo
@@ -409,25 +614,21 @@ class SlabDomain:
       torch.cuda.current_stream().wait_stream(self._side_stream)
     return bool(int(self._flag_host[0]) != 0)
 
-  def step(self, st):
+  def _step_nccl(self, st):
+    """Host-orchestrated fallback (transport='nccl'; gloo staging for tests): one host
+    decision per step, torch.distributed halo exchange."""
     s = _lib.stream()
-    # 1-2. NeighborList.update semantics (partition.py:1146) with a GLOBAL decision
-    #      (predicate evaluated on these same positions at the end of the last step)
     if self._take_decision(st):
       self._rebuild(st)
     ws = self.nbrs._ws
-    # 3. first half kick + drift of owned atoms (in place on the capacity arrays)
     _lib.call('jmd_nve_kick_drift', C.byref(self.sp), self.dtc, st.n_own, ws.ref(),
               _lib.ptr(st.R), _lib.ptr(st.P), _lib.ptr(st.F), _lib.ptr(self.mass), 0,
               self.dt, None, None, _lib.ptr(st.R), _lib.ptr(st.P), s)
-    #    the next step's rebuild decision, overlapped with steps 4-5
     self._drift_flags = True
     self._launch_decision(st)
-    # 4. halo exchange of the drifted face atoms, refresh the sorted ghost copies
     if st.n_ghost:
       self._halo(st)
       _lib.call('jmd_nbr_pack_range', ws.ref(), _lib.ptr(st.R), st.n_own, st.n_ghost, s)
-    # 5. forces on owned atoms + second half kick
     self._force(st, kick=True)
     return st
 

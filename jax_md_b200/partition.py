@@ -272,10 +272,6 @@ def _enable_cell_scan(ws, cl_capacity, static_kwargs):
     return
   c.cs_batches = -(-max(cl_capacity, 1) // 32)
   c.cs_chunks = -(-(3 ** ws.dim) * max(cl_capacity, 1) // 32)
-  words = ws.n_cells_ref * c.cs_batches * c.cs_chunks * 32
-  if words * 4 > 8 << 30:
-    return
-  ws.buf('cs_bits', (max(words, 1),), torch.int32)
   ws.buf('cs_lb', (ws.n_capacity // 2048 + 4,), torch.int64, 0)
   c.cell_scan = 1
 
