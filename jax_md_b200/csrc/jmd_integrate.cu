@@ -44,8 +44,9 @@ template <typename T, int DIM>
 __global__ void __launch_bounds__(IB) k_kick_drift(StepP<T, DIM> S) {
   const int a = blockIdx.x * IB + threadIdx.x;
   bool moved = false;
-  if (S.n_dev) { S.n = S.n_dev[1]; S.n_rows = S.n_dev[1]; }
-  if (a < S.n) {
+  const int s_n = S.n_dev ? __ldg(S.n_dev + 1) : S.n;          // (no writes to the parameter struct)
+  const int s_rows = S.n_dev ? s_n : S.n_rows;
+  if (a < s_n) {
     T dt = S.dt, dt_2 = S.dt_2;
     if (S.dt_dev) {
       dt = (T)(float)(*S.dt_dev);
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(IB) k_kick_drift(StepP<T, DIM> S) {
       T w = S.species ? (T)S.species[a] : T(0);
       S.pos_sorted[S.inv_perm[a]] = mk4<T>(r[0], r[1], r[2], w);
     }
-    if (S.skin_blk && a < S.n_rows) {
+    if (S.skin_blk && a < s_rows) {
       // the next NeighborList.update(R') asks: did any atom move further than skin/2
       // from its reference position (strict >, min-image metric, exact arithmetic)?
       T b[DIM];

@@ -42,7 +42,6 @@ struct CsWarpSmem {
   typename Vec4<T>::type home[32];   // home atoms of the current batch: x y z id
   uint2 bits[32];     // .x accept mask of home atom h over the current chunk; .y the same
                       // restricted to candidates with a smaller atom id (OrderedSparse)
-  int rank[32];       // (expand) slot of the chunk's candidate j
 };
 
 __device__ __forceinline__ int id_of(float w) { return __float_as_int(w); }
@@ -107,8 +106,11 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_test(NbrP<T, DIM> P,
   constexpr int NS = DIM == 3 ? 27 : 9;
   constexpr unsigned FULL = 0xffffffffu;
   __shared__ CsWarpSmem<T> smem[CS_WARPS];
+  extern __shared__ unsigned cs_dyn[];       // per warp: masks [cs_chunks + 1][32] | ranks [cs_chunks][32]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   CsWarpSmem<T>& sm = smem[w];
+  unsigned* const masks_s = cs_dyn + (size_t)w * (2 * P.cs_chunks + 1) * 32;
+  int* const ranks_s = reinterpret_cast<int*>(masks_s + (size_t)(P.cs_chunks + 1) * 32);
   const int cell = blockIdx.x * CS_WARPS + w;
   // the offsets scan of this rebuild starts from cleared look-back words
   {
@@ -224,20 +226,37 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_test(NbrP<T, DIM> P,
           }
           if (!has_row) { m = 0u; ml = 0u; }
           kl += __popc(ml);
-          if (P.count_only) {
-            k += __popc(m);
-          } else {
-            // append the accepted candidates to this lane's row (candidate order)
-            sm.rank[lane] = rank;
-            __syncwarp();
-            while (m) {
-              const int j = __ffs(m) - 1;
-              m &= m - 1u;
-              if (k < P.m_int) P.nl[(size_t)k * P.n_pad + slot] = sm.rank[j];
-              ++k;
-            }
-            __syncwarp();
+          k += __popc(m);
+          if (!P.count_only) {                 // parked for the row walk below
+            masks_s[q * 32 + lane] = m;
+            ranks_s[q * 32 + lane] = rank;
           }
+        }
+        if (!P.count_only) {
+          // Row walk: every lane (= home atom) pops ONE accepted candidate of its own masks
+          // per iteration, so iteration i yields entry i of every row at once and the store
+          // into the transposed list nl[i][slot] is coalesced over the lanes.  A sentinel
+          // word of ones behind the last chunk ends the search for the next non-empty mask.
+          masks_s[nchunks * 32 + lane] = 0xffffffffu;
+          __syncwarp();
+          const int c_l = min(k, P.m_int);
+          int cmax = c_l;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+          int wq = 0;
+          unsigned wm = masks_s[lane];
+          int* dst = P.nl + slot;
+#pragma unroll 1
+          for (int i = 0; i < cmax; ++i) {
+            if (i < c_l) {
+              while (wm == 0u) wm = masks_s[(++wq) * 32 + lane];
+              const int j = __ffs(wm) - 1;
+              wm &= wm - 1u;
+              *dst = ranks_s[wq * 32 + j];
+            }
+            dst += P.n_pad;
+          }
+          __syncwarp();
         }
       }
       if (lane < nh) {
@@ -312,14 +331,29 @@ __global__ void __launch_bounds__(NB) k_nbr_offsets(NbrP<T, DIM> P, int gated) {
   if (P.n == 0 && tile == 0 && threadIdx.x == 0) P.offsets[0] = 0;
 }
 
+// dynamic shared memory of one test block: per warp the parked masks (+ sentinel) and slots
+constexpr size_t CS_SMEM_MAX = 160 * 1024;
+inline size_t cs_test_smem(int cs_chunks) { return (size_t)CS_WARPS * (2 * cs_chunks + 1) * 32 * sizeof(unsigned); }
+
 template <typename T, int DIM, int FMT, bool PERIODIC>
 void launch_cell_test_f(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   constexpr int MODE = (FMT == 0 && PERIODIC) ? 1 : 0;
   const int grid = (P.n_cells + CS_WARPS - 1) / CS_WARPS;
+  const size_t bytes = cs_test_smem(P.cs_chunks);
+  static int optin[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes > 48 * 1024 && (dev >= 64 || !optin[dev])) {
+    cudaFuncSetAttribute(k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, PERIODIC>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_MAX);
+    cudaFuncSetAttribute(k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_MAX);
+    if (dev < 64) optin[dev] = 1;
+  }
   if (PERIODIC && P.filter)
-    k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, PERIODIC><<<grid, CS_WARPS * 32, 0, stream>>>(P, gated);
+    k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, PERIODIC><<<grid, CS_WARPS * 32, bytes, stream>>>(P, gated);
   else
-    k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, false><<<grid, CS_WARPS * 32, 0, stream>>>(P, gated);
+    k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, false><<<grid, CS_WARPS * 32, bytes, stream>>>(P, gated);
 }
 
 template <typename T, int DIM>

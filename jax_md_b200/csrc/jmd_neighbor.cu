@@ -1420,7 +1420,7 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   if ((unsigned long long)nb->m_int * (unsigned long long)nb->n_pad >= (1ull << 32)) return JMD_EINVAL;
   // warp-per-cell scan: reference grid in the reference's storage order only
   if (nb->cell_scan && nb->use_cells && P.bs == 0 && P.sw == 1 && P.rotate && !P.staged && P.cs_lb &&
-      P.cs_chunks > 0 && P.cs_batches > 0)
+      P.cs_chunks > 0 && P.cs_batches > 0 && cs_test_smem(P.cs_chunks) <= CS_SMEM_MAX)
     P.cellscan = 1;
   P.count_only = 0;
   P.n_rows = (nb->n_rows > 0 && nb->n_rows < nb->n) ? nb->n_rows : nb->n;

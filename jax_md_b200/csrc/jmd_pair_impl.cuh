@@ -278,14 +278,16 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
 #endif
   constexpr bool WANT_E = RED == 2;
   constexpr int NV = RedN<RED>::value;
-  if (Q.n_dev) { Q.n = Q.n_dev[0]; Q.n_rows = Q.n_dev[1]; }
+  // (never write to the parameter struct: that would move all of it to local memory)
+  const int q_n = Q.n_dev ? __ldg(Q.n_dev) : Q.n;
+  const int q_rows = Q.n_dev ? __ldg(Q.n_dev + 1) : Q.n_rows;
   const int t = blockIdx.x * PAIR_BLOCK + threadIdx.x;
   double rv[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) rv[i] = 0.0;
 
-  const int ai = t < Q.n ? Q.perm[t] : 0x7fffffff;
-  const bool valid = ai < Q.n_rows;         // ghosts (ids >= n_rows) have no row
+  const int ai = t < q_n ? Q.perm[t] : 0x7fffffff;
+  const bool valid = ai < q_rows;           // ghosts (ids >= n_rows) have no row
   {
     const V4 pi = valid ? Q.pos_sorted[t] : V4();
     const int cnt = valid ? min(Q.cnt[t], Q.m_int) : 0;

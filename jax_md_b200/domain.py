@@ -271,6 +271,25 @@ class SlabDomain:
     self._force(st, kick=False)
     return st
 
+  def reset(self, st, R_own, P_own, gid_own=None):
+    """Loads a new local state into the initialised domain (buffers, peer mappings and
+    the captured step graph are kept): rebuild + first force evaluation."""
+    n = R_own.shape[0]
+    if n > self.cap:
+      raise ValueError('state larger than the slab capacity')
+    st.R[:n] = R_own
+    st.P[:n] = P_own
+    st.gid[:n] = gid_own if gid_own is not None else torch.arange(n, device=st.R.device)
+    st.n_own, st.n_ghost = n, 0
+    self.info.zero_()
+    self.info[_lib.DD_N_OWN] = n
+    if self._peer is not None and self._epoch > 0 and self._pending is None:
+      self._poll(self._epoch)                 # the last step's decision is moot: rebuild anyway
+    self._pending = None
+    self._rebuild(st)
+    self._force(st, kick=False)
+    return st
+
   # -- peer-memory exchange (CUDA IPC) --------------------------------------------------
   def _setup_peers(self, st):
     """One shared block per rank: landing rows [2 parities][2 sides][cap_list][dim], two
@@ -709,6 +728,7 @@ def bench_domain(args, world, rank, dev):
   dist.all_reduce(n_ghost, op=dist.ReduceOp.MAX)
   ke = dom.kinetic_energy()
   rebuilds_timed = dom.rebuilds - r0
+  dom_graph, dom_transport = bool(dom._graph is not None), ('p2p' if dom._peer is not None else 'nccl')
 
   # ---- dominant kernel (fused force + half kick) timed inside 20 more steps -------
   ws = dom.nbrs._ws
@@ -725,42 +745,69 @@ def bench_domain(args, world, rank, dev):
     evs.append((a, b))
 
   dom._force = timed_force
+  graph_was, dom.use_graph = dom.use_graph, False        # (eager steps: the force launch is timed alone)
+  if dom._peer is not None:
+    real_kernels = dom._step_kernels
+
+    def timed_kernels(state):
+      # same four kernels, with events around the force launch
+      s_ = _lib.stream()
+      nb = C.byref(dom._nb_step)
+      dd = C.byref(dom._peer['dd'])
+      _lib.call('jmd_nve_kick_drift', C.byref(dom.sp), dom.dtc, dom.cap, nb, _lib.ptr(state.R), _lib.ptr(state.P),
+                _lib.ptr(state.F), _lib.ptr(dom.mass), 0, dom.dt, None, None, _lib.ptr(state.R), _lib.ptr(state.P), s_)
+      _lib.call('jmd_dd_comm_push', dd, _lib.ptr(state.R), s_)
+      _lib.call('jmd_dd_comm_wait', dd, nb, _lib.ptr(state.R), s_)
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      fn = dom.energy_fn
+      _, species, params = fn._resolve(dom.nbrs, {})
+      pt, keep, _ = fn._pair_struct(state.R, species, params, False)
+      _lib.call('jmd_pair_force', nb, C.byref(pt), _lib.ptr(state.F), None, _lib.ptr(dom.red), None,
+                _lib.ptr(dom.partials), _lib.ptr(state.P), _lib.ptr(dom.mass), 0, dom.dt_2, None, 0, s_)
+      b.record()
+      evs.append((a, b))
+    dom._step_kernels = timed_kernels
   for _ in range(20):
     st = dom.step(st)
   torch.cuda.synchronize()
   dom._force = plain_force
+  dom.use_graph = graph_was
+  if dom._peer is not None:
+    dom._step_kernels = real_kernels
   k_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in evs[3:]]))],
                       dtype=torch.float64, device=dev)
   dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
   kb = torch.tensor([kernel_bytes], dtype=torch.int64, device=dev)
   dist.all_reduce(kb, op=dist.ReduceOp.MAX)
 
-  # ---- end to end: pinned host state -> H2D -> init (first build) -> steps -> D2H ---
+  # ---- end to end (same definition as the one-GPU line): the domain exists (allocation,
+  # peer mapping and graph capture are the counterpart of the reference's first allocate +
+  # jit compile); timed: H2D of the slab state from pinned memory, rebuild on it, first
+  # force evaluation, the steps with the periodic host readbacks, D2H of the state.
   R_pin = torch.from_numpy(R_loc).pin_memory()
   P_pin = Pd.cpu().pin_memory()
   out_R = torch.empty_like(R_pin).pin_memory()
   out_P = torch.empty_like(P_pin).pin_memory()
   e2e_steps = args.steps
-  # drop the first domain: its buffers go back to torch's caching allocator, so the
-  # timed init below re-uses device memory instead of paying cudaMalloc again
-  del dom, st, ws, plain_force, timed_force
-  import gc
-  gc.collect()
   torch.cuda.synchronize()
   dist.barrier()
   t0 = time.perf_counter()
-  dom2 = SlabDomain(box, efn, bench.R_CUT, bench.SKIN, bench.DT, comm=comm)
-  st2 = dom2.init(R_pin.to(dev, non_blocking=True), P_pin.to(dev, non_blocking=True), gid)
+  st = dom.reset(st, R_pin.to(dev, non_blocking=True), P_pin.to(dev, non_blocking=True), gid)
   for i in range(e2e_steps):
-    st2 = dom2.step(st2)
+    st = dom.step(st)
     if (i + 1) % args.block == 0:
-      dom2.kinetic_energy()                       # global KE read back, like the example loop
-  out_R.copy_(st2.R[:N_loc], non_blocking=True)   # (slab populations drift by a few atoms;
-  out_P.copy_(st2.P[:N_loc], non_blocking=True)   #  the copy size is the initial one)
+      dom.kinetic_energy()                       # global KE read back, like the example loop
+      dom.check_list(st)
+  n_out = min(st.n_own, N_loc)
+  out_R[:n_out].copy_(st.R[:n_out], non_blocking=True)   # (slab populations drift by a few atoms)
+  out_P[:n_out].copy_(st.P[:n_out], non_blocking=True)
   torch.cuda.synchronize()
   dist.barrier()
   e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
   dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+  overflow = torch.tensor([int(dom.nbrs.error.code) & 3], dtype=torch.int64, device=dev)
+  dist.all_reduce(overflow, op=dist.ReduceOp.MAX)
 
   if rank == 0:
     ms_total = float(ms.item())
@@ -780,7 +827,10 @@ def bench_domain(args, world, rank, dev):
                    'atoms': N, 'ghost_atoms_per_gpu': int(n_ghost.item()),
                    'halo_bytes_per_step_per_gpu': face_bytes,
                    'rebuilds_in_timed_region': rebuilds_timed,
-                   'loop': 'eager Python loop (one host decision per step, NCCL halo exchange)',
+                   'loop': ('CUDA graph of the 4 step kernels (drift, peer-memory push, wait+unpack, force); '
+                            'host polls the device-written rebuild decision; rebuilds host-driven')
+                   if dom_graph else 'eager loop',
+                   'transport': dom_transport, 'neighbor_overflow': bool(int(overflow.item())),
                    'l2_policy': 'working set exceeds L2',
                    'kinetic_energy_per_atom': ke / N},
         'roofline': {'bound': 'hbm', 'kernel': 'k_pair_force<float,3,LJ,scalar,kick> (slowest rank)',
@@ -792,10 +842,13 @@ def bench_domain(args, world, rank, dev):
                 'h2d_bytes_per_step': 2 * N_loc * 12 * world / e2e_steps,
                 'd2h_bytes_per_step': (2 * N_loc * 12 * world + 8 * world * (e2e_steps // args.block)) / e2e_steps,
                 'steps': e2e_steps,
-                'includes': 'per rank: H2D of the slab state, domain init (first neighbour build, ghost '
-                            f'selection), {e2e_steps} steps, global KE readback every {args.block} steps, D2H of state'},
-        'gpu_launches': int(world * (args.steps * 6 + rebuilds_timed * 24)),
+                'includes': 'per rank: H2D of the slab state from pinned memory, migration + ghost selection + '
+                            f'neighbour build on it, first force evaluation, {e2e_steps} steps, global KE readback '
+                            f'every {args.block} steps, D2H of state; domain allocation, peer mapping and graph '
+                            'capture happen before the timed region (same definition as the one-GPU line)'},
+        'gpu_launches': int(world * (args.steps * 4 + rebuilds_timed * 22)),
         'clocks': clocks,
     }
     print(json.dumps(line))
+  dom.close()
   dist.destroy_process_group()

@@ -21,10 +21,14 @@ def _free_port():
   return p
 
 
-def _init(rank, world, port):
+def _init(rank, world, port, backend='gloo'):
   os.environ['MASTER_ADDR'] = '127.0.0.1'
   os.environ['MASTER_PORT'] = str(port)
-  dist.init_process_group('gloo', rank=rank, world_size=world)
+  if backend == 'nccl':
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+  else:
+    dist.init_process_group('gloo', rank=rank, world_size=world)
 
 
 # ---- CPU: ring exchange semantics ------------------------------------------------
@@ -65,9 +69,9 @@ def test_ring_comm_gloo(world):
 
 # ---- GPU: 2 ranks on one device == single-GPU run ---------------------------------
 
-def _system(dtype):
+def _system(dtype, world=2):
   a = (4.0 / 0.8442) ** (1.0 / 3.0)
-  cells = (10, 5, 5)             # two slabs of 5 cells along x: width 8.4 > 2 * 2.8
+  cells = (5 * world, 5, 5)      # slabs of 5 cells along x: width 8.4 > 2 * 2.8
   basis = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]])
   g = np.stack(np.meshgrid(*[np.arange(c) for c in cells], indexing='ij'), -1).reshape(-1, 1, 3)
   R = ((g + basis[None]) * a).reshape(-1, 3)
@@ -78,19 +82,22 @@ def _system(dtype):
   return R, P, box
 
 
-def _dd_worker(rank, world, port, steps, dtype_name, outdir):
-  _init(rank, world, port)
-  torch.cuda.set_device(0)
+def _dd_worker(rank, world, port, steps, dtype_name, outdir, transport):
+  # one GPU per rank (NCCL control plane) when the box has them, else all ranks share
+  # device 0 (gloo control plane; the peer-memory exchange works through CUDA IPC either way)
+  own_gpu = torch.cuda.device_count() >= world
+  torch.cuda.set_device(rank if own_gpu else 0)
+  _init(rank, world, port, 'nccl' if own_gpu else 'gloo')
   import jax_md_b200 as jmd
   from jax_md_b200.domain import RingComm, SlabDomain
   dtype = np.dtype(dtype_name).type
-  R, P, box = _system(dtype)
+  R, P, box = _system(dtype, world)
   comm = RingComm()
   width = float(box[0]) / world
   own = np.floor(R[:, 0] / width).astype(int) % world == rank
   disp, shift = jmd.space.periodic(box)
   _, efn = jmd.energy.lennard_jones_neighbor_list(disp, box, dr_threshold=0.3)
-  dom = SlabDomain(box, efn, 2.5, 0.3, 2e-3, comm=comm)
+  dom = SlabDomain(box, efn, 2.5, 0.3, 2e-3, comm=comm, transport=transport)
   gid = torch.as_tensor(np.nonzero(own)[0], device='cuda')
   st = dom.init(torch.as_tensor(R[own], device='cuda'), torch.as_tensor(P[own], device='cuda'), gid)
   pe0 = dom.potential_energy(st)
@@ -100,17 +107,23 @@ def _dd_worker(rank, world, port, steps, dtype_name, outdir):
   pe = dom.potential_energy(st)
   np.savez(os.path.join(outdir, f'rank{rank}.npz'), gid=st.global_id.cpu().numpy(),
            R=st.position.cpu().numpy(), P=st.momentum.cpu().numpy(), ke=ke, pe=pe, pe0=pe0,
-           rebuilds=dom.rebuilds, n_ghost=st.n_ghost)
+           rebuilds=dom.rebuilds, n_ghost=st.n_ghost, graph=int(dom._graph is not None))
+  dom.close()
   dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('dtype_name', ['float64', 'float32'])
-def test_two_slabs_match_single_gpu(tmp_path, dtype_name):
+@pytest.mark.parametrize('dtype_name,world,transport',
+                         [('float64', 2, 'p2p'), ('float32', 2, 'p2p'), ('float64', 4, 'p2p'),
+                          ('float64', 2, 'nccl')])
+def test_slabs_match_single_gpu(tmp_path, dtype_name, world, transport):
+  """2 / 4 ranks (their own GPUs when the box has them) reproduce the single-GPU
+  trajectory: peer-memory halo + graph-captured step ('p2p') and the host-orchestrated
+  torch.distributed fallback ('nccl')."""
   import jax_md_b200 as jmd
   dtype = np.dtype(dtype_name).type
   steps = 150
-  R, P, box = _system(dtype)
+  R, P, box = _system(dtype, world)
   # single-GPU reference trajectory through the public API
   disp, shift = jmd.space.periodic(box)
   nf, efn = jmd.energy.lennard_jones_neighbor_list(disp, box, dr_threshold=0.3,
@@ -129,8 +142,11 @@ def test_two_slabs_match_single_gpu(tmp_path, dtype_name):
   ke_ref = float(jmd.quantity.kinetic_energy(momentum=state.momentum, mass=state.mass))
   pe_ref = float(efn(state.position, neighbor=nbrs))
 
-  mp.spawn(_dd_worker, args=(2, _free_port(), steps, dtype_name, str(tmp_path)), nprocs=2, join=True)
-  parts = [np.load(tmp_path / f'rank{r}.npz') for r in range(2)]
+  mp.spawn(_dd_worker, args=(world, _free_port(), steps, dtype_name, str(tmp_path), transport),
+           nprocs=world, join=True)
+  parts = [np.load(tmp_path / f'rank{r}.npz') for r in range(world)]
+  if transport == 'p2p':
+    assert all(int(p['graph']) == 1 for p in parts), 'the step should have been graph-captured'
   gid = np.concatenate([p['gid'] for p in parts])
   assert sorted(gid.tolist()) == list(range(len(R)))          # every atom owned exactly once
   Rdd = np.zeros_like(R_ref)

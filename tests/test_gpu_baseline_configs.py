@@ -279,7 +279,8 @@ def test_2d_fire_descent_matches_oracle(dtype):
   params = dict(sigma=sigma, epsilon=np.float32(1.0), alpha=np.float32(2.0))
 
   def f_o(Rx):
-    holder['nb'] = holder['nb'].update(Rx)
+    # the list is the one update()d on the positions at the START of the step, exactly
+    # like the reference loop (FIRE's first steps move atoms further than the skin)
     return oenergy.pair_neighbor_list_energy(pot, d_o, Rx, holder['nb'], species=sp,
                                              want_grads=True, **params)[1]
   init_o, step_o = osim.fire_descent(f_o, s_o)
@@ -293,6 +294,7 @@ def test_2d_fire_descent_matches_oracle(dtype):
   st_g = init_g(Rd, neighbor=nbrs)
   E0 = float(efn(Rd, neighbor=nbrs))
   for i in range(120):
+    holder['nb'] = holder['nb'].update(st_o.position)
     st_o = step_o(st_o)
     nbrs = nbrs.update(st_g.position)
     st_g = step_g(st_g, neighbor=nbrs)
