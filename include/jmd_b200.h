@@ -152,11 +152,12 @@ typedef struct {
   int32_t _pad2;
   uint32_t* cs_bits;
   uint64_t* cs_lb;
-  /* Device-resident atom counts {n, n_rows} (or NULL): when set, jmd_nve_kick_drift,
-   * jmd_pair_force and the jmd_dd_comm_* kernels take the counts from here instead of the
-   * host fields, so a captured CUDA graph of the step stays valid when a rebuild of the
-   * domain decomposition changes the local atom count (grids are sized for `n`, which
-   * then is the capacity). */
+  /* Device-resident atom counts {n, n_rows} (or NULL): when set, jmd_nve_kick_drift and
+   * the jmd_dd_comm_* kernels take the counts from here instead of the host fields, so a
+   * captured CUDA graph of the step stays valid when a rebuild of the domain
+   * decomposition changes the local atom count (grids are sized for `n`, which then is
+   * the capacity).  jmd_pair_force keeps the host counts: a decomposed list marks slots
+   * without a row by cnt = 0 / perm >= n_rows (see jax_md_b200/domain.py). */
   const int32_t* n_dev;
 } jmd_nbr_t;
 

@@ -343,7 +343,7 @@ void launch_cell_test_f(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   static int optin[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (bytes > 48 * 1024 && (dev >= 64 || !optin[dev])) {
+  if (dev >= 64 || !optin[dev]) {      // static + dynamic shared memory can pass 48 KB
     cudaFuncSetAttribute(k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, PERIODIC>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_MAX);
     cudaFuncSetAttribute(k_nbr_cell_test<T, DIM, MODE, FMT == 2, PERIODIC, false>,

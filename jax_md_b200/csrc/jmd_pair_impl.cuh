@@ -42,18 +42,6 @@ constexpr int IDX_CH = JMD_PAIR_IDXCH;       // rows per TMA stage of the index 
 #ifndef JMD_PAIR_ALWAYS_WRAP
 #define JMD_PAIR_ALWAYS_WRAP 1   /* measured: branch-free rint() form 2 % faster than the |d| > L/2 test */
 #endif
-#ifndef JMD_PAIR_FAST_EXPLICIT
-#define JMD_PAIR_FAST_EXPLICIT 1
-#endif
-#ifndef JMD_PAIR_FAST_BATCH
-#define JMD_PAIR_FAST_BATCH 4
-#endif
-#ifndef JMD_PAIR_FAST_PREFETCH
-#define JMD_PAIR_FAST_PREFETCH 0
-#endif
-#ifndef JMD_PAIR_NO_FASTPATH
-#define JMD_PAIR_NO_FASTPATH 1   /* 0: warps away from the box faces skip the wrap -- measured SLOWER on B200, see DESIGN.md */
-#endif
 #ifndef JMD_PAIR_MIN_BLOCKS
 #define JMD_PAIR_MIN_BLOCKS 10
 #endif
@@ -74,7 +62,6 @@ struct PairP {
   const T* array[3];
   T r_onset2, r_cutoff2, inv_denom;   // onset^2, cutoff^2, 1/(rc^2-ro^2)^3
   T r_cutoff, r_onset;
-  T reach;            // list cutoff + skin: no listed neighbour is further away (valid list)
   // outputs
   T* force;
   T* e_atom;
@@ -95,7 +82,6 @@ struct PairP {
   // shared-memory staging (jmd_common.cuh)
   const unsigned short* nl16;
   const int* blk_table;
-  const int* n_dev;         // {n, n_rows} on the device (domain decomposition), or NULL
 };
 
 // read-only (non-coherent) 16/32-byte position gathers
@@ -278,16 +264,13 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
 #endif
   constexpr bool WANT_E = RED == 2;
   constexpr int NV = RedN<RED>::value;
-  // (never write to the parameter struct: that would move all of it to local memory)
-  const int q_n = Q.n_dev ? __ldg(Q.n_dev) : Q.n;
-  const int q_rows = Q.n_dev ? __ldg(Q.n_dev + 1) : Q.n_rows;
   const int t = blockIdx.x * PAIR_BLOCK + threadIdx.x;
   double rv[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) rv[i] = 0.0;
 
-  const int ai = t < q_n ? Q.perm[t] : 0x7fffffff;
-  const bool valid = ai < q_rows;           // ghosts (ids >= n_rows) have no row
+  const int ai = t < Q.n ? Q.perm[t] : 0x7fffffff;
+  const bool valid = ai < Q.n_rows;         // ghosts (ids >= n_rows) have no row
   {
     const V4 pi = valid ? Q.pos_sorted[t] : V4();
     const int cnt = valid ? min(Q.cnt[t], Q.m_int) : 0;
@@ -297,7 +280,6 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
     // force itself stays in the position dtype like the reference's)
     double e = 0.0, ds = 0.0, de = 0.0;
     double vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    T dmax[3] = {T(0), T(0), T(0)};    // wrap-free loop: largest |raw difference| seen per axis
     const int* col = Q.nl + t;
     const T sig0 = Q.scalar[0], eps0 = Q.scalar[1], alp0 = Q.scalar[2];
     // free space: half = +inf, never "far"
@@ -316,24 +298,21 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
     const int CUT = Q.has_cutoff;
 #endif
     // one neighbour: displacement, potential, accumulation
-    auto pair = [&](auto wrap_tag, const int j, const V4& pj) {
-      // minimum image (tolerance-level, handles unwrapped positions): d - L rint(d / L).
-      // A raw difference within half a box side on every axis IS the minimum image --
-      // the case for every pair of an atom away from the box faces -- so warps of such
-      // atoms run the loop without the wrap (WRAP false) and only track max |d_k|.
-      constexpr bool WRAP = decltype(wrap_tag)::value;
+    auto pair = [&](const int j, const V4& pj) {
+      // minimum image (tolerance-level, handles unwrapped positions): a raw
+      // difference within half a box side on every axis IS the minimum image --
+      // the case for every pair of an atom away from the box faces -- so the
+      // rint() form runs only behind a rarely taken branch.
       T d[3];
       d[0] = pi.x - pj.x;
       d[1] = pi.y - pj.y;
       d[2] = DIM == 3 ? pi.z - pj.z : T(0);
-      if (WRAP) {
+      bool far = fabs(d[0]) > hx || fabs(d[1]) > hy;
+      if (DIM == 3) far = far || fabs(d[2]) > hz;
+      if (JMD_PAIR_ALWAYS_WRAP || far) {
         d[0] = Q.sp.wrap_fast(d[0], 0);
         d[1] = Q.sp.wrap_fast(d[1], 1);
         if (DIM == 3) d[2] = Q.sp.wrap_fast(d[2], DIM - 1);
-      } else {
-        dmax[0] = fmax(dmax[0], fabs(d[0]));
-        dmax[1] = fmax(dmax[1], fabs(d[1]));
-        if (DIM == 3) dmax[2] = fmax(dmax[2], fabs(d[2]));
       }
       const T r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
       T sigma = sig0, eps = eps0, alpha = alp0;
@@ -390,12 +369,12 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
 #pragma unroll
         for (int u = 0; u < PAIR_BATCH; ++u) pj[u] = lds_v4<T>(sbase + cc[u] * (unsigned)sizeof(V4));
 #pragma unroll
-        for (int u = 0; u < PAIR_BATCH; ++u) pair(std::true_type(), 0, pj[u]);
+        for (int u = 0; u < PAIR_BATCH; ++u) pair(0, pj[u]);
       }
 #pragma unroll 1
       for (; k < cnt; ++k) {
         const unsigned c = __ldcs(col16 + (size_t)k * np);
-        pair(std::true_type(), 0, lds_v4<T>(sbase + c * (unsigned)sizeof(V4)));
+        pair(0, lds_v4<T>(sbase + c * (unsigned)sizeof(V4)));
       }
     } else
 #endif
@@ -461,86 +440,15 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
 #pragma unroll(PAIR_BATCH)
         for (int r = 0; r < kend; ++r) {
           const int j = rowp[r * PAIR_BLOCK];
-          pair(std::true_type(), j, ld_pos(&Q.pos_sorted[j]));
+          pair(j, ld_pos(&Q.pos_sorted[j]));
         }
         __syncthreads();
       }
 #else
-      // Warps whose home atoms all sit further than the list's reach from every box face
-      // (or free space) need no wrap.  The loop still checks |d_k| <= L_k / 2 -- exactly the
-      // condition under which the wrap is the identity -- and the row is evaluated again
-      // with the wrap if it ever fails (positions far outside the box, stale list).
-      bool interior = true;
-      if (Q.sp.periodic) {
-        const T c[3] = {pi.x, pi.y, pi.z};
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) interior = interior && c[k] >= Q.reach && c[k] <= Q.sp.side[k] - Q.reach;
-      }
-      bool fast = __all_sync(0xffffffffu, interior || !valid);
-      if (WANT_E && !SCALAR && Q.dparam) fast = false;      // (its table atomics must not run twice)
-      if (JMD_PAIR_NO_FASTPATH) fast = false;
-      if (fast) {
-#if JMD_PAIR_FAST_EXPLICIT
-        // explicit batches: FB row entries, then their FB position gathers, then the
-        // arithmetic (ptxas otherwise issues every gather right before its use)
-        constexpr int FB = JMD_PAIR_FAST_BATCH;
-        const int full = cnt & ~(FB - 1);
-        int k = 0;
-#if JMD_PAIR_FAST_PREFETCH
-        int jn[FB];
-#pragma unroll
-        for (int u = 0; u < FB; ++u) jn[u] = (u < full) ? __ldcs(col + (size_t)u * np) : 0;
-#endif
-#pragma unroll 1
-        for (; k < full; k += FB) {
-          int jj[FB];
-          V4 pj[FB];
-#if JMD_PAIR_FAST_PREFETCH
-#pragma unroll
-          for (int u = 0; u < FB; ++u) jj[u] = jn[u];
-#pragma unroll
-          for (int u = 0; u < FB; ++u) pj[u] = ld_pos(&Q.pos_sorted[jj[u]]);
-          if (k + FB < full) {
-#pragma unroll
-            for (int u = 0; u < FB; ++u) jn[u] = __ldcs(col + (size_t)(k + FB + u) * np);
-          }
-#else
-#pragma unroll
-          for (int u = 0; u < FB; ++u) jj[u] = __ldcs(col + (size_t)(k + u) * np);
-#pragma unroll
-          for (int u = 0; u < FB; ++u) pj[u] = ld_pos(&Q.pos_sorted[jj[u]]);
-#endif
-#pragma unroll
-          for (int u = 0; u < FB; ++u) pair(std::false_type(), jj[u], pj[u]);
-        }
-#pragma unroll 1
-        for (; k < cnt; ++k) {
-          const int j = __ldcs(col + (size_t)k * np);
-          pair(std::false_type(), j, ld_pos(&Q.pos_sorted[j]));
-        }
-#else
 #pragma unroll(PAIR_BATCH)
-        for (int k = 0; k < cnt; ++k) {
-          const int j = __ldcs(col + (size_t)k * np);        // streamed once: keep it out of L1
-          pair(std::false_type(), j, ld_pos(&Q.pos_sorted[j]));
-        }
-#endif
-        bool bad = dmax[0] > hx || dmax[1] > hy;
-        if (DIM == 3) bad = bad || dmax[2] > hz;
-        if (__any_sync(0xffffffffu, bad)) {
-          fast = false;
-          f[0] = f[1] = f[2] = T(0);
-          e = ds = de = 0.0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) vir[k] = 0.0;
-        }
-      }
-      if (!fast) {
-#pragma unroll(PAIR_BATCH)
-        for (int k = 0; k < cnt; ++k) {
-          const int j = __ldcs(col + (size_t)k * np);
-          pair(std::true_type(), j, ld_pos(&Q.pos_sorted[j]));
-        }
+      for (int k = 0; k < cnt; ++k) {
+        const int j = __ldcs(col + (size_t)k * np);        // streamed once: keep it out of L1
+        pair(j, ld_pos(&Q.pos_sorted[j]));
       }
 #endif
     }
@@ -669,10 +577,6 @@ int JMD_PAIR_LAUNCHER(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, vo
   }
   T ro = (T)pp->r_onset, rc = (T)pp->r_cutoff;
   Q.r_onset = ro; Q.r_cutoff = rc;
-  {
-    const double lc = sqrt(nb->cutoff_sq > 0 ? nb->cutoff_sq : 0.0), skin = 2.0 * sqrt(nb->threshold_sq > 0 ? nb->threshold_sq : 0.0);
-    Q.reach = (T)((lc + skin) * 1.001);
-  }
   Q.r_onset2 = (T)pp->r_onset2; Q.r_cutoff2 = (T)pp->r_cutoff2;
   T den3 = (T)pp->switch_denom;
   Q.inv_denom = pp->has_cutoff ? T(1) / den3 : T(0);
@@ -681,7 +585,6 @@ int JMD_PAIR_LAUNCHER(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, vo
   Q.dt_dev = (const T*)dt_dev;
   Q.idx = nullptr; Q.idx_m = 0; Q.position = nullptr; Q.species = nullptr;
   Q.nl16 = nb->nl16; Q.blk_table = nb->blk_table;
-  Q.n_dev = nb->n_dev;
   const bool kick = momentum != nullptr;
   if ((kick || want_e) && (!red || !partials)) return JMD_EINVAL;
   if (kick && !mass) return JMD_EINVAL;

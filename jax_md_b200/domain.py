@@ -481,6 +481,13 @@ class SlabDomain:
       _lib.call('jmd_nbr_export', ws.ref(), pp, 0, s)
       # capacity overflow of the local list (density drifts through migration): caught at
       # the NEXT rebuild's host read (`_ghosts`), see _check_list
+    if self._peer is not None or self.transport == 'p2p':
+      # The graph-captured force kernel runs over the CAPACITY with n_rows = capacity: a
+      # slot takes part iff perm[slot] < capacity.  Ghost slots have empty rows (cnt = 0,
+      # set by the scan) and zero momenta, so they add nothing; slots behind the local
+      # atoms must not alias a real atom.
+      self.nbrs._ws.t['perm'][n_loc:].fill_(_INT_MAX)
+      st.P[st.n_own:].zero_()
     self.rebuilds += 1
 
   def _allocate(self, st, Rl, extra=0):
