@@ -2,8 +2,9 @@
 
     python -m jax_md_b200.build [--force] [--verbose]
 
-Every unit is an ordinary whole-program compile (no -rdc); the neighbour-list
-update kernel uses cooperative-groups grid synchronisation, which needs none.
+Every unit is an ordinary whole-program compile (no -rdc).  The persistent
+neighbour-list update kernel synchronises its single co-resident wave with a hand-rolled
+barrier (ordinary launch; see grid_sync in csrc/jmd_neighbor.cu for the time-out guard).
 """
 import hashlib
 import os
@@ -88,6 +89,34 @@ def build(force=False, verbose=False):
   with open(stamp, 'w') as f:
     f.write(digest)
   return OUT
+
+
+def ffi_include_dir():
+  """Where the XLA FFI headers live ($JMD_XLA_FFI_INCLUDE or jax.ffi.include_dir()), or None."""
+  d = os.environ.get('JMD_XLA_FFI_INCLUDE')
+  if d and os.path.exists(os.path.join(d, 'xla', 'ffi', 'api', 'ffi.h')):
+    return d
+  try:
+    import jax
+    return jax.ffi.include_dir()
+  except Exception:
+    return None
+
+
+def build_ffi(verbose=False):
+  """libjmd_b200_ffi.so (csrc/jmd_ffi.cc) -- only where the XLA FFI headers exist; returns
+  the path or None.  This image has no jax: the source is type-checked against a stand-in
+  API by tests/test_ffi_binding.py instead."""
+  inc = ffi_include_dir()
+  if inc is None:
+    return None
+  out = os.path.join(HERE, 'libjmd_b200_ffi.so')
+  cmd = ['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-I', inc, '-I', os.path.join(ROOT, 'include'),
+         '-I', '/usr/local/cuda/include', os.path.join(CSRC, 'jmd_ffi.cc'), '-o', out,
+         '-L', HERE, '-ljmd_b200', '-Wl,-rpath,$ORIGIN', '-L', '/usr/local/cuda/lib64', '-lcudart']
+  with open(os.path.join(OBJ, 'build_ffi.log'), 'w') as log:
+    _run(cmd, verbose, log)
+  return out
 
 
 if __name__ == '__main__':

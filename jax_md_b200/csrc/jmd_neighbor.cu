@@ -112,17 +112,41 @@ __device__ __forceinline__ int gthreads() { return gridDim.x * NB; }
 // on B200 (measured), which is more than the skin predicate itself.  `bar` is a
 // pair of zero-initialised counters {arrivals, exits}; the last block to leave
 // the kernel (grid_exit) zeroes them for the next launch.
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target) {
+// The barrier assumes that every block of the launch is resident (the grid is sized by the
+// occupancy API for the current device).  Should that ever not hold -- an SM-limited MPS
+// partition, a debugger -- the spin gives up after ~2 s instead of hanging the device: the
+// caller abandons the rebuild and both overflow bits are set, so the user-visible
+// `did_buffer_overflow` asks for a fresh allocate() (which uses ordinary launches only).
+__device__ __forceinline__ bool grid_sync(unsigned int* bar, unsigned int& target) {
+  __shared__ int ok_s;
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
     __threadfence();
     atomicAdd(&bar[0], 1u);
-    while (*((volatile unsigned int*)&bar[0]) < target) { }
+    const long long t0 = clock64();
+    int ok = 1;
+    while (*((volatile unsigned int*)&bar[0]) < target) {
+      if (clock64() - t0 > 4000000000ll) { ok = 0; break; }
+    }
     __threadfence();
+    ok_s = ok;
   }
   __syncthreads();
+  return ok_s != 0;
 }
+
+template <typename T, int DIM>
+__device__ __forceinline__ void grid_fault(const NbrP<T, DIM>& P, unsigned int* bar) {
+  if (threadIdx.x == 0) {
+    atomicOr((unsigned int*)((size_t)P.error & ~(size_t)3),
+             (unsigned)(JMD_ERR_NEIGHBOR_LIST_OVERFLOW | JMD_ERR_CELL_LIST_OVERFLOW) << (8 * ((size_t)P.error & 3)));
+    bar[0] = 0u;
+    bar[1] = 0u;
+  }
+}
+#define JMD_GRID_SYNC(P, bar, target) \
+  do { if (!grid_sync(bar, target)) { grid_fault(P, bar); return; } } while (0)
 
 __device__ __forceinline__ void grid_exit(unsigned int* bar) {
   __syncthreads();
@@ -487,6 +511,11 @@ __device__ void ph_build_reset(const NbrP<T, DIM>& P) {
   if (gtid() == 0) {
     P.state[ST_MAX_ROW] = 0;
     P.state[ST_TOTAL] = 0;
+    P.state[9] = 0;                       // ST_LB_TILE: tile counter of the offsets scan
+  }
+  if (P.cs_lb) {                          // its look-back words start from zero
+    const int tiles = (P.n + SCAN_TILE - 1) / SCAN_TILE + 1;
+    for (int i = gtid(); i < tiles; i += gthreads()) P.cs_lb[i] = 0ull;
   }
 }
 
@@ -1235,7 +1264,7 @@ void launch_build(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
 template <typename T, int DIM>
 void launch_export(const NbrP<T, DIM>& P, int gated, cudaStream_t stream) {
   const int G = JMD_SM_COUNT * 8;
-  if (P.cellscan && !(P.no_public_idx || (P.lazy_idx && gated == 1))) {
+  if (P.cs_lb && !(P.no_public_idx || (P.lazy_idx && gated == 1))) {
     // cell-scan lists: look-back offsets + one export kernel that also pads the sparse
     // tail, stores the reference positions and sets the error bits (no grid barrier)
     if (P.format != JMD_DENSE)
@@ -1305,36 +1334,36 @@ __global__ void __launch_bounds__(NB, 4) k_update(NbrP<T, DIM> P) {
     const bool moved = ph_skin(P);
     const int any = __syncthreads_or(moved ? 1 : 0);
     if (threadIdx.x == 0 && any) atomicOr((unsigned long long*)&P.state[ST_PENDING], 1ull);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     rebuild = __ldcg(&P.state[ST_PENDING]) != 0 || P.always_rebuild;
   }
   if (gtid() == 0) P.state[ST_REBUILD] = rebuild ? 1 : 0;
   if (!rebuild) { grid_exit(bar); return; }       // uniform over the whole grid
   if (P.use_cells) {
     ph_zero(P);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     if (gtid() == 0) P.state[ST_PENDING] = 0;    // everyone has read it
     ph_hash(P);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_scan_tiles<int, int>(P.cell_count, P.n_cells, P.scan_tmp, nullptr, sm);
     if (ref_scan(P)) ph_scan_tiles<int, int>(P.ref_count, P.n_ref_cells, ref_sums(P), nullptr, sm);
     ph_ref_max(P);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_scan_top<int>(P.scan_tmp, P.n_cells, sm);
     if (ref_scan(P)) ph_scan_top<int>(ref_sums(P), P.n_ref_cells, sm);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_scan_apply<int, int>(P.cell_count, P.n_cells, P.scan_tmp, P.cell_start, sm);
     if (ref_scan(P)) ph_scan_apply<int, int>(P.ref_count, P.n_ref_cells, ref_sums(P), P.ref_start, sm);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_scatter(P);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_rank_sort(P);
     ph_build_reset(P);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_inv_perm(P);
     ph_plan(P);
   } else {
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     if (gtid() == 0) P.state[ST_PENDING] = 0;
     ph_identity_sort(P);
     ph_build_reset(P);
@@ -1355,13 +1384,13 @@ __global__ void __launch_bounds__(NB, JMD_EXPORT_MIN_BLOCKS) k_update_c(NbrP<T, 
     unsigned int target = 0;
     long long* sp_sums = (long long*)P.scan_tmp;
     ph_sparse_counts(P);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_scan_tiles<int, long long>(P.tmp_ids, P.n, sp_sums, nullptr, sm);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_scan_top<long long>(sp_sums, P.n, sm);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_scan_apply<int, long long>(P.tmp_ids, P.n, sp_sums, P.offsets, sm);
-    grid_sync(bar, target);
+    JMD_GRID_SYNC(P, bar, target);
     ph_export(P, sm);
     ph_sparse_pad(P);
     ph_finalize(P);
@@ -1500,7 +1529,8 @@ int launch_update(NbrP<T, DIM>& P, cudaStream_t stream) {
   if ((rc = coop_grid(k_update<T, DIM>, cache_a, &grid))) return rc;
   k_update<T, DIM><<<grid, NB, 0, stream>>>(P);
   launch_scan<T, DIM>(P, 1, stream);
-  if (P.cellscan) {
+  if (P.cs_lb) {
+    // offsets by a look-back scan + one export kernel: ordinary launches, no grid barrier
     launch_export<T, DIM>(P, 1, stream);
     JMD_LAUNCH_CHECK();
     return 0;

@@ -250,7 +250,66 @@ def _host_scalar(x):
   return x
 
 
-_CELL_SCAN = os.environ.get('JMD_CELL_SCAN', '1') != '0'
+def workspace_buffers(c, n_buf, dim, n_cells):
+  """The device buffers behind a neighbour list as (name, shape, kind, fill) with kind in
+  'i4' | 'i8' | 'u1' | 'f' (position dtype); fill None = uninitialised.  Framework
+  agnostic: the torch host (`Workspace`) and the XLA-FFI binding (`_jax_binding.py`)
+  allocate from this one table.  `nl` and `idx` are sized after the occupancy pass."""
+  n_cells_buf = c.n_fine_cells
+  return [
+      ('cell_count', (n_cells_buf + 1,), 'i4', 0),
+      ('cell_start', (n_cells_buf + 1,), 'i4', 0),
+      ('cell_cursor', (max(n_cells_buf, 1),), 'i4', 0),
+      ('ref_count', (max(n_cells, 1),), 'i4', 0),
+      ('ref_start', (max(n_cells, 1) + 1,), 'i4', 0),
+      # two int scans or one int64 scan
+      ('scan_tmp', (2 * (max(n_cells_buf, n_buf) // 2048 + 2) + 16,), 'i4', 0),
+      ('hash', (max(n_buf, 1),), 'i4', None),
+      ('tmp_ids', (max(n_buf, 1),), 'i4', None),
+      ('perm', (c.n_pad,), 'i4', 0),
+      ('inv_perm', (max(n_buf, 1),), 'i4', None),
+      ('pos_sorted', (c.n_pad, 4), 'f', 0),
+      ('cnt', (c.n_pad,), 'i4', 0),
+      ('cnt_lower', (c.n_pad,), 'i4', 0),
+      ('offsets', (n_buf + 1,), 'i8', 0),
+      ('reference_position', (n_buf, dim), 'f', None),
+      ('error', (), 'u1', 0),
+      ('state', (_lib.ST_COUNT,), 'i8', 0),
+      # skin predicate fused into the drift kernel (simulate._Stepper.step)
+      ('skin_blk', (c.n_pad // 256 + 1,), 'i4', 0),
+      # look-back words of the sparse offsets scan (csrc/jmd_nbr_cellscan.cuh)
+      ('cs_lb', (n_buf // 2048 + 4,), 'i8', 0),
+  ]
+
+
+def capacity_rule(format, N, width, mask_self, capacity_multiplier, extra_capacity, max_row, total):
+  """partition.py:1090-1104 -> (max_occupancy, m_int): the public capacity and the
+  internal row capacity (Dense: the same; sparse formats: the Dense-equivalent rule on
+  the longest row, DESIGN.md "row capacity")."""
+  sparse = is_sparse(format)
+  occupancy = total if sparse else max_row
+  full_width = N * width if sparse else width
+  _extra = extra_capacity if not sparse else N * extra_capacity
+  max_occupancy = int(occupancy * capacity_multiplier + _extra)
+  if max_occupancy > full_width:
+    max_occupancy = full_width
+  if not sparse:
+    capacity_limit = N - 1 if mask_self else N
+  elif format is Sparse:
+    capacity_limit = N * (N - 1) if mask_self else N ** 2
+  else:
+    capacity_limit = N * (N - 1) // 2
+  if max_occupancy > capacity_limit:
+    max_occupancy = capacity_limit
+  if sparse:
+    m_int = min(int(max_row * capacity_multiplier + extra_capacity), width,
+                N - 1 if mask_self else N)
+  else:
+    m_int = max_occupancy
+  return max_occupancy, max(m_int, 1)
+
+
+_CELL_SCAN = os.environ.get('JMD_CELL_SCAN', '0') != '0'
 _CELL_SCAN_MIN_OCCUPANCY = float(os.environ.get('JMD_CELL_SCAN_MIN_OCC', '8'))
 
 
@@ -259,7 +318,10 @@ def _enable_cell_scan(ws, cl_capacity, static_kwargs):
   concatenated candidate stream of a home cell's 3^d stencil, 32 candidates at a
   time.  It pays when a cell holds enough atoms to fill the lanes (LJ liquid: ~20
   per cell); sparse cells (2-D soft spheres: ~2) keep the thread-per-atom scan.
-  `cell_scan=True/False` (static kwarg) overrides the occupancy heuristic."""
+  `cell_scan=True/False` (static kwarg) overrides the default, which is OFF: measured on
+  B200 (LJ, N=1M, profiles/r02_*) the test loop needs 0.47 warp instructions per candidate
+  against 1.1 for the thread-per-atom scan (0.45 vs 0.78 ms), but turning the accept masks
+  into rows costs more than it saves (0.81-0.89 ms with the rows; rebuild 1.31 vs 1.21 ms)."""
   c = ws.c
   c.cell_scan = 0
   stage = static_kwargs.get('stage_positions', os.environ.get('JMD_STAGE', '0') != '0')
@@ -272,7 +334,6 @@ def _enable_cell_scan(ws, cl_capacity, static_kwargs):
     return
   c.cs_batches = -(-max(cl_capacity, 1) // 32)
   c.cs_chunks = -(-(3 ** ws.dim) * max(cl_capacity, 1) // 32)
-  ws.buf('cs_lb', (ws.n_capacity // 2048 + 4,), torch.int64, 0)
   c.cell_scan = 1
 
 
@@ -295,9 +356,9 @@ def neighbor_list(displacement_or_metric,
     raise NotImplementedError(
         'fractional_coordinates / periodic_general: SURVEY.md 8(f) row 3.')
   if custom_mask_function is not None:
-    raise NotImplementedError(
-        'custom_mask_function needs the uncompacted [N, 3^d*capacity] candidate '
-        'array (partition.py:1079-1080); not provided by the fused build.')
+    return _masked_neighbor_list(displacement_or_metric, box, r_cutoff, dr_threshold,
+                                 capacity_multiplier, disable_cell_list, mask_self,
+                                 custom_mask_function, format, static_kwargs)
   spec = space.get_spec(displacement_or_metric)
   r_cutoff = _host_scalar(r_cutoff)
   dr_threshold = _host_scalar(dr_threshold)
@@ -317,26 +378,19 @@ def neighbor_list(displacement_or_metric,
     # NumPy scalar against an f64 array promotes exactly.
     return float(np_dtype(x)) if isinstance(x, (float, int)) else float(x)
 
-  def _make_workspace(position, extra_capacity, n_capacity=None):
-    _lib.require_cuda()
-    if not isinstance(position, torch.Tensor) or not position.is_cuda:
-      raise TypeError('positions must be a CUDA torch.Tensor [N, dim]')
-    N, dim = position.shape
+  def fill_descriptor(c, N, dim, np_dtype, n_buf):
+    """Static half of a jmd_nbr_t for N atoms (host arithmetic only: the cell-list
+    decision and grid of partition.py:1046-1054, metric constants, search-grid options).
+    Shared by the torch host below and the XLA-FFI binding (_jax_binding.py).
+    -> (use_cells, cell_size, n_reference_cells, fine)."""
     if dim not in (2, 3):
       raise ValueError(f'Cell list spatial dimension must be 2 or 3. Found {dim}.')
-    np_dtype = np.float32 if position.dtype == torch.float32 else np.float64
-    # per-atom buffers can be over-allocated (domain decomposition: the local
-    # atom count changes at every rebuild; see jax_md_b200/domain.py)
-    n_buf = max(N, int(n_capacity or 0))
-    ws = Workspace(N, dim, position.dtype, position.device)
-    ws.n_capacity = n_buf
-    c = ws.c
-    c.n, c.dtype, c.format = N, _lib.dtype_code(position.dtype), fmt_code
+    c.n, c.dtype, c.format = N, (_lib.F32 if np_dtype == np.float32 else _lib.F64), fmt_code
     c.mask_self = 1 if mask_self else 0
     c.always_rebuild = 1 if _always_rebuild else 0
     c.cutoff_sq = _typed(cutoff_sq, np_dtype)
     c.threshold_sq = _typed(threshold_sq, np_dtype)
-    c.space = space.space_struct(spec, dim, position.dtype)
+    c.space = space.space_struct(spec, dim, torch.float32 if np_dtype == np.float32 else torch.float64)
     c.n_pad = ((n_buf + 31) // 32) * 32 if n_buf else 32
 
     use_cells, cell_size, cps, n_cells = False, None, np.ones(3, i32), 0
@@ -389,27 +443,24 @@ def neighbor_list(displacement_or_metric,
     c.no_filter = 1 if static_kwargs.get('exact_scan', False) else 0
     # lazy_idx=True (static kwarg): see NeighborList.idx
     c.lazy_idx = 1 if static_kwargs.get('lazy_idx', False) else 0
-    n_cells_buf = c.n_fine_cells
-    i4 = torch.int32
-    ws.buf('cell_count', (n_cells_buf + 1,), i4, 0)
-    ws.buf('cell_start', (n_cells_buf + 1,), i4, 0)
-    ws.buf('cell_cursor', (max(n_cells_buf, 1),), i4, 0)
-    ws.buf('ref_count', (max(n_cells, 1),), i4, 0)
-    ws.buf('ref_start', (max(n_cells, 1) + 1,), i4, 0)
-    ws.buf('scan_tmp', (2 * (max(n_cells_buf, n_buf) // 2048 + 2) + 16,), i4, 0)   # two int scans or one int64 scan
-    ws.buf('hash', (max(n_buf, 1),), i4)
-    ws.buf('tmp_ids', (max(n_buf, 1),), i4)
-    ws.buf('perm', (c.n_pad,), i4, 0)
-    ws.buf('inv_perm', (max(n_buf, 1),), i4)
-    ws.buf('pos_sorted', (c.n_pad, 4), position.dtype, 0)
-    ws.buf('cnt', (c.n_pad,), i4, 0)
-    ws.buf('cnt_lower', (c.n_pad,), i4, 0)
-    ws.buf('offsets', (n_buf + 1,), torch.int64, 0)
-    ws.buf('reference_position', (n_buf, dim), position.dtype)
-    ws.buf('error', (), torch.uint8, 0)
-    ws.buf('state', (_lib.ST_COUNT,), torch.int64, 0)
-    # skin predicate fused into the drift kernel (simulate._Stepper.step)
-    ws.buf('skin_blk', (c.n_pad // 256 + 1,), i4, 0)
+    return use_cells, cell_size, n_cells, fine
+
+  def _make_workspace(position, extra_capacity, n_capacity=None):
+    _lib.require_cuda()
+    if not isinstance(position, torch.Tensor) or not position.is_cuda:
+      raise TypeError('positions must be a CUDA torch.Tensor [N, dim]')
+    N, dim = position.shape
+    np_dtype = np.float32 if position.dtype == torch.float32 else np.float64
+    # per-atom buffers can be over-allocated (domain decomposition: the local
+    # atom count changes at every rebuild; see jax_md_b200/domain.py)
+    n_buf = max(N, int(n_capacity or 0))
+    ws = Workspace(N, dim, position.dtype, position.device)
+    ws.n_capacity = n_buf
+    c = ws.c
+    use_cells, cell_size, n_cells, fine = fill_descriptor(c, N, dim, np_dtype, n_buf)
+    kinds = {'i4': torch.int32, 'i8': torch.int64, 'u1': torch.uint8, 'f': position.dtype}
+    for name, shape, kind, fill in workspace_buffers(c, n_buf, dim, n_cells):
+      ws.buf(name, shape, kinds[kind], fill)
     ws.drift_out = None            # (weakref to the drift's position tensor, its version, update epoch)
     ws.update_epoch = 0            # bumped by every update(): drift flags older than that are stale
     ws.n_cells_ref = n_cells
@@ -452,28 +503,8 @@ def neighbor_list(displacement_or_metric,
     state = ws.state_host()
     max_row, total = state[_lib.ST_MAX_ROW], state[_lib.ST_TOTAL]
     sparse = is_sparse(format)
-    occupancy = total if sparse else max_row
-    full_width = N * width if sparse else width
-    # -- capacity rule (partition.py:1090-1104)
-    _extra = extra_capacity if not sparse else N * extra_capacity
-    max_occupancy = int(occupancy * capacity_multiplier + _extra)
-    if max_occupancy > full_width:
-      max_occupancy = full_width
-    if not sparse:
-      capacity_limit = N - 1 if mask_self else N
-    elif format is Sparse:
-      capacity_limit = N * (N - 1) if mask_self else N ** 2
-    else:
-      capacity_limit = N * (N - 1) // 2
-    if max_occupancy > capacity_limit:
-      max_occupancy = capacity_limit
-    # internal full rows: Dense uses the public capacity; sparse formats get the
-    # Dense-equivalent rule on the longest row ("row capacity").
-    if sparse:
-      m_int = min(int(max_row * capacity_multiplier + extra_capacity), width,
-                  N - 1 if mask_self else N)
-    else:
-      m_int = max_occupancy
+    max_occupancy, m_int = capacity_rule(format, N, width, mask_self, capacity_multiplier,
+                                         extra_capacity, max_row, total)
     c.max_occupancy = max_occupancy
     c.m_int = max(m_int, 1)
     ws.buf('nl', (c.m_int, c.n_pad), torch.int32)
@@ -537,7 +568,88 @@ def neighbor_list(displacement_or_metric,
     # this list's own, rewritten in place (like jit with donated arguments)
     return _copy.copy(neighbors)       # (not replace(): reading .idx would materialise a lazy idx)
 
+  allocate_fn.fill_descriptor = fill_descriptor      # host planning shared with _jax_binding.py
   return NeighborListFns(allocate_fn, update_fn)
+
+
+def _masked_neighbor_list(displacement_or_metric, box, r_cutoff, dr_threshold,
+                          capacity_multiplier, disable_cell_list, mask_self,
+                          custom_mask_function, format, static_kwargs):
+  """`custom_mask_function` (partition.py:809, 1079-1080; tests/partition_test.py:403-459).
+
+  The reference applies the user's function to the UNCOMPACTED candidate array and prunes
+  by distance afterwards.  For the functions this hook exists for -- an entry is replaced
+  by N depending on the (row, entry) pair, e.g. bonded-pair exclusions -- masking commutes
+  with the distance pruning, so it is applied here to the kernel-built Dense rows, followed
+  by the reference's stable compaction and capacity rule.  The result is a list whose `idx`
+  is not the kernels' internal one: energies over it take the generic (torch-composed)
+  pair path.  `update` re-masks only after the inner list rebuilt (one host read of the
+  build counter, like the overflow check of the reference loop)."""
+  inner = neighbor_list(displacement_or_metric, box, r_cutoff, dr_threshold, capacity_multiplier,
+                        disable_cell_list, mask_self, None, False, Dense, **static_kwargs)
+  sparse = is_sparse(format)
+
+  def _from_dense(nb_inner, max_occupancy, cl_capacity):
+    dense = nb_inner.idx
+    N = dense.shape[0]
+    masked = custom_mask_function(dense)
+    # stable compaction of every row (partition.py:960-980): valid entries first
+    order = torch.sort((masked >= N).to(torch.int8), dim=1, stable=True).indices
+    rows = torch.gather(masked, 1, order)
+    valid = rows < N
+    if format is OrderedSparse:
+      senders = torch.arange(N, device=rows.device, dtype=rows.dtype)[:, None]
+      valid = valid & (rows < senders)                       # partition.py:1021-1022
+    if sparse:
+      occupancy = int(valid.sum())
+    else:
+      occupancy = int(valid.sum(1).max()) if N else 0
+    if max_occupancy is None:
+      w = N if cl_capacity is None else 3 ** nb_inner._ws.dim * cl_capacity
+      max_occupancy, _ = capacity_rule(format, N, w, mask_self, capacity_multiplier,
+                                       _masked_neighbor_list.extra, 0 if sparse else occupancy,
+                                       occupancy)
+    if sparse:
+      senders = torch.arange(N, device=rows.device, dtype=torch.int32)[:, None].expand_as(rows)
+      recv, send = rows[valid], senders[valid]
+      idx = torch.full((2, max_occupancy), N, dtype=torch.int32, device=rows.device)
+      k = min(max_occupancy, recv.numel())
+      idx[0, :k] = recv[:k]
+      idx[1, :k] = send[:k]
+    else:
+      idx = torch.full((N, max_occupancy), N, dtype=torch.int32, device=rows.device)
+      k = min(max_occupancy, rows.shape[1])
+      idx[:, :k] = torch.where(valid, rows, torch.full_like(rows, N))[:, :k]
+    overflow = occupancy > max_occupancy
+    return idx, max_occupancy, overflow
+
+  def _wrap(nb_inner, idx, max_occupancy, overflow, builds):
+    err = nb_inner.error.update(PEC.NEIGHBOR_LIST_OVERFLOW, overflow)
+    out = NeighborList(idx, nb_inner.reference_position, err, nb_inner.cell_list_capacity,
+                       max_occupancy, format, nb_inner.cell_size, nb_inner.cell_list_fn, update_fn, None)
+    object.__setattr__(out, '_inner', nb_inner)
+    object.__setattr__(out, '_inner_builds', builds)
+    return out
+
+  def allocate_fn(position, extra_capacity: int = 0, **kwargs):
+    _masked_neighbor_list.extra = extra_capacity
+    nb_inner = inner.allocate(position, extra_capacity, **kwargs)
+    idx, max_occupancy, overflow = _from_dense(nb_inner, None, nb_inner.cell_list_capacity)
+    return _wrap(nb_inner, idx, max_occupancy, overflow, nb_inner._ws.state_host()[_lib.ST_BUILDS])
+
+  def update_fn(position, neighbors, **kwargs):
+    nb_inner = neighbors._inner.update(position, **kwargs)
+    builds = nb_inner._ws.state_host()[_lib.ST_BUILDS]
+    if builds == neighbors._inner_builds:
+      return neighbors                                         # partition.py:1146: identity branch
+    idx, max_occupancy, overflow = _from_dense(nb_inner, neighbors.max_occupancy,
+                                               nb_inner.cell_list_capacity)
+    return _wrap(nb_inner, idx, max_occupancy, overflow, builds)
+
+  return NeighborListFns(allocate_fn, update_fn)
+
+
+_masked_neighbor_list.extra = 0
 
 
 def neighbor_list_mask(neighbor: NeighborList, mask_self: bool = False):

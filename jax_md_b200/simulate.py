@@ -125,7 +125,8 @@ class _Stepper:
     neighbor = kwargs.get('neighbor')
     fused = bool(self.fused) and neighbor is not None and \
         getattr(neighbor, '_ws', None) is not None and \
-        neighbor.internal_list_is_current
+        neighbor.internal_list_is_current and \
+        not getattr(self.fn, 'always_generic', False)
     sp = self.space_struct(R)
     R2 = torch.empty_like(R)
     P2 = torch.empty_like(P)

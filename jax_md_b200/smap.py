@@ -13,11 +13,14 @@ F = -dE/dR, dE/dsigma and dE/depsilon.  Higher-order derivatives are out of
 scope.
 """
 import ctypes as C
+import enum
+from typing import Any
 
 import numpy as np
 import torch
 
 from . import _lib, partition, space
+from . import dataclasses as _dataclasses
 
 _DEFAULTS = {
     _lib.POT_LJ: {'sigma': 1.0, 'epsilon': 1.0, 'alpha': 1.0},
@@ -42,6 +45,36 @@ class Scratch:
     return s
 
 
+class ParameterTreeMapping(enum.Enum):
+  """smap.py:57-79."""
+  Global = 0
+  PerParticle = 1
+  PerBond = 2
+  PerSpecies = 3
+
+
+@_dataclasses.dataclass
+class ParameterTree:
+  """smap.py:82-93: parameters in the form of a tree (dict / list / tuple of arrays),
+  processed leaf by leaf according to `mapping`."""
+  tree: Any
+  mapping: ParameterTreeMapping = _dataclasses.static_field()
+
+
+def _tree_map(f, tree):
+  if isinstance(tree, dict):
+    return {k: _tree_map(f, v) for k, v in tree.items()}
+  if isinstance(tree, (list, tuple)):
+    return type(tree)(_tree_map(f, v) for v in tree)
+  return f(tree)
+
+
+def _needs_generic(v):
+  """Parameter forms only the generic (torch-composed) path serves: ParameterTrees and
+  `(combinator, per_atom_array)` pairs (smap.py:826-846)."""
+  return isinstance(v, ParameterTree) or (isinstance(v, tuple) and len(v) == 2 and callable(v[0]))
+
+
 def _merge(static, dynamic, ignore_unused):
   """util.merge_dicts (util.py:57-79)."""
   if not ignore_unused:
@@ -53,12 +86,38 @@ def _merge(static, dynamic, ignore_unused):
   return merged
 
 
+def pair_descriptor(pot, sigma=None, epsilon=None, alpha=None):
+  """`_lib.PairT` for scalar parameters (host arithmetic only; shared with the XLA-FFI
+  binding): potential kind, cutoff constants in the reference's dtype (energy.py:558-566)."""
+  pt = _lib.PairT()
+  kind = pot['kind']
+  pt.kind = kind
+  pt.has_cutoff = 1 if pot.get('r_cutoff') is not None else 0
+  if pt.has_cutoff:
+    pt.r_onset = float(pot['r_onset'])
+    pt.r_cutoff = float(pot['r_cutoff'])
+    r_o = pot['r_onset'] ** np.float32(2)
+    r_c = pot['r_cutoff'] ** np.float32(2)
+    pt.r_onset2 = float(r_o)
+    pt.r_cutoff2 = float(r_c)
+    pt.switch_denom = float((r_c - r_o) ** 3)
+  for k, (name, v) in enumerate(zip(_PARAM_ORDER, (sigma, epsilon, alpha))):
+    pt.mode[k] = _lib.PARAM_SCALAR
+    pt.scalar[k] = float(_DEFAULTS[kind][name] if v is None else v)
+  return pt
+
+
 class PairNeighborListFn:
   """Callable returned by `pair_neighbor_list`."""
   _jmd_fused = 'pair'
 
   def __init__(self, pot, displacement_or_metric, species, reduce_axis,
-               ignore_unused_parameters, kwargs):
+               ignore_unused_parameters, kwargs, fn=None):
+    # the same potential through the generic, torch-composed path: lists whose `idx` is
+    # not the kernel's own (custom_mask_function, a foreign NeighborList), asymmetric
+    # parameter tables, per-edge output (reduce_axis=())
+    self.generic = None if fn is None else GenericPairNeighborListFn(
+        fn, displacement_or_metric, species, reduce_axis, ignore_unused_parameters, kwargs)
     self.pot = pot                      # dict(kind, r_onset, r_cutoff)
     self.spec = space.get_spec(displacement_or_metric)
     self.species = species
@@ -67,12 +126,26 @@ class PairNeighborListFn:
     self.kwargs = dict(kwargs)
     self.kwargs.pop('fractional_coordinates', None)   # energy.py:240,340,443
     self._conv = {}
+    self.always_generic = False
     if reduce_axis is not None:
       if len(reduce_axis) == 0:
-        raise NotImplementedError('reduce_axis=() (per-edge output) is not '
-                                  'provided by the fused kernel.')
-      if 0 in reduce_axis and 1 not in reduce_axis:
+        self.always_generic = True        # per-edge output (smap.py:952-954)
+      elif 0 in reduce_axis and 1 not in reduce_axis:
         raise ValueError()
+    for v in self.kwargs.values():        # asymmetric [S, S] / [N, N] tables: row forces are not -dE/dR_i
+      if isinstance(v, (torch.Tensor, np.ndarray)) and getattr(v, 'ndim', 0) == 2:
+        t = torch.as_tensor(v)
+        if t.dtype.is_floating_point and not bool(torch.equal(t, t.T)):
+          self.always_generic = True
+    if self.always_generic and self.generic is None:
+      raise NotImplementedError('this parameter form needs the generic pair_neighbor_list path')
+
+  def _use_generic(self, neighbor):
+    if self.generic is None:
+      return False
+    if self.always_generic:
+      return True
+    return getattr(neighbor, '_ws', None) is None or not neighbor.internal_list_is_current
 
   # -- parameter canonicalisation (smap.py:697-846) ---------------------------
   def _tensor(self, x, dtype, device):
@@ -231,10 +304,21 @@ class PairNeighborListFn:
 
   def force(self, R, neighbor=None, **dynamic_kwargs):
     """-dE/dR straight from the kernel (quantity.force fast path)."""
+    if neighbor is None:
+      neighbor = dynamic_kwargs.pop('neighbor', None)
+    if self._use_generic(neighbor):
+      Rg = R.detach().requires_grad_(True)
+      with torch.enable_grad():
+        (g,) = torch.autograd.grad(self.generic(Rg, neighbor, **dynamic_kwargs), Rg)
+      return -g
     neighbor, species, params = self._resolve(neighbor, dict(dynamic_kwargs))
     return self.launch(R, neighbor, species, params, want_energy=False)['force']
 
   def __call__(self, R, neighbor=None, **dynamic_kwargs):
+    if neighbor is None:
+      neighbor = dynamic_kwargs.pop('neighbor', None)
+    if self._use_generic(neighbor):
+      return self.generic(R, neighbor, **dynamic_kwargs)
     neighbor, species, params = self._resolve(neighbor, dict(dynamic_kwargs))
     per_atom = self.reduce_axis is not None
     if per_atom and neighbor.format is partition.OrderedSparse:
@@ -328,6 +412,22 @@ class GenericPairNeighborListFn:
     comb = lambda a, b: 0.5 * (a + b)
     if isinstance(v, tuple) and len(v) == 2 and callable(v[0]):
       comb, v = v
+    if isinstance(v, ParameterTree):                      # smap.py:732-768, 806-823
+      M = ParameterTreeMapping
+      leaf = lambda p: p if isinstance(p, torch.Tensor) else torch.as_tensor(p, device=R.device)
+      if v.mapping is M.Global:
+        return v.tree
+      if si is not None:
+        if v.mapping is not M.PerSpecies:
+          raise ValueError('Parameter tree mapping must be either Global or PerSpecies if using '
+                           'a species lookup.')
+        return _tree_map(lambda p: leaf(p)[si, sj], v.tree)
+      if v.mapping is M.PerParticle:
+        return _tree_map(lambda p: comb(leaf(p)[i], leaf(p)[j]), v.tree)
+      if v.mapping is M.PerBond:
+        return _tree_map(lambda p: leaf(p)[i, j], v.tree)
+      raise ValueError('Without species information ParameterTreeMapping be Global or PerParticle. '
+                       f'Found {v.mapping}.')
     if isinstance(v, (int, float)):
       return v
     v = torch.as_tensor(v, device=R.device) if not isinstance(v, torch.Tensor) else v.to(R.device)
@@ -404,11 +504,8 @@ def pair_neighbor_list(fn, displacement_or_metric, species=None,
   the fused CUDA kernel; any other Python `fn(dr, **params)` is mapped by
   `GenericPairNeighborListFn` (torch ops over the CUDA-built list)."""
   pot = getattr(fn, '_jmd_potential', None)
-  if pot is None:
+  if pot is None or any(_needs_generic(v) for v in kwargs.values()):
     return GenericPairNeighborListFn(fn, displacement_or_metric, species, reduce_axis,
                                      ignore_unused_parameters, kwargs)
-  for k in kwargs:
-    if callable(kwargs[k]) and not isinstance(kwargs[k], torch.Tensor):
-      raise NotImplementedError('custom parameter combinators')
   return PairNeighborListFn(pot, displacement_or_metric, species, reduce_axis,
-                            ignore_unused_parameters, kwargs)
+                            ignore_unused_parameters, kwargs, fn=fn)
