@@ -243,6 +243,109 @@ def _cell_dimensions(spatial_dimension, box_size, minimum_cell_size):
   return box_size, cell_size, cells_per_side, int(cell_count)
 
 
+@dataclasses.dataclass
+class CellList:
+  """partition.py:79-131 (same fields).  Buffers have shape S = cells_per_side... +
+  [cell_capacity]; empty slots hold id N."""
+  position_buffer: Any
+  id_buffer: Any
+  particle_cell_id: Any
+  named_buffer: Any
+  did_buffer_overflow: Any
+  cell_capacity: int = dataclasses.static_field()
+  cell_size: Any = None
+  update_fn: Callable = dataclasses.static_field(default=None)
+
+  def update(self, position, **kwargs) -> 'CellList':
+    cl_data = (self.cell_capacity, self.did_buffer_overflow, self.update_fn)
+    return self.update_fn(position, cl_data, **kwargs)
+
+  @property
+  def kwarg_buffers(self):
+    logging.warning('kwarg_buffers renamed to named_buffer. The name kwarg_buffers will be depricated.')
+    return self.named_buffer
+
+
+@dataclasses.dataclass
+class CellListFns:
+  """partition.py:134-143."""
+  allocate: Callable = dataclasses.static_field()
+  update: Callable = dataclasses.static_field()
+
+  def __iter__(self):
+    return iter((self.allocate, self.update))
+
+
+def cell_list(box_size, minimum_cell_size, buffer_size_multiplier: float = 1.25) -> CellListFns:
+  """The PUBLIC cell list of the reference (partition.py:296-488): dense per-cell buffers of
+  positions, ids and per-particle side data (`**kwargs`), same shapes, slot rule
+  (`sorted rank mod capacity`, :441), padding value and overflow flag.  It is a data-format
+  utility next to the hot path -- `neighbor_list` never materialises these buffers, its
+  kernels keep a CSR cell order instead -- so it is composed from device tensor ops
+  (stable sort + scatter, like the reference's argsort + `.at[].set`)."""
+  box_np = _host_scalar(box_size)
+  if isinstance(box_np, np.ndarray) and box_np.ndim == 1:
+    box_np = np.reshape(box_np, (1, -1))
+  min_cell = _host_scalar(minimum_cell_size)
+
+  def cell_list_fn(position, capacity_overflow_update=None, extra_capacity=0, **kwargs):
+    _lib.require_cuda()
+    N, dim = position.shape
+    if dim not in (2, 3):
+      raise ValueError(f'Cell list spatial dimension must be 2 or 3. Found {dim}.')
+    _, cell_size, cells_per_side, cell_count = _cell_dimensions(dim, box_np, min_cell)
+    cps = np.broadcast_to(np.reshape(cells_per_side, (-1,)), (dim,)).astype(np.int64)
+    dev = position.device
+    cs = torch.as_tensor(np.broadcast_to(np.reshape(np.asarray(cell_size, np.float64), (-1,)), (dim,)).copy(),
+                         dtype=position.dtype, device=dev)
+    cps_t = torch.as_tensor(cps, device=dev)
+    indices = torch.remainder((position / cs).to(torch.int32), cps_t.to(torch.int32))     # :421-422
+    mult = torch.as_tensor(np.concatenate([[1], np.cumprod(cps[:-1])]), device=dev)       # x fastest (:212-224)
+    hashes = (indices.long() * mult).sum(1)
+    if capacity_overflow_update is None:
+      occ = torch.bincount(hashes, minlength=cell_count)
+      cell_capacity = int(int(occ.max()) * buffer_size_multiplier) + extra_capacity       # :243-250, 369-373
+      overflow = torch.zeros((), dtype=torch.bool, device=dev)
+      update = cell_list_fn
+    else:
+      cell_capacity, overflow, update = capacity_overflow_update
+      overflow = torch.as_tensor(overflow, device=dev, dtype=torch.bool)
+    sort_map = torch.sort(hashes, stable=True).indices                                    # :432
+    sorted_cell_id = hashes[sort_map] * cell_capacity + \
+        torch.remainder(torch.arange(N, device=dev), cell_capacity)                       # :441-442
+    shape = tuple(int(c) for c in cps[::-1]) + (cell_capacity,)
+    pos_buf = torch.zeros((cell_count * cell_capacity, dim), dtype=position.dtype, device=dev)
+    id_buf = torch.full((cell_count * cell_capacity, 1), N, dtype=torch.int32, device=dev)
+    pos_buf[sorted_cell_id] = position[sort_map]
+    id_buf[sorted_cell_id] = sort_map.to(torch.int32)[:, None]
+    named = {}
+    for k, v in kwargs.items():
+      if not isinstance(v, torch.Tensor):
+        raise ValueError(f'Data must be specified as an ndarray. Found "{k}" with type {type(v)}.')
+      if v.shape[0] != N:
+        raise ValueError(f'Data must be specified per-particle (an ndarray with shape ({N}, ...)). '
+                         f'Found "{k}" with shape {tuple(v.shape)}.')
+      tail = tuple(v.shape[1:]) if v.ndim > 1 else (1,)
+      buf = torch.full((cell_count * cell_capacity,) + tail, 10 ** 5, dtype=v.dtype, device=dev)
+      buf[sorted_cell_id] = v[sort_map].reshape((N,) + tail)
+      named[k] = buf.reshape(shape + tail)
+    occ = torch.bincount(hashes, minlength=cell_count)
+    overflow = overflow | (occ.max() > cell_capacity)                                     # :458-460
+    return CellList(pos_buf.reshape(shape + (dim,)), id_buf.reshape(shape + (1,)), indices, named,
+                    overflow, cell_capacity, cell_size, update)
+
+  def allocate_fn(position, extra_capacity: int = 0, **kwargs):
+    return cell_list_fn(position, extra_capacity=extra_capacity, **kwargs)
+
+  def update_fn(position, cl_or_capacity, **kwargs):
+    if isinstance(cl_or_capacity, int):
+      return cell_list_fn(position, (int(cl_or_capacity), False, cell_list_fn), **kwargs)
+    cl = cl_or_capacity
+    return cell_list_fn(position, (cl.cell_capacity, cl.did_buffer_overflow, cl.update_fn), **kwargs)
+
+  return CellListFns(allocate_fn, update_fn)
+
+
 def _host_scalar(x):
   """Python / NumPy scalar view of a (possibly torch) scalar, keeping dtype."""
   if isinstance(x, torch.Tensor):
