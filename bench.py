@@ -150,6 +150,51 @@ def run_reference(args):
 # B200 arm
 # ------------------------------------------------------------------------------
 
+def measure_single(cells, steps, warmup, fmt_name, unroll):
+  """atom-steps/s of update + NVE on ONE GPU for an fcc box of `cells` (graph loop); the
+  extra points of the JSON line (same physics and step as the headline)."""
+  import torch
+  import jax_md_b200 as jmd
+  from jax_md_b200 import _lib
+  R_h, box = fcc(cells)
+  N = len(R_h)
+  disp, shift = jmd.space.periodic(box)
+  fmt = jmd.partition.NeighborListFormat[fmt_name]
+  nf, efn = jmd.energy.lennard_jones_neighbor_list(disp, box, r_onset=2.0, r_cutoff=R_CUT,
+                                                   dr_threshold=SKIN, format=fmt)
+  init_fn, apply_fn = jmd.simulate.nve(efn, shift, DT)
+  Rd = torch.as_tensor(R_h, device='cuda')
+  nbrs = nf.allocate(Rd)
+  state = init_fn(0, Rd, kT=KT, momenta=torch.as_tensor(momenta(N), device='cuda'), neighbor=nbrs)
+
+  def body(i, carry):
+    st, nb = carry
+    nb = nb.update(st.position)
+    return apply_fn(st, neighbor=nb), nb
+  k = max(unroll, (max(warmup, 1) + unroll - 1) // unroll * unroll)
+  state, nbrs = jmd.lax.fori_loop(0, k, body, (state, nbrs), unroll=unroll)
+  g = jmd.lax.fori_loop.last
+  if bool(nbrs.did_buffer_overflow):
+    nbrs = nf.allocate(state.position)
+    g = None
+  torch.cuda.synchronize()
+  b0 = nbrs._ws.state_host()[_lib.ST_BUILDS]
+  k = max(unroll, steps // unroll * unroll)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  state, nbrs = jmd.lax.fori_loop(0, k, body, (state, nbrs), unroll=unroll, graph=g)
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / k
+  out = {'atoms': N, 'value': N / (ms * 1e-3), 'unit': 'atom-timesteps/s', 'ms_per_step': ms, 'steps': k,
+         'rebuilds': int(nbrs._ws.state_host()[_lib.ST_BUILDS] - b0),
+         'neighbor_overflow': bool(nbrs.did_buffer_overflow), 'n_gpus': 1}
+  del nbrs, state, g
+  jmd.lax.fori_loop.last = None
+  torch.cuda.empty_cache()
+  return out
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -355,6 +400,16 @@ def run_b200(args):
          f'every {blk} steps, D2H of state; list allocation and graph capture (first allocate / '
          'jit compile of the reference) happen before the timed region'}
 
+  # ---- extra points (not the headline): the per-GPU load of the north star's N=32M run
+  # (4M atoms) and the 8M-atom system of the strong-scaling series, on this one GPU
+  extra = {}
+  if not args.no_extra:
+    del nbrs, state, st2, nb2
+    loop['g'] = None
+    torch.cuda.empty_cache()
+    for key, cells in (('weak_4m_per_gpu', (100, 100, 100)), ('strong_8m_total', (8 * n, n, n))):
+      extra[key] = measure_single(cells, args.steps, args.warmup, args.format, args.unroll)
+
   # ---- CPU baseline (oracle port, bounded sample) -------------------------------
   cpu = None
   if not args.no_cpu:
@@ -367,13 +422,21 @@ def run_b200(args):
   # nothing to do on a non-rebuild step are still launches): fused update =
   # k_update + k_nbr_stencil_scan + k_update_c, then k_kick_drift + k_pair_force
   if args.update_mode == 'fused':
-    per_step = 5
+    # k_update, stencil scan (gated), [look-back offsets], export (gated), drift, force
+    per_step = 5 if args.format == 'Dense' else 6
   else:
     per_step = 1 + 8 + 2 + (2 if args.format == 'Dense' else 7) + 2
-  # ncu --set full of this kernel at the default workload (profiles/r01_*): DRAM
-  # bytes per launch = the 4 B/pair index stream; positions stay in L2/L1
-  traffic = 357541632 if (N == 1000188 and args.format == 'OrderedSparse') else None
-  roofline['traffic'] = traffic
+  # DRAM bytes per launch of this kernel: not measurable inside the run (needs ncu); taken
+  # from the committed ncu --set full capture of the same workload when there is one
+  # (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep), else null
+  roofline['traffic'] = None
+  tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+  if os.path.exists(tp):
+    with open(tp) as f:
+      rec = json.load(f).get('k_pair_force')
+    if rec and rec.get('atoms') == N and rec.get('format') == args.format:
+      roofline['traffic'] = rec['dram_bytes_read'] + rec['dram_bytes_write']
+      roofline['traffic_source'] = rec['source']
   line = {
       'metric': 'atom-timesteps/s', 'value': value, 'unit': 'atom-timesteps/s',
       'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
@@ -388,6 +451,7 @@ def run_b200(args):
                  'neighbor_overflow': overflow},
       'neighbor_rebuild_ms': rebuild_ms,
       'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'variants': variants,
+      'weak_4m_per_gpu': extra.get('weak_4m_per_gpu'), 'strong_8m_total': extra.get('strong_8m_total'),
       'gpu_launches': int(args.steps * per_step),
       'clocks': clocks,
   }
@@ -409,6 +473,7 @@ def main():
   ap.add_argument('--cpu-steps', type=int, default=40)
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--no-variants', action='store_true')
+  ap.add_argument('--no-extra', action='store_true', help='skip the 4M / 8M-atom extra points')
   ap.add_argument('--loop', default='graph', choices=['eager', 'graph'])
   ap.add_argument('--unroll', type=int, default=20, help='steps per captured CUDA graph')
   ap.add_argument('--update-mode', default='fused', choices=['fused', 'gated'],

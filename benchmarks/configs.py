@@ -30,19 +30,37 @@ def timeit(step, state, nbrs, nf, steps, warmup):
   torch.cuda.synchronize()
   b0 = nbrs._ws.state_host()[4]
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  def body(i, carry):
+    st_, nb_ = carry
+    nb_ = nb_.update(st_.position)
+    return step(st_, neighbor=nb_), nb_
+  # jit(lax.fori_loop) of the reference == CUDA-graph replay here; capture outside the timed region
+  state, nbrs = jmd.lax.fori_loop(0, 20, body, (state, nbrs), unroll=20)
+  g = jmd.lax.fori_loop.last
+  steps = max(20, steps // 20 * 20)
+  torch.cuda.synchronize()
+  b0 = nbrs._ws.state_host()[4]
   e0.record()
-  for _ in range(steps):
-    nbrs = nbrs.update(state.position)
-    state = step(state, neighbor=nbrs)
+  state, nbrs = jmd.lax.fori_loop(0, steps, body, (state, nbrs), unroll=20, graph=g)
   e1.record()
   torch.cuda.synchronize()
   ms = e0.elapsed_time(e1) / steps
   return ms, nbrs._ws.state_host()[4] - b0, bool(nbrs.did_buffer_overflow), state, nbrs
 
 
-def report(name, N, ms, rebuilds, overflow, **extra):
+def report(name, N, ms, rebuilds, overflow, nbrs=None, itemsize=4, **extra):
+  # whole-step HBM roofline fraction by the SURVEY 8(d) accounting: per step
+  # sum_i n_i * (4 B index + 4 * itemsize B gathered position) + N * 6 * dim * itemsize B of state
+  roof = None
+  if nbrs is not None:
+    ws = nbrs._ws
+    pairs = int(torch.clamp(ws.t['cnt'][:N], max=ws.c.m_int).sum())
+    step_bytes = pairs * (4 + 4 * itemsize) + N * 6 * ws.dim * itemsize
+    peak, src = bench.peaks()
+    roof = dict(pairs=pairs, step_bytes=step_bytes, achieved_gbs=step_bytes / (ms * 1e-3) / 1e9,
+                peak_gbs=peak, frac=step_bytes / (ms * 1e-3) / 1e9 / peak, peak_source=src)
   print(json.dumps(dict(config=name, atoms=N, ms_per_step=ms, atom_steps_per_s=N / (ms * 1e-3),
-                        rebuilds=int(rebuilds), overflow=overflow, **extra)), flush=True)
+                        rebuilds=int(rebuilds), overflow=overflow, roofline_step=roof, **extra)), flush=True)
 
 
 def c1(steps, warmup):
@@ -57,7 +75,7 @@ def c1(steps, warmup):
   init, step = jmd.simulate.nve(efn, s, 1e-3)
   st = init(0, R, kT=1e-3, neighbor=nbrs)
   ms, rb, ov, st, nbrs = timeit(step, st, nbrs, nf, steps, warmup)
-  report('c1 2-D LJ N=6400 f64 OrderedSparse NVE (examples/nve_neighbor_list.py)', N, ms, rb, ov)
+  report('c1 2-D LJ N=6400 f64 OrderedSparse NVE (examples/nve_neighbor_list.py)', N, ms, rb, ov, nbrs, 8)
 
 
 def c2(steps, warmup):
@@ -72,7 +90,7 @@ def c2(steps, warmup):
     init, step = jmd.simulate.nve(efn, s, 5e-3)
     st = init(0, R, kT=1.0, momenta=torch.as_tensor(bench.momenta(len(R_h)), device='cuda'), neighbor=nbrs)
     ms, rb, ov, st, nbrs = timeit(step, st, nbrs, nf, steps, warmup)
-    report(f'c2 LJ fcc N=32000 f32 {fmt} NVE', len(R_h), ms, rb, ov)
+    report(f'c2 LJ fcc N=32000 f32 {fmt} NVE', len(R_h), ms, rb, ov, nbrs)
 
 
 def c3(steps, warmup):
@@ -90,7 +108,7 @@ def c3(steps, warmup):
     init, step = jmd.minimize.fire_descent(efn, s)
     st = init(R, neighbor=nbrs)
     ms, rb, ov, st, nbrs = timeit(step, st, nbrs, nf, steps, warmup)
-    report(f'c3 soft spheres {dim}-D N=256000 f32 OrderedSparse FIRE', N, ms, rb, ov,
+    report(f'c3 soft spheres {dim}-D N=256000 f32 OrderedSparse FIRE', N, ms, rb, ov, nbrs, 4,
            max_force=float(st.force.abs().max()))
 
 
@@ -109,7 +127,7 @@ def c4(steps, warmup):
   st = init(0, R, mass=mass, neighbor=nbrs)
   ms, rb, ov, st, nbrs = timeit(step, st, nbrs, nf, steps, warmup)
   T = float(jmd.quantity.temperature(momentum=st.momentum, mass=st.mass)) / 8.617333262e-5
-  report('c4 Stillinger-Weber Si N=512000 f32 Dense NVT Nose-Hoover', len(R_h), ms, rb, ov,
+  report('c4 Stillinger-Weber Si N=512000 f32 Dense NVT Nose-Hoover', len(R_h), ms, rb, ov, nbrs, 4,
          temperature_K=T)
 
 
@@ -123,7 +141,7 @@ def f64(steps, warmup):
   st = init(0, R, kT=1.0, momenta=torch.as_tensor(bench.momenta(len(R_h)).astype(np.float64), device='cuda'),
             neighbor=nbrs)
   ms, rb, ov, st, nbrs = timeit(step, st, nbrs, nf, steps, warmup)
-  report('f64 LJ fcc N=1000188 f64 OrderedSparse NVE', len(R_h), ms, rb, ov)
+  report('f64 LJ fcc N=1000188 f64 OrderedSparse NVE', len(R_h), ms, rb, ov, nbrs, 8)
 
 
 if __name__ == '__main__':

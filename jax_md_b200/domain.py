@@ -683,6 +683,53 @@ class SlabDomain:
 # bench.py entry for N > 1
 # ----------------------------------------------------------------------------------
 
+def measure_domain(args, comm, rank, world, dev, cells):
+  """value / ms_per_step of `args.steps` steps for a slab of `cells` fcc cells per rank
+  (stacked along x): the extra points of the multi-GPU JSON line."""
+  import bench
+  from . import energy
+  R_loc, box_loc = bench.fcc(cells)
+  a = box_loc[1] / cells[1]
+  R_loc[:, 0] += rank * cells[0] * a
+  box = np.array([world * cells[0] * a, cells[1] * a, cells[2] * a], np.float32)
+  N_loc = len(R_loc)
+  rng = np.random.default_rng(2000 + rank)
+  P_loc = rng.normal(0, np.sqrt(bench.KT), (N_loc, 3)).astype(np.float32)
+  disp, shift = space.periodic(box)
+  _, efn = energy.lennard_jones_neighbor_list(disp, box, r_onset=2.0, r_cutoff=bench.R_CUT,
+                                              dr_threshold=bench.SKIN)
+  dom = SlabDomain(box, efn, bench.R_CUT, bench.SKIN, bench.DT, comm=comm)
+  Rd, Pd = torch.as_tensor(R_loc, device=dev), torch.as_tensor(P_loc, device=dev)
+  Pd -= (comm.sum(Pd.sum(0, dtype=torch.float64)) / (world * N_loc)).to(Pd.dtype)
+  st = dom.init(Rd, Pd, torch.arange(N_loc, device=dev) + rank * N_loc)
+  for _ in range(max(args.warmup, 4)):
+    st = dom.step(st)
+  torch.cuda.synchronize()
+  dist.barrier()
+  r0 = dom.rebuilds
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    st = dom.step(st)
+  e1.record()
+  torch.cuda.synchronize()
+  dist.barrier()
+  ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+  dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  n_tot = torch.tensor([st.n_own], dtype=torch.int64, device=dev)
+  dist.all_reduce(n_tot)
+  ov = torch.tensor([int(dom.nbrs.error.code) & 3], dtype=torch.int64, device=dev)
+  dist.all_reduce(ov, op=dist.ReduceOp.MAX)
+  out = {'atoms': int(n_tot.item()), 'atoms_per_gpu': N_loc,
+         'value': int(n_tot.item()) * args.steps / (float(ms.item()) * 1e-3), 'unit': 'atom-timesteps/s',
+         'ms_per_step': float(ms.item()) / args.steps, 'steps': args.steps,
+         'rebuilds': dom.rebuilds - r0, 'neighbor_overflow': bool(int(ov.item())), 'n_gpus': world}
+  dom.close()
+  del dom, st
+  torch.cuda.empty_cache()
+  return out
+
+
 def bench_domain(args, world, rank, dev):
   import time
   """Weak-scaling LJ NVE: every rank owns a slab of `cells^3` fcc cells stacked
@@ -816,6 +863,17 @@ def bench_domain(args, world, rank, dev):
   overflow = torch.tensor([int(dom.nbrs.error.code) & 3], dtype=torch.int64, device=dev)
   dist.all_reduce(overflow, op=dist.ReduceOp.MAX)
 
+  # ---- extra points: 4M atoms per GPU (N = 32M on 8 GPUs, the north star's run) and the
+  # strong-scaling series (8M atoms in total, split over the ranks)
+  extra = {}
+  dom.close()
+  del dom, st
+  torch.cuda.empty_cache()
+  if not args.no_extra:
+    extra['weak_4m_per_gpu'] = measure_domain(args, comm, rank, world, dev, (100, 100, 100))
+    if (8 * n) % world == 0:
+      extra['strong_8m_total'] = measure_domain(args, comm, rank, world, dev, (8 * n // world, n, n))
+
   if rank == 0:
     ms_total = float(ms.item())
     N = int(n_tot.item())
@@ -853,9 +911,9 @@ def bench_domain(args, world, rank, dev):
                             f'neighbour build on it, first force evaluation, {e2e_steps} steps, global KE readback '
                             f'every {args.block} steps, D2H of state; domain allocation, peer mapping and graph '
                             'capture happen before the timed region (same definition as the one-GPU line)'},
+        'weak_4m_per_gpu': extra.get('weak_4m_per_gpu'), 'strong_8m_total': extra.get('strong_8m_total'),
         'gpu_launches': int(world * (args.steps * 4 + rebuilds_timed * 22)),
         'clocks': clocks,
     }
     print(json.dumps(line))
-  dom.close()
   dist.destroy_process_group()

@@ -175,6 +175,91 @@ def morse_neighbor_list(displacement_or_metric, box_size, species=None,
   return neighbor_fn, energy_fn
 
 
+def dsf_coulomb(r, Q_sq, alpha=0.25, cutoff=8.0):
+  """energy.py:578-597: damped-shifted-force Coulomb."""
+  qqr2e = 332.06371
+  import math
+  cutoffsq = cutoff * cutoff
+  erfcc = math.erfc(alpha * cutoff)
+  erfcd = math.exp(-alpha * alpha * cutoffsq)
+  f_shift = -(erfcc / cutoffsq + 2 / math.sqrt(math.pi) * alpha * erfcd / cutoff)
+  e_shift = erfcc / cutoff - f_shift * cutoff
+  e = qqr2e * Q_sq / r * (torch.erfc(alpha * r) - r * e_shift - r ** 2 * f_shift)
+  return torch.where(r < cutoff, e, torch.zeros_like(e))
+
+
+def bks(dr, Q_sq, exp_coeff, exp_decay, attractive_coeff, repulsive_coeff, coulomb_alpha, cutoff,
+        **unused_kwargs):
+  """energy.py:600-650: Beest-Kramer-van Santen silica potential (Buckingham form + DSF
+  Coulomb + r^-24 repulsion)."""
+  safe = torch.where(dr > 0, dr, torch.ones_like(dr))
+  e = (dsf_coulomb(safe, Q_sq, coulomb_alpha, cutoff) + exp_coeff * torch.exp(-safe / exp_decay)
+       + attractive_coeff / safe ** 6 + repulsive_coeff / safe ** 24)
+  return torch.where((dr < cutoff) & (dr > 0), e, torch.zeros_like(e))
+
+
+CHARGE_OXYGEN = -0.977476019
+CHARGE_SILICON = 1.954952037
+BKS_SILICA_DICT = {
+    'Q_sq': [[CHARGE_SILICON ** 2, CHARGE_SILICON * CHARGE_OXYGEN],
+             [CHARGE_SILICON * CHARGE_OXYGEN, CHARGE_OXYGEN ** 2]],
+    'exp_coeff': [[0, 471671.1243], [471671.1243, 23138.64826]],
+    'exp_decay': [[1, 0.19173537], [0.19173537, 0.356855265]],
+    'attractive_coeff': [[0, -2156.074422], [-2156.074422, -1879.223108]],
+    'repulsive_coeff': [[78940848.06, 668.7557239], [668.7557239, 2605.841269]],
+    'coulomb_alpha': 0.25,
+}
+
+
+def bks_neighbor_list(displacement_or_metric, box_size, species, Q_sq, exp_coeff, exp_decay,
+                      attractive_coeff, repulsive_coeff, coulomb_alpha, cutoff, dr_threshold=0.8,
+                      fractional_coordinates=False, format=partition.OrderedSparse,
+                      neighbor_list_fn=partition.neighbor_list,
+                      pair_neighbor_list_fn=smap.pair_neighbor_list, **neighbor_kwargs):
+  """energy.py:686-735.  The neighbour list is the CUDA one; the pair sum takes the
+  generic (torch-composed) `smap.pair_neighbor_list` path: BKS has no fused kernel."""
+  def table(x):
+    return torch.as_tensor(np.asarray(maybe_downcast(np.asarray(x, np.float64))))
+  neighbor_fn = neighbor_list_fn(displacement_or_metric, box_size, cutoff, maybe_downcast(dr_threshold),
+                                 fractional_coordinates=fractional_coordinates, format=format,
+                                 **neighbor_kwargs)
+  energy_fn = pair_neighbor_list_fn(
+      bks, space.canonicalize_displacement_or_metric(displacement_or_metric), species=species,
+      ignore_unused_parameters=True, Q_sq=table(Q_sq), exp_coeff=table(exp_coeff),
+      exp_decay=table(exp_decay), attractive_coeff=table(attractive_coeff),
+      repulsive_coeff=table(repulsive_coeff), coulomb_alpha=coulomb_alpha, cutoff=cutoff,
+      fractional_coordinates=fractional_coordinates)
+  return neighbor_fn, energy_fn
+
+
+def _bks_silica_self(Q_sq, alpha, cutoff):
+  """energy.py:760-771."""
+  import math
+  cutoffsq = cutoff * cutoff
+  erfcc = math.erfc(alpha * cutoff)
+  erfcd = math.exp(-alpha * alpha * cutoffsq)
+  f_shift = -(erfcc / cutoffsq + 2.0 / math.sqrt(math.pi) * alpha * erfcd / cutoff)
+  e_shift = erfcc / cutoff - f_shift * cutoff
+  return -(e_shift / 2.0 + alpha / math.sqrt(math.pi)) * Q_sq * 332.06371
+
+
+def bks_silica_neighbor_list(displacement_or_metric, box_size, species, cutoff=8.0,
+                             fractional_coordinates=False, format=partition.OrderedSparse,
+                             **neighbor_kwargs):
+  """energy.py:800-835: BKS for SiO2 incl. the self-energy terms."""
+  neighbor_fn, pair_fn = bks_neighbor_list(displacement_or_metric, box_size, species, cutoff=cutoff,
+                                           fractional_coordinates=fractional_coordinates, format=format,
+                                           **BKS_SILICA_DICT, **neighbor_kwargs)
+  sp = torch.as_tensor(species)
+  N_0, N_1 = int((sp == 0).sum()), int((sp == 1).sum())
+  e_self = N_0 * _bks_silica_self(CHARGE_SILICON ** 2, 0.25, cutoff) + \
+      N_1 * _bks_silica_self(CHARGE_OXYGEN ** 2, 0.25, cutoff)
+
+  def energy_fn(R, neighbor=None, **kwargs):
+    return pair_fn(R, neighbor, **kwargs) + e_self
+  return neighbor_fn, energy_fn
+
+
 class StillingerWeberFn:
   """energy_fn of `stillinger_weber_neighbor_list` (energy.py:994-1012) backed
   by csrc/jmd_sw.cu; also serves -dE/dR (quantity.force) from the same kernel."""

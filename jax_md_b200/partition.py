@@ -13,7 +13,7 @@ import ctypes as C
 import logging
 import os
 from enum import Enum, IntEnum
-from typing import Any, Callable, Optional
+from typing import Any, Callable, NamedTuple, Optional
 
 import numpy as np
 import torch
@@ -768,6 +768,59 @@ def neighbor_list_mask(neighbor: NeighborList, mask_self: bool = False):
     rows = torch.arange(N, dtype=torch.int32, device=neighbor.idx.device)
     mask = mask & (neighbor.idx != rows[:, None])
   return mask
+
+
+class GraphsTuple(NamedTuple):
+  """Field-for-field stand-in for `jraph.GraphsTuple` (jraph is not installed here): what
+  `to_jraph` returns; pass its fields to `jraph.GraphsTuple(**g._asdict())` where jraph exists."""
+  nodes: Any
+  edges: Any
+  receivers: Any
+  senders: Any
+  globals: Any
+  n_node: Any
+  n_edge: Any
+
+
+def _tree_map(f, tree):
+  if tree is None:
+    return None
+  if isinstance(tree, dict):
+    return {k: _tree_map(f, v) for k, v in tree.items()}
+  if isinstance(tree, (list, tuple)):
+    return type(tree)(_tree_map(f, v) for v in tree)
+  return f(tree)
+
+
+def to_jraph(neighbor: NeighborList, mask=None, nodes=None, edges=None, globals=None) -> GraphsTuple:
+  """partition.py:1185-1243: sparse neighbour list -> graph tuple, padded by one fictitious
+  graph with a single node (same edge reordering under an extra `mask`)."""
+  if not is_sparse(neighbor.format):
+    raise ValueError('Cannot convert a dense neighbor list to jraph format. Please use either '
+                     'NeighborListFormat.Sparse or NeighborListFormat.OrderedSparse.')
+  receivers, senders = neighbor.idx
+  N = len(neighbor.reference_position)
+  _mask = neighbor_list_mask(neighbor)
+
+  def pad(x):
+    return torch.cat((x, torch.zeros((1,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)), 0)
+  nodes = _tree_map(pad, nodes)
+  globals = _tree_map(pad, globals)
+  if mask is not None:
+    _mask = _mask & mask
+    cumsum = torch.cumsum(_mask.to(torch.int64), 0)
+    index = torch.where(_mask, cumsum - 1, torch.full_like(cumsum, len(receivers)))
+    ordered = torch.full((len(receivers) + 1,), N, dtype=torch.int32, device=receivers.device)
+    receivers = ordered.clone().index_put_((index,), receivers)[:-1]
+    senders = ordered.clone().index_put_((index,), senders)[:-1]
+
+    def reorder_edges(x):
+      out = torch.zeros((len(x) + 1,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+      return out.index_put_((index,), x)[:-1]
+    edges = _tree_map(reorder_edges, edges)
+  n_edge = torch.stack([_mask.sum(), (~_mask).sum()])
+  return GraphsTuple(nodes, edges, receivers, senders, globals,
+                     torch.tensor([N, 1], device=receivers.device), n_edge)
 
 
 def to_dense(neighbor: NeighborList):

@@ -89,7 +89,14 @@ class _Stepper:
     self.fn = energy_or_force_fn
     self.fused = getattr(energy_or_force_fn, '_jmd_fused', None)
     self.force_fn = quantity.canonicalize_force(energy_or_force_fn)
-    self.spec = space.get_spec(shift_fn)
+    # A shift function made by jax_md_b200.space is inlined into the drift kernel; any
+    # other callable `shift_fn(R, dR, **kw)` is applied as given (simulate.py:176-188),
+    # with the kick halves still on the CUDA kernels.
+    self.shift_fn = shift_fn
+    self.spec = getattr(shift_fn, '_jmd_space', None)
+    self.generic_shift = self.spec is None
+    if self.generic_shift:
+      self.spec = space.SpaceSpec(_lib.SPACE_FREE, None, False)
     self.dt = float(f32(dt))
     self.dt_2 = float(f32(f32(dt) / 2))
     self._sp = {}
@@ -133,6 +140,8 @@ class _Stepper:
     mass_is_array = 1 if mass.numel() > 1 else 0
     red = self.red(R)
     st = _lib.stream()
+    if self.generic_shift:
+      return self._step_generic_shift(R, P, F, mass, kwargs, dt_h, dt2_h, dt_dev, scale_dev)
     nb_ref = None
     if fused:
       ws = neighbor._ws
@@ -169,6 +178,41 @@ class _Stepper:
                 _lib.ptr(mass), mass_is_array, dt2_h, _lib.ptr(dt_dev),
                 _lib.ptr(red), _lib.ptr(partials), st)
     return R2, P2, F2
+
+
+def _generic_shift_step(self, R, P, F, mass, kwargs, dt_h, dt2_h, dt_dev, scale_dev):
+  """velocity Verlet around a user `shift_fn` (simulate.py:227-243): the position update is
+  the user's callable, forces come from `force_fn`, second kick + reductions from the
+  kick kernel."""
+  dt = dt_h if dt_dev is None else dt_dev.reshape(-1)[0].to(R.dtype)
+  dt_2 = dt2_h if dt_dev is None else (dt / 2)
+  P1 = P * scale_dev if scale_dev is not None else P
+  P1 = P1 + dt_2 * F
+  space_kw = {k: v for k, v in kwargs.items() if k != 'neighbor'}
+  R2 = self.shift_fn(R, dt * P1 / mass, **space_kw).contiguous()
+  F2 = self.force(R2, kwargs).contiguous()
+  P2 = P1.contiguous().clone()
+  partials = smap.Scratch.get(R.shape[0], R.device)
+  _lib.call('jmd_kick_reduce', _lib.dtype_code(R.dtype), R.shape[0], R.shape[1], _lib.ptr(P2), _lib.ptr(F2),
+            _lib.ptr(mass), 1 if mass.numel() > 1 else 0, dt2_h, _lib.ptr(dt_dev),
+            _lib.ptr(self.red(R)), _lib.ptr(partials), _lib.stream())
+  return R2, P2, F2
+
+
+_Stepper._step_generic_shift = _generic_shift_step
+
+
+def dispatch_by_state(fn):
+  """simulate.py:100-116: single dispatch on the type of the `state` argument (second
+  argument if the first is not a state-like dataclass)."""
+  import functools
+  dispatcher = functools.singledispatch(fn)
+
+  @functools.wraps(fn)
+  def wrapper(state, *args, **kwargs):
+    return dispatcher.dispatch(state.__class__)(state, *args, **kwargs)
+  wrapper.register = dispatcher.register
+  return wrapper
 
 
 def nve(energy_or_force_fn, shift_fn, dt=1e-3, **sim_kwargs):
@@ -318,6 +362,87 @@ def nvt_nose_hoover(energy_or_force_fn, shift_fn, dt, kT, chain_length=5,
                      chain=_make_chain(buf, chain_length, chain.tau, dof))
 
   apply_fn._stepper = stepper
+  return init_fn, apply_fn
+
+
+# -- Langevin / Brownian ---------------------------------------------------
+
+@dataclasses.dataclass
+class NVTLangevinState:
+  """simulate.py:1078-1099."""
+  position: Any
+  momentum: Any
+  force: Any
+  mass: Any
+  rng: Any
+
+  @property
+  def velocity(self):
+    return self.momentum / self.mass
+
+
+def nvt_langevin(energy_or_force_fn, shift_fn, dt, kT, gamma=0.1, center_velocity=True, **sim_kwargs):
+  """simulate.py:1113-1190: BAOAB Langevin.  B (kick) and A (drift) use the integrator
+  kernels -- `jmd_nve_kick_drift` is called with half the drift length, twice -- the O step
+  is elementwise tensor arithmetic around the device RNG (`torch.Generator`, the stand-in for
+  the reference's PRNG key: streams differ, distributions agree)."""
+  stepper = _Stepper(energy_or_force_fn, shift_fn, dt)
+
+  def init_fn(key, R, mass=f32(1.0), momenta=None, **kwargs):
+    _kT = kwargs.pop('kT', kT)
+    R = R.contiguous()
+    force = stepper.force(R, kwargs).contiguous()
+    m = _canonical_mass(mass, R)
+    g = _generator(key, R.device)
+    P = initialize_momenta(R, m, g, _kT) if momenta is None else momenta.to(dtype=R.dtype, device=R.device)
+    return NVTLangevinState(R, P.contiguous(), force, m, g)
+
+  def step_fn(state, **kwargs):
+    _dt = float(kwargs.pop('dt', dt))
+    _kT = kwargs.pop('kT', kT)
+    R, P, F, m, g = state.position, state.momentum, state.force, state.mass, state.rng
+    dt_2 = _dt / 2
+    space_kw = {k: v for k, v in kwargs.items() if k != 'neighbor'}
+    P = P + dt_2 * F                                            # B
+    R = stepper.shift_fn(R, dt_2 * P / m, **space_kw)           # A
+    c1 = float(np.exp(-gamma * _dt))                            # O (simulate.py:1102-1110)
+    c2 = torch.sqrt(torch.as_tensor(_kT, dtype=R.dtype, device=R.device) * (1 - c1 ** 2))
+    P = c1 * P + c2 * torch.sqrt(m) * torch.randn(P.shape, dtype=P.dtype, device=P.device, generator=g)
+    R = stepper.shift_fn(R, dt_2 * P / m, **space_kw).contiguous()    # A
+    F = stepper.force(R, kwargs).contiguous()
+    P = (P + dt_2 * F).contiguous()                             # B
+    return NVTLangevinState(R, P, F, m, g)
+
+  return init_fn, step_fn
+
+
+@dataclasses.dataclass
+class BrownianState:
+  """simulate.py:1193-1208."""
+  position: Any
+  mass: Any
+  rng: Any
+
+
+def brownian(energy_or_force, shift, dt, kT, gamma=0.1):
+  """simulate.py:1211-1268: overdamped Langevin dynamics."""
+  force_fn = quantity.canonicalize_force(energy_or_force)
+
+  def init_fn(key, R, mass=f32(1)):
+    return BrownianState(R.contiguous(), _canonical_mass(mass, R), _generator(key, R.device))
+
+  def apply_fn(state, **kwargs):
+    _dt = kwargs.pop('dt', dt)
+    _kT = kwargs.pop('kT', kT)
+    _gamma = kwargs.pop('gamma', gamma)
+    R, mass, g = state.position, state.mass, state.rng
+    F = force_fn(R, **kwargs)
+    xi = torch.randn(R.shape, dtype=R.dtype, device=R.device, generator=g)
+    nu = 1.0 / (mass * _gamma)
+    dR = F * _dt * nu + torch.sqrt(2.0 * _kT * _dt * nu) * xi
+    space_kw = {k: v for k, v in kwargs.items() if k != 'neighbor'}
+    return BrownianState(shift(R, dR, **space_kw).contiguous(), mass, g)
+
   return init_fn, apply_fn
 
 

@@ -623,9 +623,12 @@ def test_asymmetric_species_table_orientation(fmt):
   np.testing.assert_allclose(float(generic(Rd, neighbor=nb_g)), E_o, rtol=1e-10)
   F = jmd.quantity.force(generic)(Rd, neighbor=nb_g).cpu().numpy()
   np.testing.assert_allclose(F, F_o, rtol=1e-8, atol=1e-9 * np.abs(F_o).max())
-  # the fused kernel's per-row force needs symmetric tables: it must refuse, not guess
-  with pytest.raises(NotImplementedError):
-    fused(Rd, neighbor=nb_g)
+  # the fused kernel's per-row force needs symmetric tables: the factory notices the
+  # asymmetric table and serves this energy through the generic path instead of guessing
+  assert fused.always_generic
+  np.testing.assert_allclose(float(fused(Rd, neighbor=nb_g)), E_o, rtol=1e-10)
+  np.testing.assert_allclose(jmd.quantity.force(fused)(Rd, neighbor=nb_g).cpu().numpy(), F_o,
+                             rtol=1e-8, atol=1e-9 * np.abs(F_o).max())
   sym = jmd.smap.pair_neighbor_list(jmd.energy.soft_sphere, d_g, species=_dev(sp),
                                     sigma=_dev(0.5 * (sig + sig.T)))
   E_s, F_s, _ = oenergy.pair_neighbor_list_energy(pot, d_o, R, nb_o, species=sp, want_grads=True,

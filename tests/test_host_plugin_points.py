@@ -78,8 +78,8 @@ def test_neighbor_list_fns_interface():
     partition.neighbor_list(d, np.float32(20.0), 2.5, 0.3, format='Dense')
   with pytest.raises(NotImplementedError):
     partition.neighbor_list(d, np.float32(20.0), 2.5, 0.3, fractional_coordinates=True)
-  with pytest.raises(NotImplementedError):
-    partition.neighbor_list(d, np.float32(20.0), 2.5, 0.3, custom_mask_function=lambda idx: idx)
+  masked = partition.neighbor_list(d, np.float32(20.0), 2.5, 0.3, custom_mask_function=lambda idx: idx)
+  assert isinstance(masked, partition.NeighborListFns)        # served by the post-mask path
   assert partition.is_sparse(partition.OrderedSparse) and not partition.is_sparse(partition.Dense)
 
 
