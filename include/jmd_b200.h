@@ -49,9 +49,18 @@ typedef struct {
   int32_t dim;        /* 2 or 3 */
   int32_t kind;       /* JMD_SPACE_* */
   int32_t wrapped;    /* shift_fn wraps into [0, side) */
-  int32_t _pad;
+  int32_t general;    /* 0: space.periodic / free; 1: space.periodic_general (space.py:332-472)
+                         with an orthorhombic box (scalar, vector or diagonal matrix): the
+                         exact displacement is box * (mod(sa - sb + 1/2, 1) - 1/2) on the
+                         unit cube; `side` is the box diagonal, `inv_box` = 1 / box in the
+                         position dtype */
   double side[3];
   double half[3];
+  int32_t fractional; /* general: positions are stored in the unit cube (fractional_coordinates=True);
+                         the cell-sorted float4 copy and everything the force kernels see stay in
+                         real space (fractional * side) */
+  int32_t _pad;
+  double inv_box[3];
 } jmd_space_t;
 
 /* Slots of the device scalar block `jmd_nbr_t.state` (int64 each). */

@@ -32,8 +32,9 @@ RED_COUNT = 16
 
 class SpaceT(C.Structure):
   _fields_ = [('dim', C.c_int32), ('kind', C.c_int32), ('wrapped', C.c_int32),
-              ('_pad', C.c_int32), ('side', C.c_double * 3),
-              ('half', C.c_double * 3)]
+              ('general', C.c_int32), ('side', C.c_double * 3),
+              ('half', C.c_double * 3), ('fractional', C.c_int32), ('_pad', C.c_int32),
+              ('inv_box', C.c_double * 3)]
 
 
 class NbrT(C.Structure):

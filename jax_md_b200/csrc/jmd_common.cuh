@@ -79,9 +79,15 @@ struct Space {
   T side_f[DIM];     // side, or 0 for free space
   int periodic;
   int wrapped;
+  int general;       // space.periodic_general, orthorhombic (see jmd_space_t)
+  int frac;          // ... with positions stored in the unit cube
+  T ibox[DIM];       // 1 / box
   __host__ void init(const jmd_space_t& s) {
     periodic = s.kind == JMD_SPACE_PERIODIC;
     wrapped = s.wrapped;
+    general = periodic && s.general;
+    frac = general && s.fractional;
+    for (int k = 0; k < DIM; ++k) ibox[k] = general ? (T)s.inv_box[k] : T(1);
     for (int k = 0; k < DIM; ++k) {
       side[k] = (T)s.side[k];
       half[k] = (T)s.half[k];
@@ -117,15 +123,47 @@ struct Space {
   }
   // shift_fn (space.py:250-252 / 268-270)
   __device__ __forceinline__ T shift(T r, T dr, int k) const {
+    if (general) return shift_general(r, dr, k);
     T s = add_rn(r, dr);
     if (periodic && wrapped) s = mod_pos(s, side[k]);
     return s;
   }
+  // periodic_general (space.py:437-470): dR -> inv_box * dR, the update happens on the unit
+  // cube (R itself is transformed there and back when it is stored in real space)
+  __device__ __forceinline__ T shift_general(T r, T dr, int k) const {
+    const T du = mul_rn(dr, ibox[k]);
+    if (!frac && !wrapped) return add_rn(r, dr);
+    T u = frac ? r : mul_rn(r, ibox[k]);
+    u = add_rn(u, du);
+    if (wrapped) u = mod_pos(u, T(1));
+    return frac ? u : mul_rn(u, side[k]);
+  }
+  // exact displacement component of periodic_general (space.py:419-433):
+  // box * (mod(ua - ub + 1/2, 1) - 1/2), ua = a (fractional) or inv_box * a
+  __device__ __forceinline__ T disp_general(T a, T b, int k) const {
+    const T ua = frac ? a : mul_rn(a, ibox[k]);
+    const T ub = frac ? b : mul_rn(b, ibox[k]);
+    const T d = sub_rn(ua, ub);
+    const T m = sub_rn(mod_pos(add_rn(d, T(0.5)), T(1)), T(0.5));
+    return mul_rn(m, side[k]);
+  }
+  // fractional -> real (what the cell-sorted copy holds)
+  __device__ __forceinline__ T to_real(T r, int k) const { return frac ? mul_rn(r, side[k]) : r; }
 };
 
 // Exact squared distance sum_k d_k^2, sequential (space.py:227-235).
 template <typename T, int DIM>
 __device__ __forceinline__ T dist2_exact(const Space<T, DIM>& sp, const T* a, const T* b) {
+  if (sp.general) {
+    T g = sp.disp_general(a[0], b[0], 0);
+    T acc = mul_rn(g, g);
+#pragma unroll
+    for (int k = 1; k < DIM; ++k) {
+      g = sp.disp_general(a[k], b[k], k);
+      acc = add_rn(acc, mul_rn(g, g));
+    }
+    return acc;
+  }
   T dx = sp.disp(a[0], b[0], 0);
   T acc = mul_rn(dx, dx);
 #pragma unroll

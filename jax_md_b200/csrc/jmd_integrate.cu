@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(IB) k_kick_drift(StepP<T, DIM> S) {
     }
     if (S.pos_sorted) {
       T w = S.species ? (T)S.species[a] : T(0);
-      S.pos_sorted[S.inv_perm[a]] = mk4<T>(r[0], r[1], r[2], w);
+      S.pos_sorted[S.inv_perm[a]] = mk4<T>(S.sp.to_real(r[0], 0), S.sp.to_real(r[1], 1),
+                                           DIM == 3 ? S.sp.to_real(r[2], DIM - 1) : T(0), w);
     }
     if (S.skin_blk && a < s_rows) {
       // the next NeighborList.update(R') asks: did any atom move further than skin/2

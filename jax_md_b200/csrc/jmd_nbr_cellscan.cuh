@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_nbr_cell_test(NbrP<T, DIM> P,
               bool keep = a2 < c2;
               if (valid && (lane_exact || fabs(a2 - c2) <= bw)) {
                 const T hp3[3] = {hp.x, hp.y, hp.z};
-                keep = exact_keep<T, DIM, MODE, PERIODIC>(P, hp3, cv, hh, qq, c2);
+                keep = P.sp.general ? general_keep<T, DIM, MODE>(P, id_of(hp.w), __ldg(&P.perm[rank]), c2)
+                                    : exact_keep<T, DIM, MODE, PERIODIC>(P, hp3, cv, hh, qq, c2);
               }
               keep = keep && valid;
               const unsigned b = __ballot_sync(FULL, keep);

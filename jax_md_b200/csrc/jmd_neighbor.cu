@@ -175,9 +175,10 @@ __device__ __forceinline__ double4 make_v4<double>(double x, double y, double z,
 template <typename T, int DIM>
 __device__ __forceinline__ typename Vec4<T>::type load_atom(const NbrP<T, DIM>& P, int i) {
   const T* r = P.position + (size_t)i * DIM;
-  T z = DIM == 3 ? r[DIM - 1] : T(0);
+  // (periodic_general with fractional coordinates: the sorted copy is in real space)
+  T z = DIM == 3 ? P.sp.to_real(r[DIM - 1], DIM - 1) : T(0);
   T w = P.species ? (T)P.species[i] : T(0);
-  return make_v4<T>(r[0], r[1], z, w);
+  return make_v4<T>(P.sp.to_real(r[0], 0), P.sp.to_real(r[1], 1), z, w);
 }
 
 
@@ -553,6 +554,7 @@ __device__ void ph_pack(const NbrP<T, DIM>& P) {
 template <typename T, int DIM>
 __device__ __forceinline__ bool candidate_test(const NbrP<T, DIM>& P, const T* hp, const T* cp) {
   bool keep;
+  // (periodic_general: callers pass the user's own coordinates, see general_keep)
   if (P.rev_only) {
     keep = dist2_exact<T, DIM>(P.sp, cp, hp) < P.cutoff_sq;
   } else {
@@ -650,6 +652,22 @@ __device__ __forceinline__ void append_if_below(double a2, double lo, int rank, 
   JMD_APPEND_ASM("f64", "d");
 }
 #undef JMD_APPEND_ASM
+
+// periodic_general: the reference evaluates the metric on the USER's coordinates (unit cube
+// or real space, space.py:419-433), not on the real-space sorted copy: fetch them by id.
+// Dense (MODE 1) keeps a pair only if both orientations pass (partition.py:960-980).
+template <typename T, int DIM, int MODE>
+__device__ __forceinline__ bool general_keep(const NbrP<T, DIM>& P, int home_id, int cand_id, T c2) {
+  T a[DIM], b[DIM];
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) {
+    a[k] = P.position[(size_t)home_id * DIM + k];
+    b[k] = P.position[(size_t)cand_id * DIM + k];
+  }
+  bool keep = dist2_exact<T, DIM>(P.sp, a, b) < c2;
+  if (MODE == 1) keep = keep && (dist2_exact<T, DIM>(P.sp, b, a) < c2);
+  return keep;
+}
 
 // The reference's candidate test on one (home, candidate) pair, bit for bit:
 // forward d2(R_i, R_c) < cutoff^2 (partition.py:945-951) and, for Dense (MODE 1),
@@ -813,7 +831,8 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
             T a2 = ax * ax + ay * ay;
             if (DIM == 3) { const T az = h2 - cv.z; a2 += az * az; }
             if (!(a2 < lo_c) && !(a2 > hi_c))     // rare: inside the band / dirty cell
-              a2 = exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2) ? T(-2) : (T)INFINITY;
+              a2 = (P.sp.general ? general_keep<T, DIM, MODE>(P, hid, __ldg(&P.perm[rank]), c2)
+                                 : exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2)) ? T(-2) : (T)INFINITY;
             const int k_before = k;
             append_if_below<STAGE>(a2, lo_c, rank, self, off_end, (unsigned)P.n_pad, P.nl, P.nl16, lbase, off, k);
             if (ORDERED && COUNT) { if (k != k_before) kl += (__ldg(&P.perm[rank]) < hid); }
@@ -832,7 +851,8 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
         } else {
           for (int rank = start; rank < end; ++rank) {
             const V4 cv = pos[rank];
-            bool keep = exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2);
+            bool keep = P.sp.general ? general_keep<T, DIM, MODE>(P, hid, __ldg(&P.perm[rank]), c2)
+                                     : exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2);
             keep = keep && (rank != self);
             if (keep) {
               if (off < off_end) {
@@ -907,7 +927,14 @@ __device__ void ph_build_all_pairs(const NbrP<T, DIM>& P) {
       if (j < P.n) {
         const V4 cv = P.pos_sorted[j];
         const T cp[3] = {cv.x, cv.y, cv.z};
-        keep = candidate_test<T, DIM>(P, hp, cp);
+        if (P.sp.general) {                       // identity order: slot == atom id
+          T a[DIM], b[DIM];
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) { a[k] = P.position[(size_t)i * DIM + k]; b[k] = P.position[(size_t)j * DIM + k]; }
+          keep = P.rev_only ? dist2_exact<T, DIM>(P.sp, b, a) < P.cutoff_sq : dist2_exact<T, DIM>(P.sp, a, b) < P.cutoff_sq;
+        } else {
+          keep = candidate_test<T, DIM>(P, hp, cp);
+        }
         if (P.mask_self && j == i) keep = false;
       }
       unsigned b = __ballot_sync(0xffffffffu, keep);
@@ -1480,6 +1507,13 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   P.f_lo = (T)(nb->cutoff_sq - 2.0 * band);
   P.f_hi = (T)(nb->cutoff_sq + 2.0 * band);
   P.filter = (nb->use_cells && periodic && !nb->no_filter) ? 1 : 0;
+  if (nb->space.general) {
+    // the pre-filter runs on the real-space copy (fractional * side: one more rounding of
+    // size ulp(L)/2 per coordinate than the derivation above counts): double the band
+    P.band = (T)(4.0 * band);
+    P.f_lo = (T)(nb->cutoff_sq - 4.0 * band);
+    P.f_hi = (T)(nb->cutoff_sq + 4.0 * band);
+  }
   for (int k = 0; k < DIM; ++k)
     if (P.cps[k] < 2 * P.sw + 3) P.filter = 0;
   P.cell_count = nb->cell_count; P.cell_start = nb->cell_start; P.cell_cursor = nb->cell_cursor;

@@ -346,6 +346,53 @@ def cell_list(box_size, minimum_cell_size, buffer_size_multiplier: float = 1.25)
   return CellListFns(allocate_fn, update_fn)
 
 
+def _cell_size(box, minimum_cell_size):
+  """partition.py:590-592."""
+  cells_per_side = np.floor(box / minimum_cell_size)
+  return box / cells_per_side
+
+
+def _fractional_cell_size(box, cutoff):
+  """partition.py:595-638 (f32 host arithmetic)."""
+  box = np.asarray(box, f32) if not np.isscalar(box) else f32(box)
+  cutoff = f32(cutoff)
+  if np.ndim(box) == 0:
+    return cutoff / box
+  if box.ndim == 1:
+    return cutoff / np.min(box)
+  if box.ndim == 2:
+    if box.shape[0] == 1:
+      return f32(1) / np.floor(box[0, 0] / cutoff)
+    if box.shape[0] == 2:
+      xx, yy = box[0, 0], box[1, 1]
+      xy = box[0, 1] / yy
+      nx, ny = xx / np.sqrt(f32(1) + xy ** 2), yy
+      nmin = np.floor(np.min(np.array([nx, ny], f32)) / cutoff)
+      nmin = f32(1) if nmin == 0 else nmin
+      return f32(1) / nmin
+    if box.shape[0] == 3:
+      xx, yy, zz = box[0, 0], box[1, 1], box[2, 2]
+      xy, xz, yz = box[0, 1] / yy, box[0, 2] / zz, box[1, 2] / zz
+      nx = xx / np.sqrt(f32(1) + xy ** 2 + (xy * yz - xz) ** 2)
+      ny = yy / np.sqrt(f32(1) + yz ** 2)
+      nz = zz
+      nmin = np.floor(np.min(np.array([nx, ny, nz], f32)) / cutoff)
+      nmin = f32(1) if nmin == 0 else nmin
+      return f32(1) / nmin
+    raise ValueError(f'Expected box to be either 1-, 2-, or 3-dimensional found {box.shape[0]}')
+  raise ValueError(f'Expected box to be either a scalar, a vector, or a matrix. Found {type(box)}.')
+
+
+def is_box_valid(box) -> bool:
+  """partition.py:676-681."""
+  box = np.asarray(box)
+  if box.ndim in (0, 1):
+    return True
+  if box.ndim == 2:
+    return bool(np.all(np.triu(box) == box))
+  return False
+
+
 def _host_scalar(x):
   """Python / NumPy scalar view of a (possibly torch) scalar, keeping dtype."""
   if isinstance(x, torch.Tensor):
@@ -455,9 +502,6 @@ def neighbor_list(displacement_or_metric,
   same capacity rules and error bits; the displacement function must come from
   `jax_md_b200.space` so its metric can be inlined into the kernels."""
   is_format_valid(format)
-  if fractional_coordinates:
-    raise NotImplementedError(
-        'fractional_coordinates / periodic_general: SURVEY.md 8(f) row 3.')
   if custom_mask_function is not None:
     return _masked_neighbor_list(displacement_or_metric, box, r_cutoff, dr_threshold,
                                  capacity_multiplier, disable_cell_list, mask_self,
@@ -468,8 +512,13 @@ def neighbor_list(displacement_or_metric,
   _always_rebuild = bool(dr_threshold == 0)                       # :892
   box_np = _host_scalar(box)
   box_np = f32(box_np) if np.ndim(box_np) == 0 else np.asarray(box_np, f32)  # :897
-  if np.ndim(box_np) == 2:
-    raise NotImplementedError('matrix boxes: SURVEY.md 8(f) row 3.')
+  if fractional_coordinates and not (spec.general and spec.fractional):
+    raise ValueError('fractional_coordinates=True needs a displacement function from '
+                     'space.periodic_general(box, fractional_coordinates=True)')
+  if np.ndim(box_np) == 2 and not fractional_coordinates:
+    box_np = np.asarray(space._box_diagonal(box_np), f32)
+  # the box currently in force (fractional coordinates: `box=` overrides, partition.py:1045)
+  current = {'box': box_np}
   cutoff = r_cutoff + dr_threshold                                # :899
   cutoff_sq = cutoff ** 2                                         # :900
   threshold_sq = (dr_threshold / f32(2)) ** 2                     # :901
@@ -493,14 +542,19 @@ def neighbor_list(displacement_or_metric,
     c.always_rebuild = 1 if _always_rebuild else 0
     c.cutoff_sq = _typed(cutoff_sq, np_dtype)
     c.threshold_sq = _typed(threshold_sq, np_dtype)
-    c.space = space.space_struct(spec, dim, torch.float32 if np_dtype == np.float32 else torch.float64)
+    _spec = spec._replace(side=current['box']) if fractional_coordinates else spec
+    c.space = space.space_struct(_spec, dim, torch.float32 if np_dtype == np.float32 else torch.float64)
     c.n_pad = ((n_buf + 31) // 32) * 32 if n_buf else 32
 
     use_cells, cell_size, cps, n_cells = False, None, np.ones(3, i32), 0
     if not disable_cell_list:
       cell_size = cutoff                                           # :1046
-      if np.all(np.asarray(cell_size) < box_np / 3.0):             # :1052
-        _, cs, cpside, n_cells = _cell_dimensions(dim, box_np, cell_size)
+      _box = box_np
+      if fractional_coordinates:                                   # :1047-1051
+        cell_size = _fractional_cell_size(current['box'], cutoff)
+        _box = 1.0
+      if np.all(np.asarray(cell_size) < _box / 3.0):               # :1052
+        _, cs, cpside, n_cells = _cell_dimensions(dim, _box, cell_size)
         use_cells = True
         cps[:dim] = np.broadcast_to(np.reshape(cpside, (-1,)), (dim,))
         cs = np.broadcast_to(np.reshape(np.asarray(cs, f32), (-1,)), (dim,))
@@ -577,10 +631,17 @@ def neighbor_list(displacement_or_metric,
     """partition.py:1156-1157 -> neighbor_fn with neighbors=None (not jittable:
     reads occupancies back to the host)."""
     if 'box' in kwargs:
-      raise ValueError('Neighbor list cannot accept a box keyword argument if '
-                       'fractional_coordinates is not enabled.')
+      if not fractional_coordinates:
+        raise ValueError('Neighbor list cannot accept a box keyword argument if '
+                         'fractional_coordinates is not enabled.')
+      b = _host_scalar(kwargs['box'])
+      current['box'] = f32(b) if np.ndim(b) == 0 else np.asarray(b, f32)
     position = position.contiguous()
     ws = _make_workspace(position, extra_capacity, n_capacity)
+    if fractional_coordinates and not disable_cell_list and is_box_valid(current['box']):
+      # partition.py:1049: `err.update(MALFORMED_BOX, is_box_valid(box))` -- the bit is set
+      # when the box IS valid (reference quirk, SURVEY appendix C.2; replicated, not fixed)
+      ws.t['error'].fill_(int(PEC.MALFORMED_BOX))
     c, N, dim = ws.c, ws.n, ws.dim
     c.n_rows = int(n_rows) if n_rows else 0
     c.no_public_idx = 1 if no_public_idx else 0
@@ -641,10 +702,27 @@ def neighbor_list(displacement_or_metric,
 
   def update_fn(position, neighbors, **kwargs):
     """partition.py:1159-1160 / 1119-1154.  Never syncs with the host."""
-    if 'box' in kwargs and not disable_cell_list:
-      raise ValueError('Neighbor list cannot accept a box keyword argument if '
-                       'fractional_coordinates is not enabled.')
     ws = neighbors._ws
+    if 'box' in kwargs and not disable_cell_list:                  # partition.py:1125-1139
+      if not fractional_coordinates:
+        raise ValueError('Neighbor list cannot accept a box keyword argument if '
+                         'fractional_coordinates is not enabled.')
+      b = _host_scalar(kwargs['box'])
+      b = f32(b) if np.ndim(b) == 0 else np.asarray(b, f32)
+      bits = 0
+      if neighbors.cell_list_fn is not None:
+        cur = _cell_size(1.0, neighbors.cell_size)
+        new = _cell_size(1.0, _fractional_cell_size(b, cutoff))
+        if np.any(new > cur):
+          bits |= int(PEC.CELL_SIZE_TOO_SMALL)
+      if is_box_valid(b):
+        bits |= int(PEC.MALFORMED_BOX)
+      if bits and ws is not None:
+        ws.t['error'].bitwise_or_(torch.tensor(bits, dtype=torch.uint8, device=ws.t['error'].device))
+      if ws is not None:
+        # the metric of every later kernel (skin predicate, candidate tests, forces) uses the new box
+        current['box'] = b
+        ws.c.space = space.space_struct(spec._replace(side=b), ws.dim, ws.dtype)
     if ws is None:
       raise ValueError('This NeighborList was not allocated by jax_md_b200.')
     if position.shape != (ws.n, ws.dim) or position.dtype != ws.dtype:

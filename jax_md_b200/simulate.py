@@ -135,6 +135,11 @@ class _Stepper:
         neighbor.internal_list_is_current and \
         not getattr(self.fn, 'always_generic', False)
     sp = self.space_struct(R)
+    if self.spec.general and kwargs.get('box') is not None:
+      # periodic_general: `box=` overrides the box of the shift for this step (space.py:445-447)
+      b = kwargs['box']
+      b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b
+      sp = space.space_struct(self.spec._replace(side=b), R.shape[1], R.dtype)
     R2 = torch.empty_like(R)
     P2 = torch.empty_like(P)
     mass_is_array = 1 if mass.numel() > 1 else 0

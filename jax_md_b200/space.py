@@ -25,6 +25,8 @@ class SpaceSpec(NamedTuple):
   kind: int                 # _lib.SPACE_FREE / SPACE_PERIODIC
   side: Optional[object]    # as given by the user (float, np scalar, array)
   wrapped: bool
+  general: bool = False     # space.periodic_general (orthorhombic box)
+  fractional: bool = False  # ... positions stored in the unit cube
 
 
 def _side_vectors(side, dim, np_dtype):
@@ -49,11 +51,33 @@ def space_struct(spec: SpaceSpec, dim: int, torch_dtype) -> '_lib.SpaceT':
   st.kind = spec.kind
   st.wrapped = 1 if spec.wrapped else 0
   if spec.kind == _lib.SPACE_PERIODIC:
-    full, half = _side_vectors(spec.side, dim, np_dtype)
+    side = _box_diagonal(spec.side) if spec.general else spec.side
+    full, half = _side_vectors(side, dim, np_dtype)
     for k in range(dim):
       st.side[k] = float(full[k])
       st.half[k] = float(half[k])
+    if spec.general:
+      st.general = 1
+      st.fractional = 1 if spec.fractional else 0
+      inv = (np_dtype(1) / np.asarray(full, np_dtype)).astype(np.float64)      # space.inverse: 1 / box
+      for k in range(dim):
+        st.inv_box[k] = float(inv[k])
   return st
+
+
+def _box_diagonal(box):
+  """Scalar / vector / DIAGONAL-matrix box -> scalar or vector; a box with non-zero
+  off-diagonal elements (triclinic) is not served by the kernels."""
+  if isinstance(box, torch.Tensor):
+    box = box.detach().cpu().numpy()
+  b = np.asarray(box) if not isinstance(box, (float, int)) else box
+  if isinstance(b, np.ndarray) and b.ndim == 2:
+    if not np.array_equal(np.diag(np.diag(b)), b):
+      raise NotImplementedError(
+          'space.periodic_general with a triclinic box (off-diagonal elements): the CUDA kernels '
+          'serve scalar, vector and diagonal-matrix boxes (SURVEY.md 8f row 3).')
+    return np.diag(b).copy()
+  return b
 
 
 def _as_like(x, ref):
@@ -149,10 +173,61 @@ def periodic(side, wrapped: bool = True):
   return displacement_fn, shift_fn
 
 
+def inverse(box):
+  """space.py:110-121."""
+  b = box if isinstance(box, torch.Tensor) else torch.as_tensor(np.asarray(box))
+  if b.numel() == 1 or b.ndim == 1:
+    return 1 / b
+  if b.ndim == 2:
+    return torch.linalg.inv(b)
+  raise ValueError(f'Box must be either: a scalar, a vector, or a matrix. Found {box}.')
+
+
+def transform(box, R):
+  """space.py:156-186 (forward value; gradients w.r.t. R pass through unscaled like the
+  reference's custom JVP)."""
+  return raw_transform(box, R)
+
+
 def periodic_general(box, fractional_coordinates=True, wrapped=True):
-  raise NotImplementedError(
-      'space.periodic_general is row 3 of SURVEY.md 8(f) ("next"), not part of '
-      'the B200 hot path yet.')
+  """space.py:332-472: periodic boundary conditions on `box * [0, 1]^d`.  The returned
+  closures evaluate the reference's formulas with torch ops (host glue, tests); the tag
+  lets the kernels inline the same arithmetic.  Kernel support: scalar, vector and
+  diagonal-matrix boxes, `box=` overrides as host values."""
+  def _b(x, like):
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+    return t.to(device=like.device, dtype=like.dtype if t.is_floating_point() else None)
+
+  def displacement_fn(Ra, Rb, perturbation=None, **kwargs):
+    _box = kwargs.get('new_box', kwargs.get('box', box))
+    _inv_src = kwargs.get('box', box)
+    bt = _b(_box, Ra)
+    if not fractional_coordinates:
+      it = inverse(_b(_inv_src, Ra))
+      Ra, Rb = raw_transform(it, Ra), raw_transform(it, Rb)
+    dR = torch.remainder(Ra - Rb + 0.5, 1.0) - 0.5                 # periodic_displacement(f32(1.0), .)
+    dR = raw_transform(bt, dR)
+    if perturbation is not None:
+      dR = raw_transform(perturbation, dR)
+    return dR
+
+  def shift_fn(R, dR, **kwargs):
+    if not fractional_coordinates and not wrapped:
+      return R + dR
+    _box = kwargs.get('new_box', kwargs.get('box', box))
+    bt = _b(_box, R)
+    it = inverse(_b(kwargs.get('box', box), R))
+    dR = raw_transform(it, dR)
+    if not fractional_coordinates:
+      R = raw_transform(it, R)
+    R = torch.remainder(R + dR, 1.0) if wrapped else R + dR
+    if not fractional_coordinates:
+      R = raw_transform(bt, R)
+    return R
+  spec = SpaceSpec(_lib.SPACE_PERIODIC, box, wrapped, True, bool(fractional_coordinates))
+  displacement_fn._jmd_space = spec
+  shift_fn._jmd_space = spec
+  return displacement_fn, shift_fn
 
 
 def metric(displacement):

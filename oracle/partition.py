@@ -147,6 +147,47 @@ def cell_list_build(position, box_size, minimum_cell_size,
 # Neighbour list
 # ----------------------------------------------------------------------------
 
+def cell_size_fn(box, minimum_cell_size):
+  """partition.py:590-592."""
+  cells_per_side = np.floor(box / minimum_cell_size)
+  return box / cells_per_side
+
+
+def fractional_cell_size(box, cutoff):
+  """partition.py:595-638."""
+  box = np.asarray(box, f32)
+  cutoff = f32(cutoff)
+  if box.ndim == 0:
+    return cutoff / box
+  if box.ndim == 1:
+    return cutoff / np.min(box)
+  if box.shape[0] == 1:
+    return f32(1) / np.floor(box[0, 0] / cutoff)
+  if box.shape[0] == 2:
+    xx, yy = box[0, 0], box[1, 1]
+    xy = box[0, 1] / yy
+    nx, ny = xx / np.sqrt(f32(1) + xy ** 2), yy
+    nmin = np.floor(np.min(np.array([nx, ny], f32)) / cutoff)
+  else:
+    xx, yy, zz = box[0, 0], box[1, 1], box[2, 2]
+    xy, xz, yz = box[0, 1] / yy, box[0, 2] / zz, box[1, 2] / zz
+    nx = xx / np.sqrt(f32(1) + xy ** 2 + (xy * yz - xz) ** 2)
+    ny = yy / np.sqrt(f32(1) + yz ** 2)
+    nmin = np.floor(np.min(np.array([nx, ny, zz], f32)) / cutoff)
+  nmin = f32(1) if nmin == 0 else nmin
+  return f32(1) / nmin
+
+
+def is_box_valid(box):
+  """partition.py:676-681."""
+  box = np.asarray(box)
+  if box.ndim in (0, 1):
+    return True
+  if box.ndim == 2:
+    return bool(np.all(np.triu(box) == box))
+  return False
+
+
 def neighboring_cells(dim):
   """partition.py:232-240: first coordinate slowest, last fastest."""
   return np.array(list(np.ndindex(*([3] * dim))), dtype=i32) - 1
@@ -187,14 +228,14 @@ class neighbor_list:
                mask_self=True, custom_mask_function=None,
                fractional_coordinates=False, format=Dense, chunk=4096,
                **static_kwargs):
-    if fractional_coordinates:
-      raise NotImplementedError('oracle: fractional coordinates (SURVEY 8f-3)')
+    self.fractional = fractional_coordinates
     self.always_rebuild = (dr_threshold == 0)                    # :892
     self.box = f32(box) if np.ndim(box) == 0 else np.asarray(box, f32)  # :897
     self.cutoff = r_cutoff + dr_threshold                        # :899
     self.cutoff_sq = self.cutoff ** 2                            # :900
     self.threshold_sq = (dr_threshold / f32(2)) ** 2             # :901
     self.metric_sq = space.metric_sq(displacement)
+    self._mkw = {}
     self.capacity_multiplier = capacity_multiplier
     self.disable_cell_list = disable_cell_list
     self.mask_self = mask_self
@@ -222,25 +263,31 @@ class neighbor_list:
     cell_1d = np.sum(shifted * mult, axis=2)                     # [n, 3^d]
     ids = cl.id_buffer[cell_1d].reshape(hi - lo, -1)
     pos = cl.position_buffer[cell_1d].reshape(hi - lo, -1, dim)
-    d2 = self.metric_sq(position[lo:hi, None, :], pos)
+    d2 = self.metric_sq(position[lo:hi, None, :], pos, **self._mkw)
     return np.where(self._cmp(d2, position.dtype), ids, N).astype(i32)
 
-  def _build(self, position, err, neighbors, extra_capacity, max_occupancy):
+  def _build(self, position, err, neighbors, extra_capacity, max_occupancy, **kwargs):
     """`neighbor_fn`, partition.py:1037-1117."""
     N, dim = position.shape
     cl = None
     cell_size = None
     use_cells = False
+    self._mkw = {k: v for k, v in kwargs.items() if k == 'box'}   # metric kwargs (:1063)
     if not self.disable_cell_list:
       if neighbors is None:
+        _box = kwargs.get('box', self.box)
         cell_size = self.cutoff
-        if np.all(np.asarray(cell_size) < self.box / 3.0):       # :1052
-          cl = cell_list_build(position, self.box, cell_size,
+        if self.fractional:                                      # :1047-1051
+          err = err_update(err, PEC.MALFORMED_BOX, is_box_valid(_box))
+          cell_size = fractional_cell_size(_box, self.cutoff)
+          _box = 1.0
+        if np.all(np.asarray(cell_size) < _box / 3.0):           # :1052
+          cl = cell_list_build(position, _box, cell_size,
                                self.capacity_multiplier, None, extra_capacity)
       else:
         cell_size = neighbors.cell_size
         if neighbors.use_cell_list:
-          cl = cell_list_build(position, self.box, cell_size,
+          cl = cell_list_build(position, 1.0 if self.fractional else self.box, cell_size,
                                self.capacity_multiplier,
                                neighbors.cell_list_capacity)
       use_cells = cl is not None
@@ -276,7 +323,7 @@ class neighbor_list:
           mask = idx < N
         else:                                                    # :982-1008
           jj = np.minimum(idx, N - 1)
-          d2 = self.metric_sq(position[lo:hi, None, :], position[jj])
+          d2 = self.metric_sq(position[lo:hi, None, :], position[jj], **self._mkw)
           mask = self._cmp(d2, position.dtype) & (idx < N)
         if fmt is OrderedSparse:
           mask = mask & (idx < sender)
@@ -286,7 +333,7 @@ class neighbor_list:
       else:                                                      # :960-980
         jj = np.minimum(idx, N - 1)           # OOB gather clamps
         # map_neighbor evaluates d(R_j, R_i) (space.py:494-502)
-        d2 = self.metric_sq(position[jj], position[lo:hi, None, :])
+        d2 = self.metric_sq(position[jj], position[lo:hi, None, :], **self._mkw)
         mask = self._cmp(d2, position.dtype) & (idx < N)
         cs = np.cumsum(mask, axis=1)
         r, c = np.nonzero(mask)
@@ -332,11 +379,12 @@ class neighbor_list:
   # -- public ----------------------------------------------------------------
   def allocate(self, position, extra_capacity=0, **kw):
     """partition.py:1156-1157."""
-    return self._build(position, np.uint8(0), None, extra_capacity, None)
+    return self._build(position, np.uint8(0), None, extra_capacity, None, **kw)
 
-  def needs_rebuild(self, position, neighbors):
+  def needs_rebuild(self, position, neighbors, **kw):
     """partition.py:1146-1154 predicate (strict >)."""
-    d2 = self.metric_sq(position, neighbors.reference_position)
+    mkw = {k: v for k, v in kw.items() if k == 'box'}
+    d2 = self.metric_sq(position, neighbors.reference_position, **mkw)
     t = self.threshold_sq
     if isinstance(t, float):
       t = position.dtype.type(t)
@@ -344,9 +392,20 @@ class neighbor_list:
 
   def update(self, position, neighbors, **kw):
     """partition.py:1159-1160 / 1119-1154."""
-    if self.always_rebuild or self.needs_rebuild(position, neighbors):
+    if 'box' in kw and not self.disable_cell_list:               # :1125-1139
+      if not self.fractional:
+        raise ValueError('Neighbor list cannot accept a box keyword argument if '
+                         'fractional_coordinates is not enabled.')
+      err = neighbors.error
+      if neighbors.use_cell_list:
+        cur = cell_size_fn(1.0, neighbors.cell_size)
+        new = cell_size_fn(1.0, fractional_cell_size(kw['box'], self.cutoff))
+        err = err_update(err, PEC.CELL_SIZE_TOO_SMALL, bool(np.any(new > cur)))
+      err = err_update(err, PEC.MALFORMED_BOX, is_box_valid(kw['box']))
+      neighbors.error = err
+    if self.always_rebuild or self.needs_rebuild(position, neighbors, **kw):
       return self._build(position, neighbors.error, neighbors, 0,
-                         neighbors.max_occupancy)
+                         neighbors.max_occupancy, **kw)
     neighbors.did_rebuild = False
     return neighbors
 

@@ -83,6 +83,55 @@ def periodic(side, wrapped=True):
   return displacement_fn, shift_fn
 
 
+def inverse(box):
+  """space.py:110-121."""
+  box = np.asarray(box)
+  if box.size == 1 or box.ndim == 1:
+    return 1 / box
+  return np.linalg.inv(box)
+
+
+def periodic_general(box, fractional_coordinates=True, wrapped=True):
+  """space.py:332-472.  (Matrix boxes go through einsum, whose summation order XLA does
+  not pin: parity for triclinic boxes is unpinned; diagonal boxes are exact.)"""
+  inv_box = inverse(box)
+
+  def displacement_fn(Ra, Rb, perturbation=None, **kwargs):
+    _box, _inv_box = box, inv_box
+    if 'box' in kwargs:
+      _box = kwargs['box']
+      if not fractional_coordinates:
+        _inv_box = inverse(_box)
+    if 'new_box' in kwargs:
+      _box = kwargs['new_box']
+    if not fractional_coordinates:
+      Ra = raw_transform(_inv_box, Ra)
+      Rb = raw_transform(_inv_box, Rb)
+    dR = periodic_displacement(f32(1.0), pairwise_displacement(Ra, Rb))
+    dR = raw_transform(_box, dR)
+    if perturbation is not None:
+      dR = raw_transform(perturbation, dR)
+    return dR
+
+  def shift_fn(R, dR, **kwargs):
+    if not fractional_coordinates and not wrapped:
+      return R + dR
+    _box, _inv_box = box, inv_box
+    if 'box' in kwargs:
+      _box = kwargs['box']
+      _inv_box = inverse(_box)
+    if 'new_box' in kwargs:
+      _box = kwargs['new_box']
+    dR = raw_transform(_inv_box, dR)
+    if not fractional_coordinates:
+      R = raw_transform(_inv_box, R)
+    R = periodic_shift(f32(1.0), R, dR) if wrapped else R + dR
+    if not fractional_coordinates:
+      R = raw_transform(_box, R)
+    return R
+  return displacement_fn, shift_fn
+
+
 def metric_sq(displacement_fn):
   """partition.py:564-587 for a displacement function."""
   return lambda Ra, Rb, **kw: square_distance(displacement_fn(Ra, Rb, **kw))

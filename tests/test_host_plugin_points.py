@@ -76,8 +76,11 @@ def test_neighbor_list_fns_interface():
   assert allocate is fns.allocate and update is fns.update
   with pytest.raises(ValueError):
     partition.neighbor_list(d, np.float32(20.0), 2.5, 0.3, format='Dense')
-  with pytest.raises(NotImplementedError):
+  with pytest.raises(ValueError):        # fractional coordinates need a periodic_general space
     partition.neighbor_list(d, np.float32(20.0), 2.5, 0.3, fractional_coordinates=True)
+  dg, _ = space.periodic_general(np.float32(20.0))
+  assert isinstance(partition.neighbor_list(dg, np.float32(20.0), 2.5, 0.3, fractional_coordinates=True),
+                    partition.NeighborListFns)
   masked = partition.neighbor_list(d, np.float32(20.0), 2.5, 0.3, custom_mask_function=lambda idx: idx)
   assert isinstance(masked, partition.NeighborListFns)        # served by the post-mask path
   assert partition.is_sparse(partition.OrderedSparse) and not partition.is_sparse(partition.Dense)
