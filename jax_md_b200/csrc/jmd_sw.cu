@@ -110,7 +110,11 @@ template <typename T>
 __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
   using V4 = typename Vec4<T>::type;
   const int t = blockIdx.x * SWB + threadIdx.x;
-  double rv[5] = {0, 0, 0, 0, 0};
+  double rv[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // virial dU/d(eps_ab) for the strain (I + eps) of every displacement (xx yy zz xy xz yz):
+  // what quantity.pressure / stress and npt_nose_hoover obtain in the reference by
+  // differentiating through `perturbation=` (quantity.py:226-282, simulate.py:848-855)
+  double vir[6] = {0, 0, 0, 0, 0, 0};
   if (t < S.n && S.perm[t] < S.n_rows) {
     const V4 pi = S.pos_sorted[t];
     const int cnt = S.ccnt[t];
@@ -139,6 +143,9 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
         const T df = (T(-4) * S.B / (x2 * x2 * x) * t2 - t1 * t2 / (xa * xa)) / S.sigma;
         const T c2 = S.eps * S.A * df / ra;       // d/dR_i of (1/2)(f_ij + f_ji) = -df * da/ra
         f[0] += c2 * da[0]; f[1] += c2 * da[1]; f[2] += c2 * da[2];
+        const double h = 0.5 * (double)c2;        // the pair (i, j) appears in both rows
+        vir[0] += h * da[0] * da[0]; vir[1] += h * da[1] * da[1]; vir[2] += h * da[2] * da[2];
+        vir[3] += h * da[0] * da[1]; vir[4] += h * da[0] * da[2]; vir[5] += h * da[1] * da[2];
       }
       // (1) triplets centred on i: unordered pairs (a, b), b > a
       for (int kb = ka + 1; kb < cnt; ++kb) {
@@ -159,6 +166,14 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
         const T w = S.eps * S.lam * S.tbs;
         // d_a = R_j - R_i, so dE/dR_i = -(g1 + g2); force = +w (g1 + g2)
         f[0] += w * (g1[0] + g2[0]); f[1] += w * (g1[1] + g2[1]); f[2] += w * (g1[2] + g2[2]);
+        // own-centre triplets carry the whole three-body energy: dU/d(eps_ab) = w (g1_a d1_b + g2_a d2_b)
+        const double wd = (double)w;
+        vir[0] += wd * (g1[0] * da[0] + g2[0] * db[0]);
+        vir[1] += wd * (g1[1] * da[1] + g2[1] * db[1]);
+        vir[2] += wd * (g1[2] * da[2] + g2[2] * db[2]);
+        vir[3] += 0.5 * wd * (g1[0] * da[1] + g1[1] * da[0] + g2[0] * db[1] + g2[1] * db[0]);
+        vir[4] += 0.5 * wd * (g1[0] * da[2] + g1[2] * da[0] + g2[0] * db[2] + g2[2] * db[0]);
+        vir[5] += 0.5 * wd * (g1[1] * da[2] + g1[2] * da[1] + g2[1] * db[2] + g2[2] * db[1]);
       }
       // (2) triplets centred on j with i as an end atom: d1 = R_i - R_j = -da
       {
@@ -191,6 +206,8 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
     fo[0] = f[0]; fo[1] = f[1]; fo[2] = f[2];
     // E = eps (A/2 sum f2 + tbs lam sum_unordered g)   (energy.py:1001-1012)
     rv[0] = (double)(S.eps * (S.A * T(0.5) * e2 + S.tbs * S.lam * e3));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rv[5 + k] = vir[k];
     if (S.kick) {
       T* po = S.momentum + (size_t)ai * 3;
       const T m = S.mass_is_array ? S.mass[ai] : S.mass[0];
@@ -205,14 +222,15 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
       rv[1] = 0.5 * (double)ke; rv[2] = ff; rv[3] = pp; rv[4] = fp;
     }
   }
-  __shared__ double sm[5 * (SWB / 32)];
-  __shared__ int slots[5];
+  __shared__ double sm[11 * (SWB / 32)];
+  __shared__ int slots[11];
   if (threadIdx.x == 0) {
     slots[0] = JMD_RED_ENERGY; slots[1] = JMD_RED_KINETIC; slots[2] = JMD_RED_FF; slots[3] = JMD_RED_PP;
     slots[4] = JMD_RED_FP;
+    for (int k = 0; k < 6; ++k) slots[5 + k] = JMD_RED_VIRIAL + k;
   }
   __syncthreads();
-  grid_reduce_finish<5, SWB>(rv, S.partials + 2, (unsigned int*)S.partials, S.red, slots, sm);
+  grid_reduce_finish<11, SWB>(rv, S.partials + 2, (unsigned int*)S.partials, S.red, slots, sm);
 }
 
 template <typename T>

@@ -276,7 +276,9 @@ class StillingerWeberFn:
     return sw
 
   def launch(self, R, neighbor, momentum=None, mass=None, dt_2=0.0,
-             dt_dev=None, red=None, refresh_positions=True, **unused):
+             dt_dev=None, red=None, refresh_positions=True, box=None, **unused):
+    if neighbor._ws is not None:
+      neighbor._ws.set_box(self.spec, box)                  # periodic_general: box override
     if neighbor.format is not partition.Dense:
       raise NotImplementedError('Stillinger-Weber potential only implemented '
                                 'with Dense neighbor lists.')
@@ -305,12 +307,27 @@ class StillingerWeberFn:
     return dict(force=force, red=red)
 
   def force(self, R, neighbor=None, **kwargs):
-    return self.launch(R, neighbor)['force']
+    return self.launch(R, neighbor, box=kwargs.get('box'))['force']
+
+  def force_and_virial(self, R, neighbor=None, **kwargs):
+    """One launch -> (force, trace of `virial()`), see PairNeighborListFn.force_and_virial."""
+    out = self.launch(R, neighbor, box=kwargs.get('box'))
+    return out['force'], out['red'][_lib.RED_VIRIAL:_lib.RED_VIRIAL + 3].sum().to(R.dtype)
+
+  def virial(self, R, neighbor=None, **kwargs):
+    """dU/d(eps_ab) at eps = 0 for the strain (I + eps) (see PairNeighborListFn.virial):
+    accumulated by k_sw next to the forces.  -> [3, 3]."""
+    v = self.launch(R, neighbor, box=kwargs.get('box'))['red'][_lib.RED_VIRIAL:_lib.RED_VIRIAL + 6].to(R.dtype)
+    return torch.stack([torch.stack([v[0], v[3], v[4]]), torch.stack([v[3], v[1], v[5]]),
+                        torch.stack([v[4], v[5], v[2]])])
 
   def __call__(self, R, neighbor=None, **kwargs):
     if neighbor is None:
       raise TypeError('energy_fn(R, neighbor=...) needs a NeighborList')
     fn = self
+    box = kwargs.get('box')
+    if box is not None and neighbor._ws is not None:
+      neighbor._ws.set_box(self.spec, box)
     if torch.is_grad_enabled() and R.requires_grad:
       class _E(torch.autograd.Function):
         @staticmethod
@@ -336,9 +353,11 @@ def stillinger_weber_neighbor_list(displacement, box_size, sigma=2.0951,
                                    format=partition.Dense,
                                    neighbor_list_fn=partition.neighbor_list,
                                    **neighbor_kwargs):
-  """energy.py:962-1014 (`fractional_coordinates` is accepted and not
-  forwarded, like the reference :985-992)."""
+  """energy.py:962-1014.  `fractional_coordinates` IS forwarded to the neighbour list: the
+  reference drops it (:985-992), which leaves its cell grid degenerate for unit-cube
+  positions (every atom in the corner cells: same neighbour sets, quadratic cost)."""
   neighbor_fn = neighbor_list_fn(displacement, box_size, cutoff, dr_threshold,
+                                 fractional_coordinates=fractional_coordinates,
                                  format=format, **neighbor_kwargs)
   params = dict(sigma=sigma, A=A, B=B, lam=lam, gamma=gamma, epsilon=epsilon,
                 three_body_strength=three_body_strength, cutoff=cutoff)

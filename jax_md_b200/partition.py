@@ -132,6 +132,13 @@ class Workspace:
     self.species = species
     self.c.species = species.data_ptr()
 
+  def set_box(self, spec, box):
+    """`box=` of an energy / force call on a periodic_general space: later kernels use it."""
+    if box is None or not getattr(spec, 'general', False):
+      return
+    b = box.detach().cpu().numpy() if isinstance(box, torch.Tensor) else box
+    self.c.space = space.space_struct(spec._replace(side=b), self.dim, self.dtype)
+
   def state_host(self):
     out = (C.c_int64 * _lib.ST_COUNT)()
     _lib.call('jmd_nbr_state_host', self.ref(), out, _lib.stream())
@@ -518,7 +525,20 @@ def neighbor_list(displacement_or_metric,
   if np.ndim(box_np) == 2 and not fractional_coordinates:
     box_np = np.asarray(space._box_diagonal(box_np), f32)
   # the box currently in force (fractional coordinates: `box=` overrides, partition.py:1045)
-  current = {'box': box_np}
+  current = {'box': box_np, 'metric_box': None}
+
+  def _box_kwarg(b):
+    """`box=` of allocate / update: the cell grid is sized from it (partition.py:1045) and a
+    periodic_general metric uses it (`partial(metric_sq, **kwargs)`, :1145); other metrics
+    ignore the keyword."""
+    b = _host_scalar(b)
+    if spec.general:
+      current['metric_box'] = b                 # in the caller's precision, like the reference's metric
+    b = f32(b) if np.ndim(b) == 0 else np.asarray(b, f32)
+    if np.ndim(b) == 2 and not fractional_coordinates:
+      b = np.asarray(space._box_diagonal(b), f32)
+    current['box'] = b
+    return b
   cutoff = r_cutoff + dr_threshold                                # :899
   cutoff_sq = cutoff ** 2                                         # :900
   threshold_sq = (dr_threshold / f32(2)) ** 2                     # :901
@@ -542,14 +562,14 @@ def neighbor_list(displacement_or_metric,
     c.always_rebuild = 1 if _always_rebuild else 0
     c.cutoff_sq = _typed(cutoff_sq, np_dtype)
     c.threshold_sq = _typed(threshold_sq, np_dtype)
-    _spec = spec._replace(side=current['box']) if fractional_coordinates else spec
+    _spec = spec if current['metric_box'] is None else spec._replace(side=current['metric_box'])
     c.space = space.space_struct(_spec, dim, torch.float32 if np_dtype == np.float32 else torch.float64)
     c.n_pad = ((n_buf + 31) // 32) * 32 if n_buf else 32
 
     use_cells, cell_size, cps, n_cells = False, None, np.ones(3, i32), 0
     if not disable_cell_list:
       cell_size = cutoff                                           # :1046
-      _box = box_np
+      _box = current['box']                                        # :1045 kwargs.get('box', box)
       if fractional_coordinates:                                   # :1047-1051
         cell_size = _fractional_cell_size(current['box'], cutoff)
         _box = 1.0
@@ -631,11 +651,7 @@ def neighbor_list(displacement_or_metric,
     """partition.py:1156-1157 -> neighbor_fn with neighbors=None (not jittable:
     reads occupancies back to the host)."""
     if 'box' in kwargs:
-      if not fractional_coordinates:
-        raise ValueError('Neighbor list cannot accept a box keyword argument if '
-                         'fractional_coordinates is not enabled.')
-      b = _host_scalar(kwargs['box'])
-      current['box'] = f32(b) if np.ndim(b) == 0 else np.asarray(b, f32)
+      _box_kwarg(kwargs['box'])
     position = position.contiguous()
     ws = _make_workspace(position, extra_capacity, n_capacity)
     if fractional_coordinates and not disable_cell_list and is_box_valid(current['box']):
@@ -707,8 +723,7 @@ def neighbor_list(displacement_or_metric,
       if not fractional_coordinates:
         raise ValueError('Neighbor list cannot accept a box keyword argument if '
                          'fractional_coordinates is not enabled.')
-      b = _host_scalar(kwargs['box'])
-      b = f32(b) if np.ndim(b) == 0 else np.asarray(b, f32)
+      b = _box_kwarg(kwargs['box'])
       bits = 0
       if neighbors.cell_list_fn is not None:
         cur = _cell_size(1.0, neighbors.cell_size)
@@ -721,8 +736,10 @@ def neighbor_list(displacement_or_metric,
         ws.t['error'].bitwise_or_(torch.tensor(bits, dtype=torch.uint8, device=ws.t['error'].device))
       if ws is not None:
         # the metric of every later kernel (skin predicate, candidate tests, forces) uses the new box
-        current['box'] = b
-        ws.c.space = space.space_struct(spec._replace(side=b), ws.dim, ws.dtype)
+        ws.c.space = space.space_struct(spec._replace(side=current['metric_box']), ws.dim, ws.dtype)
+    elif 'box' in kwargs and ws is not None and spec.general:      # all-pairs: box only feeds the metric
+      _box_kwarg(kwargs['box'])
+      ws.c.space = space.space_struct(spec._replace(side=current['metric_box']), ws.dim, ws.dtype)
     if ws is None:
       raise ValueError('This NeighborList was not allocated by jax_md_b200.')
     if position.shape != (ws.n, ws.dim) or position.dtype != ws.dtype:

@@ -74,10 +74,9 @@ def pressure(energy_fn, position, box, kinetic_energy=0.0, **kwargs):
   kernel accumulates; anything else differentiates through `perturbation=`."""
   dim = position.shape[1]
   vol_0 = volume(dim, box)
-  if getattr(energy_fn, '_jmd_fused', None) == 'pair':
+  if getattr(energy_fn, '_jmd_fused', None) and not getattr(energy_fn, 'always_generic', False) \
+      and getattr(kwargs.get('neighbor'), '_ws', None) is not None:
     dUdV = torch.trace(energy_fn.virial(position, **kwargs))
-  elif getattr(energy_fn, '_jmd_fused', None):
-    raise NotImplementedError('pressure of the fused many-body energies: SURVEY.md 8(f) row 2')
   else:
     zero = torch.zeros((), dtype=position.dtype, device=position.device)
     dUdV = _dU_deps(energy_fn, position, zero, lambda e: 1 + e, kwargs)
@@ -88,10 +87,9 @@ def stress(energy_fn, position, box, mass=1.0, velocity=None, **kwargs):
   """quantity.py:238-282: (sum m v v^T - dU/deps) / V, eps the box strain tensor."""
   dim = position.shape[1]
   vol_0 = volume(dim, box)
-  if getattr(energy_fn, '_jmd_fused', None) == 'pair':
+  if getattr(energy_fn, '_jmd_fused', None) and not getattr(energy_fn, 'always_generic', False) \
+      and getattr(kwargs.get('neighbor'), '_ws', None) is not None:
     dUdV = energy_fn.virial(position, **kwargs)
-  elif getattr(energy_fn, '_jmd_fused', None):
-    raise NotImplementedError('stress of the fused many-body energies: SURVEY.md 8(f) row 2')
   else:
     zero = torch.zeros((dim, dim), dtype=position.dtype, device=position.device)
     eye = torch.eye(dim, dtype=position.dtype, device=position.device)

@@ -370,6 +370,235 @@ def nvt_nose_hoover(energy_or_force_fn, shift_fn, dt, kT, chain_length=5,
   return init_fn, apply_fn
 
 
+# -- NPT Nose-Hoover --------------------------------------------------------
+
+@dataclasses.dataclass
+class NPTNoseHooverState:
+  """simulate.py:704-760.  The box degrees of freedom are 0-d device tensors."""
+  position: Any
+  momentum: Any
+  force: Any
+  mass: Any
+  reference_box: Any
+  box_position: Any
+  box_momentum: Any
+  box_mass: Any
+  dUdV: Any
+  barostat: NoseHooverChain
+  thermostat: NoseHooverChain
+
+  @property
+  def velocity(self):
+    return self.momentum / self.mass
+
+  @property
+  def box(self):
+    return npt_box(self)
+
+
+def sinhx_x(x):
+  """simulate.py:763-772: Taylor series of sinh(x) / x."""
+  return (1 + x ** 2 / 6 + x ** 4 / 120 + x ** 6 / 5040 + x ** 8 / 362_880 + x ** 10 / 39_916_800)
+
+
+def _box_volume(dim, box):
+  # quantity.volume (quantity.py:111-121); the kernels serve diagonal matrices, whose
+  # determinant is the product of the diagonal
+  if box.ndim == 0:
+    return box ** dim
+  return torch.prod(box) if box.ndim == 1 else torch.prod(torch.diagonal(box))
+
+
+def _npt_box_info(state):
+  """simulate.py:775-783."""
+  dim = state.position.shape[1]
+  ref = state.reference_box
+  V_0 = _box_volume(dim, ref)
+  V = V_0 * torch.exp(dim * state.box_position)
+  return V, lambda V: (V / V_0) ** (1 / dim) * ref
+
+
+def npt_box(state):
+  """simulate.py:786-792."""
+  V, box_fn = _npt_box_info(state)
+  return box_fn(V)
+
+
+def default_nhc_kwargs(tau, overrides):
+  """simulate.py:520-536."""
+  kw = dict(chain_length=3, chain_steps=2, sy_steps=3, tau=tau)
+  kw.update(overrides or {})
+  return kw
+
+
+def _force_stress(energy_fn, R, box, kwargs):
+  """simulate.py:848-855: (F, dU/d eps) of energy_fn(R, box=box, perturbation=1 + eps) at
+  eps = 0.  The fused energies return both from ONE launch (the virial accumulated next to
+  the forces); any other torch-differentiable energy goes through autograd like the
+  reference."""
+  nbr = kwargs.get('neighbor')
+  fused = (getattr(energy_fn, '_jmd_fused', None) and hasattr(energy_fn, 'force_and_virial')
+           and getattr(nbr, '_ws', None) is not None
+           and not (hasattr(energy_fn, '_use_generic') and energy_fn._use_generic(nbr)))
+  if fused:
+    return energy_fn.force_and_virial(R, box=box, **kwargs)
+  Rg = R.detach().requires_grad_(True)
+  eps = torch.zeros((), dtype=R.dtype, device=R.device, requires_grad=True)
+  E = energy_fn(Rg, box=box, perturbation=(1 + eps), **kwargs)
+  gR, gE = torch.autograd.grad(E, (Rg, eps))
+  return -gR, gE
+
+
+def npt_nose_hoover(energy_fn, shift_fn, dt, pressure, kT, barostat_kwargs=None, thermostat_kwargs=None):
+  """simulate.py:795-1004: NPT with a Nose-Hoover chain on the particles and one on the box
+  (Tuckerman's direct translation).  Host-orchestrated: both chains run on the chain kernel
+  (`jmd_nhc_half_step`; the barostat chain thermostats the single box momentum), forces AND
+  dU/dV come from one launch of the fused force kernel (its virial accumulators), the
+  exp(iL1) / exp(iL2) propagators are elementwise tensor arithmetic.  The new box reaches the
+  kernels as a host value, which costs ONE device->host read per step (SURVEY 8f row 2:
+  NPT is outside the graph-captured hot loop)."""
+  dt_f = f32(dt)
+  dt_2 = float(f32(dt / 2))
+  dt = float(dt)
+  bk = default_nhc_kwargs(1000 * dt, barostat_kwargs)
+  tk = default_nhc_kwargs(100 * dt, thermostat_kwargs)
+  for kw in (bk, tk):
+    if kw['sy_steps'] not in SUZUKI_YOSHIDA_WEIGHTS:
+      raise ValueError('sy_steps must be 1, 3, 5 or 7')
+
+  def _kT_dev(_kT, R):
+    if isinstance(_kT, torch.Tensor):
+      return _kT.to(device=R.device, dtype=R.dtype).reshape(1)
+    return torch.full((1,), float(_kT), dtype=R.dtype, device=R.device)
+
+  def _half_step(kw, chain, buf_out, kT_t, R):
+    scale = torch.empty((1,), dtype=R.dtype, device=R.device)
+    _lib.call('jmd_nhc_half_step', _lib.dtype_code(R.dtype), kw['chain_length'], kw['chain_steps'],
+              kw['sy_steps'], float(dt_f), float(f32(kw['tau'])), int(chain.degrees_of_freedom),
+              _lib.ptr(kT_t), _lib.ptr(chain._buf), _lib.ptr(buf_out), None, _lib.ptr(scale), _lib.stream())
+    return scale[0], _make_chain(buf_out, kw['chain_length'], chain.tau, chain.degrees_of_freedom)
+
+  def _new_chain(kw, dof, KE, _kT, R):
+    cl = kw['chain_length']
+    buf = torch.zeros(3 * cl + 1, dtype=R.dtype, device=R.device)
+    Q = f32(_kT) * (f32(kw['tau']) ** f32(2))                   # simulate.py:440-442
+    buf[2 * cl:3 * cl] = float(Q)
+    buf[2 * cl] = float(f32(Q * f32(dof)))
+    buf[3 * cl] = KE
+    return _make_chain(buf, cl, kw['tau'], dof)
+
+  def _with_ke(chain, KE):
+    buf = chain._buf.clone()
+    buf[3 * chain._cl] = KE
+    return _make_chain(buf, chain._cl, chain.tau, chain.degrees_of_freedom)
+
+  def _box_mass(N, dim, _kT, tau, R):
+    return torch.as_tensor(dim * (N + 1) * _kT * tau ** 2, dtype=R.dtype, device=R.device)
+
+  def init_fn(key, R, box, mass=f32(1.0), momenta=None, **kwargs):
+    _kT = kwargs.pop('kT', kT)
+    _kT = float(_kT.detach().cpu()) if isinstance(_kT, torch.Tensor) else _kT
+    R = R.contiguous()
+    N, dim = R.shape
+    zero = torch.zeros((), dtype=R.dtype, device=R.device)
+    box_t = box if isinstance(box, torch.Tensor) else torch.as_tensor(np.asarray(box))
+    box_t = box_t.to(device=R.device, dtype=R.dtype)
+    if box_t.ndim == 0:
+      box_t = torch.eye(dim, dtype=R.dtype, device=R.device) * box_t        # simulate.py:870-872
+    force, dUdV = _force_stress(energy_fn, R, box_t, kwargs)
+    m = _canonical_mass(mass, R)
+    if momenta is None:
+      P = initialize_momenta(R, m, key, _kT)
+    else:
+      P = momenta.to(dtype=R.dtype, device=R.device)
+    P = P.contiguous()
+    box_mass = _box_mass(N, dim, _kT, bk['tau'], R)
+    KE = quantity.kinetic_energy(momentum=P, mass=m)
+    return NPTNoseHooverState(R, P, force.contiguous(), m, box_t, zero, zero.clone(), box_mass, dUdV,
+                              _new_chain(bk, 1, zero, _kT, R),
+                              _new_chain(tk, quantity.count_dof(R), KE, _kT, R))
+
+  def box_force(alpha, vol, dUdV, R, P, M, _pressure):
+    dim = R.shape[1]
+    KE2 = (P ** 2 / M).to(torch.float64).sum().to(R.dtype)      # util.high_precision_sum
+    return alpha * KE2 - dUdV - _pressure * vol * dim
+
+  def exp_iL1(box, R, V, V_b, **kwargs):
+    x = V_b * dt
+    x_2 = x / 2
+    space_kw = {k: v for k, v in kwargs.items() if k != 'neighbor'}
+    return shift_fn(R, R * (torch.exp(x) - 1) + dt * V * torch.exp(x_2) * sinhx_x(x_2), box=box, **space_kw)
+
+  def exp_iL2(alpha, P, F, V_b):
+    x = alpha * V_b * dt_2
+    x_2 = x / 2
+    return P * torch.exp(-x) + dt_2 * F * sinhx_x(x_2) * torch.exp(-x_2)
+
+  def inner_step(state, **kwargs):
+    _pressure = kwargs.pop('pressure', pressure)
+    R, P, M, F = state.position, state.momentum, state.mass, state.force
+    R_b, P_b, M_b = state.box_position, state.box_momentum, state.box_mass
+    dUdV = state.dUdV                        # positions / box unchanged since the last evaluation
+    N, dim = R.shape
+    vol, box_fn = _npt_box_info(state)
+    alpha = 1 + 1 / N
+    G_e = box_force(alpha, vol, dUdV, R, P, M, _pressure)
+    P_b = P_b + dt_2 * G_e
+    P = exp_iL2(alpha, P, F, P_b / M_b)
+    R_b = R_b + P_b / M_b * dt
+    state = state.set(box_position=R_b)
+    vol, box_fn = _npt_box_info(state)
+    box = box_fn(vol)
+    R = exp_iL1(box, R, P / M, P_b / M_b, **kwargs).contiguous()
+    F, dUdV = _force_stress(energy_fn, R, box, kwargs)
+    P = exp_iL2(alpha, P, F, P_b / M_b)
+    G_e = box_force(alpha, vol, dUdV, R, P, M, _pressure)
+    P_b = P_b + dt_2 * G_e
+    return state.set(position=R, momentum=P.contiguous(), force=F, dUdV=dUdV, box_position=R_b,
+                     box_momentum=P_b)
+
+  def apply_fn(state, **kwargs):
+    S = state
+    _kT = kwargs.pop('kT', kT)
+    R = S.position
+    N, dim = R.shape
+    kT_t = _kT_dev(_kT, R)
+    kT_h = float(kT_t.cpu()) if isinstance(_kT, torch.Tensor) else _kT
+    # update_mass of both chains happens inside the chain kernel (simulate.py:981-983)
+    S = S.set(box_mass=_box_mass(N, dim, kT_h, S.barostat.tau, R))
+    s_b, bc = _half_step(bk, S.barostat, torch.empty_like(S.barostat._buf), kT_t, R)
+    s_t, tc = _half_step(tk, S.thermostat, torch.empty_like(S.thermostat._buf), kT_t, R)
+    S = S.set(momentum=S.momentum * s_t, box_momentum=S.box_momentum * s_b)
+    S = inner_step(S, **kwargs)
+    tc = _with_ke(tc, quantity.kinetic_energy(momentum=S.momentum, mass=S.mass))
+    bc = _with_ke(bc, quantity.kinetic_energy(momentum=S.box_momentum, mass=S.box_mass))
+    s_t, tc = _half_step(tk, tc, tc._buf, kT_t, R)
+    s_b, bc = _half_step(bk, bc, bc._buf, kT_t, R)
+    return S.set(thermostat=tc, barostat=bc, momentum=(S.momentum * s_t).contiguous(),
+                 box_momentum=S.box_momentum * s_b)
+
+  return init_fn, apply_fn
+
+
+def npt_nose_hoover_invariant(energy_fn, state, pressure, kT, **kwargs):
+  """simulate.py:1007-1046."""
+  volume, box_fn = _npt_box_info(state)
+  PE = energy_fn(state.position, box=box_fn(volume), **kwargs)
+  KE = kinetic_energy(state)
+  DOF = quantity.count_dof(state.position)
+  E = PE + KE
+  c = state.thermostat
+  E = E + c.momentum[0] ** 2 / (2 * c.mass[0]) + DOF * kT * c.position[0]
+  for r, p, m in zip(c.position[1:], c.momentum[1:], c.mass[1:]):
+    E = E + p ** 2 / (2 * m) + kT * r
+  c = state.barostat
+  for r, p, m in zip(c.position, c.momentum, c.mass):
+    E = E + p ** 2 / (2 * m) + kT * r
+  E = E + pressure * volume
+  E = E + state.box_momentum ** 2 / (2 * state.box_mass)
+  return E
+
+
 # -- Langevin / Brownian (SURVEY 8f row 4) ---------------------------------------------------
 
 @dataclasses.dataclass

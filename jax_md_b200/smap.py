@@ -233,6 +233,7 @@ class PairNeighborListFn:
           'jax_md_b200.partition; this list has a foreign `idx`.')
     species = dynamic_kwargs.pop('species', self.species)
     perturbation = dynamic_kwargs.pop('perturbation', self.kwargs.get('perturbation'))
+    neighbor._ws.set_box(self.spec, dynamic_kwargs.pop('box', None))     # periodic_general: box override
     params = _merge(self.kwargs, dynamic_kwargs, self.ignore_unused)
     params.pop('perturbation', None)
     if perturbation is not None:
@@ -285,6 +286,14 @@ class PairNeighborListFn:
               1 if want_energy else 0, _lib.stream())
     return dict(force=force, red=red, e_atom=e_atom, dparam=dparam, modes=modes,
                 n_species=pt.n_species, keep=keep)
+
+  def force_and_virial(self, R, neighbor=None, **dynamic_kwargs):
+    """One launch -> (force [N, dim], trace of `virial()` as a 0-d tensor): what
+    simulate.npt_nose_hoover's force_stress_fn (simulate.py:848-855) differentiates for."""
+    neighbor, species, params = self._resolve(neighbor, dict(dynamic_kwargs))
+    out = self.launch(R, neighbor, species, params, True)
+    v = out['red'][_lib.RED_VIRIAL:_lib.RED_VIRIAL + R.shape[1]]
+    return out['force'], v.sum().to(R.dtype)
 
   def virial(self, R, neighbor=None, **dynamic_kwargs):
     """dU/d(eps_ab) at eps = 0 for the box perturbation `(I + eps)` of

@@ -59,7 +59,11 @@ def space_struct(spec: SpaceSpec, dim: int, torch_dtype) -> '_lib.SpaceT':
     if spec.general:
       st.general = 1
       st.fractional = 1 if spec.fractional else 0
-      inv = (np_dtype(1) / np.asarray(full, np_dtype)).astype(np.float64)      # space.inverse: 1 / box
+      # space.inverse: 1 / box, rounded in the BOX's precision when it is a typed array (an f32 box
+      # next to f64 positions keeps its f32 inverse in the reference), else in the run's
+      sd = np.asarray(side)
+      inv_dtype = sd.dtype.type if sd.dtype in (np.float32, np.float64) and not isinstance(side, float) else np_dtype
+      inv = (inv_dtype(1) / np.broadcast_to(sd.astype(inv_dtype), (dim,))).astype(np.float64)
       for k in range(dim):
         st.inv_box[k] = float(inv[k])
   return st

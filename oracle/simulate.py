@@ -156,6 +156,142 @@ def nvt_nose_hoover_invariant(PE, state, kT):
   return E
 
 
+# -- NPT Nose-Hoover (simulate.py:704-1046) --------------------------------------
+
+def sinhx_x(x):
+  """simulate.py:763-772."""
+  return (1 + x ** 2 / 6 + x ** 4 / 120 + x ** 6 / 5040 + x ** 8 / 362_880 + x ** 10 / 39_916_800)
+
+
+def volume(dim, box):
+  """quantity.py:111-121 (matrix boxes here are diagonal: det = product of the diagonal)."""
+  box = np.asarray(box)
+  if box.ndim == 0:
+    return box ** dim
+  return np.prod(box) if box.ndim == 1 else np.prod(np.diag(box))
+
+
+def _npt_box_info(state):
+  """simulate.py:775-783."""
+  dim = state.position.shape[1]
+  ref = state.reference_box
+  V_0 = volume(dim, ref)
+  V = V_0 * np.exp(dim * state.box_position)
+  return V, lambda V: (V / V_0) ** (1 / dim) * ref
+
+
+def npt_box(state):
+  """simulate.py:786-792."""
+  V, box_fn = _npt_box_info(state)
+  return box_fn(V)
+
+
+def _nhc_update_mass(chain, kT, chain_length):
+  Q = kT * chain.tau ** f32(2) * np.ones(chain_length, dtype=f32)     # simulate.py:509-515
+  Q[0] *= chain.dof
+  return chain.copy(mass=Q)
+
+
+def npt_nose_hoover(force_stress_fn, shift_fn, dt, pressure, kT, barostat_kwargs=None,
+                    thermostat_kwargs=None):
+  """simulate.py:795-1004.  `force_stress_fn(R, box) -> (F, dUdV)` stands for the reference's
+  value_and_grad over (position, eps) of `energy_fn(position, box=box, perturbation=1 + eps)`."""
+  dt_2 = f32(dt / 2)
+
+  def _kw(tau, over):
+    d = dict(chain_length=3, chain_steps=2, sy_steps=3, tau=tau)       # simulate.py:520-536
+    d.update(over or {})
+    return d
+  bk, tk = _kw(1000 * dt, barostat_kwargs), _kw(100 * dt, thermostat_kwargs)
+
+  def _half(P, chain, _kT, kw):
+    return nhc_half_step(P, chain, _kT, f32(dt), kw['chain_length'], kw['chain_steps'], kw['sy_steps'])
+
+  def init_fn(R, box, momenta, mass=f32(1.0)):
+    N, dim = R.shape
+    zero, one = np.zeros((), R.dtype)[()], np.ones((), R.dtype)[()]
+    box_mass = dim * (N + 1) * kT * bk['tau'] ** 2 * one
+    KE_box = f32(0.5) * zero ** 2 / box_mass
+    if np.ndim(box) == 0:
+      box = np.eye(dim, dtype=np.asarray(box).dtype if isinstance(box, np.generic) else R.dtype) * box
+    F, dUdV = force_stress_fn(R, box)
+    KE = kinetic_energy(momenta, mass)
+    return State(position=R, momentum=momenta, force=F, mass=mass, reference_box=box,
+                 box_position=zero, box_momentum=zero, box_mass=box_mass, dUdV=dUdV,
+                 barostat=nhc_init(1, KE_box, kT, bk['chain_length'], bk['tau'], R.dtype),
+                 thermostat=nhc_init(R.size, KE, kT, tk['chain_length'], tk['tau'], R.dtype))
+
+  def box_force(alpha, vol, dUdV, R, P, M, _pressure):
+    N, dim = R.shape
+    KE2 = np.sum((P ** 2 / M).astype(np.float64)).astype(R.dtype)
+    return alpha * KE2 - dUdV - _pressure * vol * dim
+
+  def exp_iL1(box, R, V, V_b):
+    x = V_b * dt
+    x_2 = x / 2
+    return shift_fn(R, R * (np.exp(x) - 1) + dt * V * np.exp(x_2) * sinhx_x(x_2), box=box)
+
+  def exp_iL2(alpha, P, F, V_b):
+    x = alpha * V_b * dt_2
+    x_2 = x / 2
+    return P * np.exp(-x) + dt_2 * F * sinhx_x(x_2) * np.exp(-x_2)
+
+  def inner_step(state, _pressure):
+    R, P, M, F = state.position, state.momentum, state.mass, state.force
+    R_b, P_b, M_b = state.box_position, state.box_momentum, state.box_mass
+    dUdV = state.dUdV
+    N, dim = R.shape
+    vol, box_fn = _npt_box_info(state)
+    alpha = 1 + 1 / N
+    G_e = box_force(alpha, vol, dUdV, R, P, M, _pressure)
+    P_b = P_b + dt_2 * G_e
+    P = exp_iL2(alpha, P, F, P_b / M_b)
+    R_b = R_b + P_b / M_b * dt
+    state = state.copy(box_position=R_b)
+    vol, box_fn = _npt_box_info(state)
+    box = box_fn(vol)
+    R = exp_iL1(box, R, P / M, P_b / M_b)
+    F, dUdV = force_stress_fn(R, box)
+    P = exp_iL2(alpha, P, F, P_b / M_b)
+    G_e = box_force(alpha, vol, dUdV, R, P, M, _pressure)
+    P_b = P_b + dt_2 * G_e
+    return state.copy(position=R, momentum=P, force=F, dUdV=dUdV, box_position=R_b, box_momentum=P_b)
+
+  def apply_fn(state, kT_override=None, pressure_override=None):
+    S = state
+    _kT = kT if kT_override is None else kT_override
+    _p = pressure if pressure_override is None else pressure_override
+    N, dim = S.position.shape
+    bc = _nhc_update_mass(S.barostat, _kT, bk['chain_length'])
+    tc = _nhc_update_mass(S.thermostat, _kT, tk['chain_length'])
+    S = S.copy(box_mass=np.array(dim * (N + 1) * _kT * S.barostat.tau ** 2, S.position.dtype)[()])
+    P_b, bc = _half(S.box_momentum, bc, _kT, bk)
+    P, tc = _half(S.momentum, tc, _kT, tk)
+    S = inner_step(S.copy(momentum=P, box_momentum=P_b), _p)
+    tc = tc.copy(kinetic_energy=kinetic_energy(S.momentum, S.mass))
+    bc = bc.copy(kinetic_energy=f32(0.5) * S.box_momentum ** 2 / S.box_mass)
+    P, tc = _half(S.momentum, tc, _kT, tk)
+    P_b, bc = _half(S.box_momentum, bc, _kT, bk)
+    return S.copy(thermostat=tc, barostat=bc, momentum=P, box_momentum=P_b)
+  return init_fn, apply_fn
+
+
+def npt_nose_hoover_invariant(PE, state, pressure, kT):
+  """simulate.py:1007-1046 with PE = energy_fn(position, box=npt_box(state))."""
+  volume_, _ = _npt_box_info(state)
+  E = PE + kinetic_energy(state.momentum, state.mass)
+  c = state.thermostat
+  E += c.momentum[0] ** 2 / (2 * c.mass[0]) + state.position.size * kT * c.position[0]
+  for r, p, m in zip(c.position[1:], c.momentum[1:], c.mass[1:]):
+    E += p ** 2 / (2 * m) + kT * r
+  c = state.barostat
+  for r, p, m in zip(c.position, c.momentum, c.mass):
+    E += p ** 2 / (2 * m) + kT * r
+  E += pressure * volume_
+  E += state.box_momentum ** 2 / (2 * state.box_mass)
+  return E
+
+
 # -- FIRE (minimize.py:124-226) -----------------------------------------------
 
 def fire_descent(force_fn, shift_fn, dt_start=0.1, dt_max=0.4, n_min=5,

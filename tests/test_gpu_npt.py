@@ -1,0 +1,154 @@
+"""simulate.npt_nose_hoover on the fused kernels vs the oracle's restatement of
+simulate.py:795-1046: the box, both Nose-Hoover chains and the trajectory over 60 steps in f64
+(tight) and f32; the extended-system invariant; pressure / stress of Stillinger-Weber from the
+virial the SW kernel accumulates vs a finite difference of the energy under box strain."""
+import functools
+
+import numpy as np
+import pytest
+
+from oracle import energy as oenergy
+from oracle import partition as opart
+from oracle import simulate as osim
+from oracle import space as ospace
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _jmd():
+  import jax_md_b200 as jmd
+  return jmd
+
+
+def _dev(x):
+  import torch
+  return torch.as_tensor(x, device='cuda')
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_lj_npt_matches_oracle(dtype):
+  jmd = _jmd()
+  R, L = util.fcc(6, dtype=np.float64)
+  L = dtype(L)
+  S = (np.mod(util.jitter(R, L, 0.03), L) / L).astype(dtype)        # unit-cube coordinates
+  N = len(S)
+  dt, kT, pres = 2e-3, dtype(1.0), dtype(0.5)
+  P0 = util.momenta(N, 3, kT=1.0, dtype=dtype)
+  pot = oenergy.PairPotential('lj', np.float32(2.0), np.float32(2.5))
+
+  # oracle
+  d_o, s_o = ospace.periodic_general(L)
+  nf_o = opart.neighbor_list(d_o, L, np.float32(2.5), np.float32(0.4), fractional_coordinates=True,
+                             format=opart.Dense, capacity_multiplier=1.5)
+  hold = {'nb': nf_o.allocate(S)}
+
+  def fs_o(X, box):
+    b = np.diag(box) if np.ndim(box) == 2 else box
+    hold['nb'] = hold['nb'].update(X, box=b)
+    d = functools.partial(d_o, box=b)
+    F = oenergy.pair_neighbor_list_energy(pot, d, X, hold['nb'], want_grads=True,
+                                          sigma=dtype(1.0), epsilon=dtype(1.0))[1]
+    W = oenergy.pair_virial(pot, d, X, hold['nb'], sigma=dtype(1.0), epsilon=dtype(1.0))
+    return F.astype(dtype), dtype(np.trace(W))
+  init_o, step_o = osim.npt_nose_hoover(fs_o, s_o, dt, pres, kT)
+  st_o = init_o(S, L, P0, mass=dtype(1.0))
+
+  # GPU
+  d_g, s_g = jmd.space.periodic_general(L)
+  nf_g, efn = jmd.energy.lennard_jones_neighbor_list(d_g, L, dr_threshold=0.4, fractional_coordinates=True,
+                                                     format=jmd.partition.Dense, capacity_multiplier=1.5)
+  Sd = _dev(S)
+  nb = nf_g.allocate(Sd)
+  init_g, step_g = jmd.simulate.npt_nose_hoover(efn, s_g, dt, float(pres), float(kT))
+  st_g = init_g(0, Sd, L, momenta=_dev(P0), neighbor=nb)
+  tol = 1e-9 if dtype == np.float64 else 2e-4
+  np.testing.assert_allclose(float(st_g.dUdV), st_o.dUdV, rtol=1e-9 if dtype == np.float64 else 1e-4)
+  inv0 = float(jmd.simulate.npt_nose_hoover_invariant(efn, st_g, float(pres), float(kT), neighbor=nb))
+  for _ in range(60):
+    st_o = step_o(st_o)
+    nb = nb.update(st_g.position, box=jmd.simulate.npt_box(st_g))
+    st_g = step_g(st_g, neighbor=nb)
+  assert not bool(nb.did_buffer_overflow)
+  box_o = osim.npt_box(st_o)
+  box_g = jmd.simulate.npt_box(st_g).cpu().numpy()
+  np.testing.assert_allclose(box_g, box_o, rtol=tol)
+  assert abs(box_g[0, 0] / float(L) - 1) > 1e-4                        # the box did move
+  np.testing.assert_allclose(float(st_g.box_momentum), st_o.box_momentum, rtol=50 * tol, atol=50 * tol)
+  dX = st_g.position.cpu().numpy() - st_o.position
+  dX -= np.round(dX)
+  assert np.abs(dX).max() < tol
+  np.testing.assert_allclose(st_g.momentum.cpu().numpy(), st_o.momentum, atol=20 * tol, rtol=0)
+  for cg, co in ((st_g.thermostat, st_o.thermostat), (st_g.barostat, st_o.barostat)):
+    np.testing.assert_allclose(cg.position.cpu().numpy(), co.position, atol=20 * tol, rtol=20 * tol)
+    np.testing.assert_allclose(cg.momentum.cpu().numpy(), co.momentum, atol=2e3 * tol, rtol=20 * tol)
+    np.testing.assert_allclose(cg.mass.cpu().numpy(), co.mass, rtol=1e-6)
+  # the extended-system Hamiltonian (simulate.py:1007-1046).  NOT asserted to be conserved here:
+  # for unit-cube positions the reference's exp(iL1) hands `R * (exp(x) - 1)` -- an affine term
+  # that belongs to real-space coordinates -- to the shift function (simulate.py:925-927), and
+  # the invariant drifts with the box velocity; the restatement keeps the term, so both sides
+  # must drift alike.
+  nb = nb.update(st_g.position, box=jmd.simulate.npt_box(st_g))
+  inv1 = float(jmd.simulate.npt_nose_hoover_invariant(efn, st_g, float(pres), float(kT), neighbor=nb))
+  PE_o = oenergy.pair_neighbor_list_energy(pot, functools.partial(d_o, box=np.diag(box_o)), st_o.position,
+                                           hold['nb'], sigma=dtype(1.0), epsilon=dtype(1.0))
+  inv_o = osim.npt_nose_hoover_invariant(PE_o, st_o, pres, kT)
+  np.testing.assert_allclose(inv1, inv_o, rtol=1e-8 if dtype == np.float64 else 1e-4)
+  assert np.isfinite(inv0)
+
+
+def test_sw_virial_pressure_matches_strain_derivative():
+  """quantity.pressure / stress of Stillinger-Weber come from the kernel's virial: check them
+  against a central difference of the energy under an affine strain of box and positions."""
+  import torch
+  jmd = _jmd()
+  R, L = util.diamond(4, a=5.431, dtype=np.float64)
+  Rj = np.mod(util.jitter(R, L, 0.08, seed=5), L)
+  d, s = jmd.space.periodic_general(np.float64(L))
+  nf, efn = jmd.energy.stillinger_weber_neighbor_list(d, np.float64(L), fractional_coordinates=True)
+  Sd = _dev(Rj / L)
+  nb = nf.allocate(Sd, extra_capacity=4)
+  W = efn.virial(Sd, neighbor=nb).cpu().numpy()
+  np.testing.assert_allclose(W, W.T, atol=1e-12)
+
+  def E_at(box):
+    nb2 = nf.allocate(Sd, box=box, extra_capacity=4)
+    return float(efn(Sd, neighbor=nb2, box=box))
+  h = 1e-5
+  # isotropic strain: dU/d eps = trace(W)
+  dE = (E_at(np.float64(L * (1 + h))) - E_at(np.float64(L * (1 - h)))) / (2 * h)
+  np.testing.assert_allclose(np.trace(W), dE, rtol=1e-6)
+  # uniaxial strains: the diagonal of W
+  for k in range(3):
+    bp, bm = np.full(3, L), np.full(3, L)
+    bp[k] *= 1 + h
+    bm[k] *= 1 - h
+    np.testing.assert_allclose(W[k, k], (E_at(bp) - E_at(bm)) / (2 * h), rtol=1e-6, atol=1e-6)
+  KE = 3.0
+  P = float(jmd.quantity.pressure(efn, Sd, np.float64(L), KE, neighbor=nb))
+  np.testing.assert_allclose(P, (2 * KE - np.trace(W)) / (3 * L ** 3), rtol=1e-10)
+  sig = jmd.quantity.stress(efn, Sd, np.float64(L), neighbor=nb).cpu().numpy()
+  np.testing.assert_allclose(sig, -W / L ** 3, rtol=1e-10, atol=1e-14)
+
+
+def test_sw_npt_runs_and_conserves():
+  jmd = _jmd()
+  unit = jmd.units.metal_unit_system()
+  R, L = util.diamond(4, a=5.431, dtype=np.float64)
+  d, s = jmd.space.periodic_general(np.float64(L))
+  nf, efn = jmd.energy.stillinger_weber_neighbor_list(d, np.float64(L), fractional_coordinates=True)
+  Sd = _dev(np.mod(util.jitter(R, L, 0.02, seed=1), L) / L)
+  nb = nf.allocate(Sd, extra_capacity=6)
+  dt, kT, pres = 1e-3 * unit['time'], 300 * unit['temperature'], 1.0 * unit['pressure']
+  init, step = jmd.simulate.npt_nose_hoover(efn, s, dt, pres, kT)
+  st = init(3, Sd, np.float64(L), mass=28.0855 * unit['mass'], neighbor=nb)
+  inv0 = float(jmd.simulate.npt_nose_hoover_invariant(efn, st, pres, kT, neighbor=nb))
+  for _ in range(100):
+    nb = nb.update(st.position, box=jmd.simulate.npt_box(st))
+    st = step(st, neighbor=nb)
+  assert not bool(nb.did_buffer_overflow)
+  nb = nb.update(st.position, box=jmd.simulate.npt_box(st))
+  inv1 = float(jmd.simulate.npt_nose_hoover_invariant(efn, st, pres, kT, neighbor=nb))
+  assert abs(inv1 - inv0) / len(R) < 1e-3, (inv0, inv1)
+  T = float(jmd.simulate.temperature(st)) / unit['temperature']
+  assert 100 < T < 400

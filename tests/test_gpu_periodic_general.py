@@ -105,7 +105,7 @@ def test_lj_energy_force_and_nve_general_box(frac, dtype):
   100-step NVE trajectory vs the oracle."""
   jmd = _jmd()
   R, L = util.fcc(6, dtype=np.float64)
-  box = np.array([L, L * 1.08, L * 0.96], np.float32)
+  box = np.array([L, L * 1.08, L * 0.96], np.float32).astype(dtype)
   Rr = np.mod(util.jitter(R, L, 0.05) * (box / L), box)
   X = (Rr / box if frac else Rr).astype(dtype)
   N = len(X)
@@ -122,10 +122,8 @@ def test_lj_energy_force_and_nve_general_box(frac, dtype):
   np.testing.assert_array_equal(np.sort(nb_g.idx.cpu().numpy(), -1), np.sort(nb_o.idx, -1))
   E_o, F_o, _ = oenergy.pair_neighbor_list_energy(pot, d_o, X.astype(np.float64), nb_o, want_grads=True,
                                                   sigma=np.float64(1.0), epsilon=np.float64(1.0))
-  if frac:
-    # the oracle differentiates w.r.t. the unit-cube coordinates; the reference's custom JVP
-    # (space.py:171-186) reports REAL-space forces: dE/dx_real = dE/ds / box
-    F_o = F_o / box.astype(np.float64)
+  # (the oracle's analytic gradient is w.r.t. the REAL displacement -- what the reference's custom
+  #  JVP of space.transform, space.py:171-186, reports for unit-cube positions as well)
   rt = 1e-5 if dtype == np.float32 else 1e-10
   np.testing.assert_allclose(float(efn(Xd, neighbor=nb_g)), E_o, rtol=rt, atol=rt)
   Fg = jmd.quantity.force(efn)(Xd, neighbor=nb_g).cpu().numpy()
@@ -137,7 +135,7 @@ def test_lj_energy_force_and_nve_general_box(frac, dtype):
   def f_o(Xx):
     F = oenergy.pair_neighbor_list_energy(pot, d_o, Xx, holder['nb'], want_grads=True,
                                           sigma=dtype(1.0), epsilon=dtype(1.0))[1]
-    return (F / box).astype(Xx.dtype) if frac else F
+    return F
   init_o, step_o = osim.nve(f_o, s_o, 1e-3)
   st_o = init_o(X, P, mass=dtype(1.0))
   init_g, step_g = jmd.simulate.nve(efn, s_g, 1e-3)
@@ -161,13 +159,13 @@ def test_sw_nvt_with_periodic_general_as_in_the_example():
   jmd = _jmd()
   R, L = util.diamond(4, a=5.431, dtype=np.float64)
   Rj = util.jitter(R, L, 0.05, seed=3)
-  latvec = np.diag(np.array([L, L, L], np.float32))
+  latvec = np.diag(np.array([L, L, L], np.float64))
   d_g, s_g = jmd.space.periodic_general(latvec)
-  nf, efn = jmd.energy.stillinger_weber_neighbor_list(d_g, latvec, fractional_coordinates=True)
+  nf, efn = jmd.energy.stillinger_weber_neighbor_list(d_g, latvec, disable_cell_list=True)
   S = _dev((Rj / L).astype(np.float64))
   nb = nf.allocate(S, box=latvec, extra_capacity=2)
-  d_p, _ = jmd.space.periodic(np.float32(L))
-  nf_p, efn_p = jmd.energy.stillinger_weber_neighbor_list(d_p, np.float32(L))
+  d_p, _ = jmd.space.periodic(np.float64(L))
+  nf_p, efn_p = jmd.energy.stillinger_weber_neighbor_list(d_p, np.float64(L))
   Rp = _dev(Rj)
   nb_p = nf_p.allocate(Rp, extra_capacity=2)
   np.testing.assert_allclose(float(efn(S, neighbor=nb)), float(efn_p(Rp, neighbor=nb_p)), rtol=1e-10)
