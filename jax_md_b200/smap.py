@@ -151,10 +151,16 @@ class PairNeighborListFn:
   def _tensor(self, x, dtype, device):
     # converted copies are cached per tensor object AND version (in-place edits make a
     # new entry); NumPy inputs can be mutated without notice, so they are never cached
+    # (small tables are keyed by their bytes instead: the usual [S, S] species tables then
+    #  convert once, which also keeps the call capturable in a CUDA graph)
     cacheable = isinstance(x, torch.Tensor)
-    key = (id(x), dtype, x._version if cacheable else None)
-    hit = self._conv.get(key) if cacheable else None
-    if hit is not None and hit[0] is x:
+    if cacheable:
+      key = (id(x), dtype, x._version)
+    else:
+      a = np.ascontiguousarray(x)
+      key = ('np', a.shape, a.dtype.str, a.tobytes(), dtype, str(device)) if a.size <= 4096 else None
+    hit = self._conv.get(key) if key is not None else None
+    if hit is not None and (hit[0] is x or not cacheable):
       return hit[1]
     if isinstance(x, torch.Tensor):
       t = x.detach().to(device=device, dtype=dtype).contiguous()
@@ -169,8 +175,8 @@ class PairNeighborListFn:
           'smap.pair_neighbor_list path.')
     if len(self._conv) > 64:
       self._conv.clear()
-    if cacheable:
-      self._conv[key] = (x, t)
+    if key is not None:
+      self._conv[key] = (x if cacheable else None, t)
     return t
 
   def _pair_struct(self, R, species, params, sparse=False):
