@@ -92,9 +92,11 @@ def test_box_kwarg_error_bits_and_metric():
     if not (int(nb_o.error) & 3):
       np.testing.assert_array_equal(nb_g.idx.cpu().numpy(), nb_o.idx)
   assert int(nb_g.error.code) & 4               # CELL_SIZE_TOO_SMALL after the shrink
+  # partition.py:1125-1130: update() with box= but without fractional coordinates raises (allocate does not)
+  d_p, _ = jmd.space.periodic(box)
+  nb_p = jmd.partition.neighbor_list(d_p, box, 2.5, 0.3).allocate(_dev(S * L), box=box)
   with pytest.raises(ValueError):
-    d_p, _ = jmd.space.periodic(box)
-    jmd.partition.neighbor_list(d_p, box, 2.5, 0.3).allocate(_dev(S * L), box=box)
+    nb_p.update(_dev(S * L), box=box)
 
 
 @pytest.mark.parametrize('frac', [True, False])
