@@ -263,7 +263,9 @@ typedef struct {
   double sigma, A, B, lam, gamma, epsilon, three_body_strength, cutoff;
 } jmd_sw_t;
 
-/* scratch: int32[(m_int + 1) * n_pad] for the compact in-range rows. */
+/* scratch: int32[jmd_sw_scratch_ints(nb)], 16-byte aligned: the in-range neighbours of every atom as
+ * compact transposed records (count | displacement + slot | r, h(r), h'(r)). */
+int64_t jmd_sw_scratch_ints(const jmd_nbr_t* nb);
 int jmd_sw_force(const jmd_nbr_t* nb, const jmd_sw_t* sw, int32_t* scratch, void* force,
                  double* red, double* partials, void* momentum,
                  const void* mass, int mass_is_array, double dt_2,

@@ -134,7 +134,7 @@ _SIGNATURES = {
     'jmd_fire_mix': [_I, _L, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D,
                      _D, _P],
 }
-EXPORTED = sorted(list(_SIGNATURES) + ['jmd_red_scratch_doubles', 'jmd_version'])
+EXPORTED = sorted(list(_SIGNATURES) + ['jmd_red_scratch_doubles', 'jmd_sw_scratch_ints', 'jmd_version'])
 
 _lib = None
 
@@ -159,6 +159,8 @@ def load():
     fn.restype = C.c_int
   lib.jmd_red_scratch_doubles.argtypes = [C.c_int64]
   lib.jmd_red_scratch_doubles.restype = C.c_int64
+  lib.jmd_sw_scratch_ints.argtypes = [C.POINTER(NbrT)]
+  lib.jmd_sw_scratch_ints.restype = C.c_int64
   lib.jmd_version.restype = C.c_char_p
   _lib = lib
   return lib

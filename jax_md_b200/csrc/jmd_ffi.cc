@@ -149,7 +149,7 @@ ffi::Error PairForceImpl(cudaStream_t stream, std::string_view nbr_desc, std::st
 
 // ---- Stillinger-Weber (energy.py:842-893, 994-1012) --------------------------------------------
 // operands: mass, dt_dev (optional), momentum (aliased), workspace...
-// results:  force, red, partials, scratch i32[(m_int + 1) * n_pad], momentum (or empty), workspace...
+// results:  force, red, partials, scratch i32[jmd_sw_scratch_ints(nb)], momentum (or empty), workspace...
 ffi::Error SwForceImpl(cudaStream_t stream, std::string_view nbr_desc, std::string_view sw_desc,
                        int32_t mass_is_array, double dt_2, int32_t kick, ffi::RemainingArgs args,
                        ffi::RemainingRets rets) {

@@ -3,18 +3,23 @@
 // Replaces energy.py:842-893 (+ :994-1012) and its autodiff gradient.  The
 // reference evaluates the full M x M neighbour square per atom (97 % masked for
 // diamond Si).  Two kernels, one thread per atom:
-//   k_sw_compact  walks the Verlet row once and writes the IN-RANGE neighbours
-//                 (r < cutoff; 4 of ~16-27 entries in Si) to a compact
-//                 transposed list -- uniform trip counts, predicated appends.
-//   k_sw          works on compact lists only:
+//   k_sw_compact  walks the Verlet row once, applies the exact in-range test
+//                 (r < cutoff; 4 of ~16-27 entries in cold Si, up to ~12 at 300 K) and
+//                 writes, per in-range neighbour, a 2 x 16-byte record to compact
+//                 TRANSPOSED rows: (dx, dy, dz, slot) and (r, h(r), h'(r), -) with
+//                 h = exp(gamma / (r/sigma - a)).  Uniform trip counts, predicated appends.
+//   k_sw          works on the compact records only -- no position gathers, no min-image,
+//                 no sqrt / exp in the triplet loops:
 //     (1) the unordered pairs (a, b) of its own compact row: triplets centred
-//         on i (energy + force on i),
+//         on i (energy + force on i + virial); the records are coalesced loads,
 //     (2) for every compact neighbour j, j's compact row: triplets centred on j
-//         that have i as an end atom (force on i only).
+//         that have i as an end atom (force on i only); two 16-byte gathers per entry.
 // Every force component is produced by exactly one thread in a fixed order: no
 // atomics, bitwise reproducible.  Needs symmetric rows (the Dense build
-// guarantees that).  (The first version walked full rows inside the triplet
-// loops: 5.3 of 32 lanes active on average, 2.2 ms at N=512k.)
+// guarantees that; d(i,j) = -d(j,i) exactly, so r, h and the in-range decision agree).
+// History: walking full rows inside the triplet loops: 5.3 of 32 lanes active, 2.2 ms at
+// N=512k; compact index rows with positions re-gathered and h re-evaluated per triplet
+// (three times per triplet overall): 0.24 ms on the cold lattice but 0.74-0.97 ms at 300 K.
 #include <cuda_runtime.h>
 #include <math.h>
 #include "jmd_common.cuh"
@@ -32,8 +37,9 @@ struct SwP {
   const int* nl;
   const int* cnt;
   const int* perm;
-  int* cl;      // [m_int, n_pad] compact in-range rows (slot indices)
-  int* ccnt;    // [n_pad]
+  int* ccnt;                              // [n_pad] in-range neighbours per slot
+  typename Vec4<T>::type* geo;            // [m_int, n_pad] (dx, dy, dz, slot of the neighbour)
+  typename Vec4<T>::type* hd;             // [m_int, n_pad] (r, h, dh/dr, unused)
   T sigma, A, B, lam, gamma, eps, tbs, cutoff, a, cutoff2;
   T* force;
   double* red;
@@ -57,10 +63,8 @@ __device__ __forceinline__ void sw_h(const SwP<T>& S, T r, T& h, T& dh) {
 // triplet term g = h1 h2 (cos + 1/3)^2 with cos = d1.d2 / ((r1+1e-7)(r2+1e-7)),
 // clipped to [-1, 1] (quantity.py:285-289).  Returns g and dg/dd1, dg/dd2.
 template <typename T>
-__device__ __forceinline__ T sw_triplet(const SwP<T>& S, const T* d1, T r1, const T* d2, T r2, T* g1, T* g2) {
-  T h1, dh1, h2, dh2;
-  sw_h(S, r1, h1, dh1);
-  sw_h(S, r2, h2, dh2);
+__device__ __forceinline__ T sw_triplet(const T* d1, T r1, T h1, T dh1, const T* d2, T r2, T h2, T dh2,
+                                        T* g1, T* g2) {
   const T n1 = r1 + T(1e-7), n2 = r2 + T(1e-7);
   const T dot = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
   T c = dot / n1 / n2;
@@ -79,6 +83,18 @@ __device__ __forceinline__ T sw_triplet(const SwP<T>& S, const T* d1, T r1, cons
   return g;
 }
 
+// the neighbour's slot travels in the 4th component: bit pattern for float, value for double
+__device__ __forceinline__ float sw_pack_idx(int j, float) { return __int_as_float(j); }
+__device__ __forceinline__ double sw_pack_idx(int j, double) { return (double)j; }
+__device__ __forceinline__ int sw_unpack_idx(float w) { return __float_as_int(w); }
+__device__ __forceinline__ int sw_unpack_idx(double w) { return (int)w; }
+__device__ __forceinline__ float4 sw_ld(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ double4 sw_ld(const double4* p) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(SWB) k_sw_compact(SwP<T> S) {
   using V4 = typename Vec4<T>::type;
@@ -89,7 +105,8 @@ __global__ void __launch_bounds__(SWB) k_sw_compact(SwP<T> S) {
     const V4 pi = S.pos_sorted[t];
     const int cnt = min(S.cnt[t], S.m_int);
     const int* col = S.nl + t;
-    int* out = S.cl + t;
+    V4* og = S.geo + t;
+    V4* oh = S.hd + t;
 #pragma unroll 4
     for (int k = 0; k < cnt; ++k) {
       const int j = __ldcs(col + (size_t)k * S.n_pad);
@@ -97,9 +114,18 @@ __global__ void __launch_bounds__(SWB) k_sw_compact(SwP<T> S) {
       const T dx = S.sp.disp_fast(pj.x, pi.x, 0), dy = S.sp.disp_fast(pj.y, pi.y, 1),
               dz = S.sp.disp_fast(pj.z, pi.z, 2);
       const T r2 = dx * dx + dy * dy + dz * dz;
-      if (r2 > T(0) && r2 < S.cutoff2) {      // conservative; k_sw applies the exact test
-        out[(size_t)kc * S.n_pad] = j;
-        ++kc;
+      if (r2 > T(0) && r2 < S.cutoff2) {      // conservative, skips the sqrt of skin-only entries
+        const T r = sqrt(r2);
+        if (r < S.cutoff) {                   // energy.py:868-870
+          T h, dh;
+          sw_h(S, r, h, dh);
+          V4 g, q;
+          g.x = dx; g.y = dy; g.z = dz; g.w = sw_pack_idx(j, T(0));
+          q.x = r; q.y = h; q.z = dh; q.w = T(0);
+          og[(size_t)kc * S.n_pad] = g;
+          oh[(size_t)kc * S.n_pad] = q;
+          ++kc;
+        }
       }
     }
   }
@@ -116,22 +142,18 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
   // differentiating through `perturbation=` (quantity.py:226-282, simulate.py:848-855)
   double vir[6] = {0, 0, 0, 0, 0, 0};
   if (t < S.n && S.perm[t] < S.n_rows) {
-    const V4 pi = S.pos_sorted[t];
     const int cnt = S.ccnt[t];
-    const int* col = S.cl + t;
+    const V4* gcol = S.geo + t;
+    const V4* hcol = S.hd + t;
     T f[3] = {0, 0, 0};
     T e2 = 0, e3 = 0;
+    const T w = S.eps * S.lam * S.tbs;
     for (int ka = 0; ka < cnt; ++ka) {
-      const int j = __ldg(col + (size_t)ka * S.n_pad);
-      const V4 pj = S.pos_sorted[j];
-      T da[3];
-      da[0] = S.sp.disp_fast(pj.x, pi.x, 0);
-      da[1] = S.sp.disp_fast(pj.y, pi.y, 1);
-      da[2] = S.sp.disp_fast(pj.z, pi.z, 2);
-      const T ra2 = da[0] * da[0] + da[1] * da[1] + da[2] * da[2];
-      if (!(ra2 > T(0)) || !(ra2 < S.cutoff2)) continue;      // skin-only entries: no sqrt
-      const T ra = sqrt(ra2);
-      if (!(ra < S.cutoff)) continue;
+      const V4 ga = gcol[(size_t)ka * S.n_pad];
+      const V4 ha = hcol[(size_t)ka * S.n_pad];
+      const int j = sw_unpack_idx(ga.w);
+      const T da[3] = {ga.x, ga.y, ga.z};
+      const T ra = ha.x;
       // two-body, energy.py:883-893: [B (r/s)^-4 - 1] exp(1/(r/s - a))
       {
         const T x = ra / S.sigma;
@@ -149,21 +171,13 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
       }
       // (1) triplets centred on i: unordered pairs (a, b), b > a
       for (int kb = ka + 1; kb < cnt; ++kb) {
-        const int k2 = __ldg(col + (size_t)kb * S.n_pad);
-        const V4 pk = S.pos_sorted[k2];
-        T db[3];
-        db[0] = S.sp.disp_fast(pk.x, pi.x, 0);
-        db[1] = S.sp.disp_fast(pk.y, pi.y, 1);
-        db[2] = S.sp.disp_fast(pk.z, pi.z, 2);
-        const T rb2 = db[0] * db[0] + db[1] * db[1] + db[2] * db[2];
-        if (!(rb2 > T(0)) || !(rb2 < S.cutoff2)) continue;
-        const T rb = sqrt(rb2);
-        if (!(rb < S.cutoff)) continue;
+        const V4 gb = gcol[(size_t)kb * S.n_pad];
+        const V4 hb = hcol[(size_t)kb * S.n_pad];
+        const T db[3] = {gb.x, gb.y, gb.z};
         const T s0 = da[0] - db[0], s1 = da[1] - db[1], s2 = da[2] - db[2];
         if (!(sqrt(s0 * s0 + s1 * s1 + s2 * s2) > T(1e-5))) continue;    // energy.py:872-874
         T g1[3], g2[3];
-        e3 += sw_triplet(S, da, ra, db, rb, g1, g2);
-        const T w = S.eps * S.lam * S.tbs;
+        e3 += sw_triplet(da, ra, ha.y, ha.z, db, hb.x, hb.y, hb.z, g1, g2);
         // d_a = R_j - R_i, so dE/dR_i = -(g1 + g2); force = +w (g1 + g2)
         f[0] += w * (g1[0] + g2[0]); f[1] += w * (g1[1] + g2[1]); f[2] += w * (g1[2] + g2[2]);
         // own-centre triplets carry the whole three-body energy: dU/d(eps_ab) = w (g1_a d1_b + g2_a d2_b)
@@ -175,28 +189,21 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
         vir[4] += 0.5 * wd * (g1[0] * da[2] + g1[2] * da[0] + g2[0] * db[2] + g2[2] * db[0]);
         vir[5] += 0.5 * wd * (g1[1] * da[2] + g1[2] * da[1] + g2[1] * db[2] + g2[2] * db[1]);
       }
-      // (2) triplets centred on j with i as an end atom: d1 = R_i - R_j = -da
+      // (2) triplets centred on j with i as an end atom: d1 = R_i - R_j = -da, same r and h
       {
         const T d1[3] = {-da[0], -da[1], -da[2]};
         const int cj = S.ccnt[j];
-        const int* colj = S.cl + j;
+        const V4* gj = S.geo + j;
+        const V4* hj = S.hd + j;
         for (int kc = 0; kc < cj; ++kc) {
-          const int k3 = __ldg(colj + (size_t)kc * S.n_pad);
-          if (k3 == t) continue;
-          const V4 pk = S.pos_sorted[k3];
-          T dc[3];
-          dc[0] = S.sp.disp_fast(pk.x, pj.x, 0);
-          dc[1] = S.sp.disp_fast(pk.y, pj.y, 1);
-          dc[2] = S.sp.disp_fast(pk.z, pj.z, 2);
-          const T rc2 = dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2];
-          if (!(rc2 > T(0)) || !(rc2 < S.cutoff2)) continue;
-          const T rc = sqrt(rc2);
-          if (!(rc < S.cutoff)) continue;
+          const V4 gc = sw_ld(gj + (size_t)kc * S.n_pad);
+          if (sw_unpack_idx(gc.w) == t) continue;
+          const V4 hc = sw_ld(hj + (size_t)kc * S.n_pad);
+          const T dc[3] = {gc.x, gc.y, gc.z};
           const T s0 = d1[0] - dc[0], s1 = d1[1] - dc[1], s2 = d1[2] - dc[2];
           if (!(sqrt(s0 * s0 + s1 * s1 + s2 * s2) > T(1e-5))) continue;
           T g1[3], g2[3];
-          sw_triplet(S, d1, ra, dc, rc, g1, g2);
-          const T w = S.eps * S.lam * S.tbs;
+          sw_triplet(d1, ra, ha.y, ha.z, dc, hc.x, hc.y, hc.z, g1, g2);
           f[0] -= w * g1[0]; f[1] -= w * g1[1]; f[2] -= w * g1[2];
         }
       }
@@ -251,8 +258,10 @@ int launch_sw(const jmd_nbr_t* nb, const jmd_sw_t* sw, int* scratch, void* force
   S.momentum = (T*)momentum; S.mass = (const T*)mass; S.mass_is_array = mass_is_array; S.dt_2 = (T)dt_2;
   S.dt_dev = (const T*)dt_dev;
   S.kick = momentum != nullptr;
-  S.cl = scratch;
-  S.ccnt = scratch + (size_t)nb->m_int * nb->n_pad;
+  // scratch: ccnt | geo | hd (jmd_sw_scratch_ints)
+  S.ccnt = scratch;
+  S.geo = (typename Vec4<T>::type*)(scratch + nb->n_pad);
+  S.hd = S.geo + (size_t)nb->m_int * nb->n_pad;
   const int grid = (int)jmd_div_up(S.n > 0 ? S.n : 1, SWB);
   k_sw_compact<T><<<grid, SWB, 0, s>>>(S);
   k_sw<T><<<grid, SWB, 0, s>>>(S);
@@ -261,6 +270,12 @@ int launch_sw(const jmd_nbr_t* nb, const jmd_sw_t* sw, int* scratch, void* force
 }
 
 }  // namespace
+
+extern "C" int64_t jmd_sw_scratch_ints(const jmd_nbr_t* nb) {
+  if (!nb) return 0;
+  const int64_t rec = nb->dtype == JMD_F64 ? 16 : 8;           // two 4-vectors per entry, in int32 units
+  return (int64_t)nb->n_pad + (int64_t)nb->m_int * nb->n_pad * rec;
+}
 
 extern "C" int jmd_sw_force(const jmd_nbr_t* nb, const jmd_sw_t* sw, int32_t* scratch, void* force, double* red,
                             double* partials,

@@ -297,7 +297,7 @@ class StillingerWeberFn:
     sw = self._struct()
     mass_is_array = 1 if (mass is not None and mass.numel() > 1) else 0
     scratch = ws.t.get('sw_scratch')
-    need = (ws.c.m_int + 1) * ws.c.n_pad
+    need = int(_lib.load().jmd_sw_scratch_ints(ws.ref()))
     if scratch is None or scratch.numel() < need:
       scratch = ws.buf_plain('sw_scratch', (need,), torch.int32)
     _lib.call('jmd_sw_force', ws.ref(), C.byref(sw), _lib.ptr(scratch), _lib.ptr(force),

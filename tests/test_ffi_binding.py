@@ -11,7 +11,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FFI = os.path.join(ROOT, 'jax_md_b200', 'csrc', 'jmd_ffi.cc')
-HOST_ONLY = {'jmd_nbr_state_host', 'jmd_red_scratch_doubles', 'jmd_version', 'jmd_p2p_alloc',
+HOST_ONLY = {'jmd_nbr_state_host', 'jmd_red_scratch_doubles', 'jmd_sw_scratch_ints', 'jmd_version', 'jmd_p2p_alloc',
              'jmd_p2p_open', 'jmd_p2p_close', 'jmd_p2p_free', 'jmd_host_flag_alloc', 'jmd_host_flag_free'}
 
 
