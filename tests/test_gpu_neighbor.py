@@ -242,6 +242,29 @@ def test_fine_search_grid_same_sets(fmt, dim):
   _assert_same(nb_o.update(R2), nb_g.update(_dev(R2)), exact_order=False)
 
 
+@pytest.mark.parametrize('fmt', FORMATS)
+@pytest.mark.parametrize('dim,dtype', [(3, np.float32), (3, np.float64), (2, np.float32)])
+def test_warp_per_cell_scan_element_exact(fmt, dim, dtype):
+  """The opt-in warp-per-cell candidate scan (`cell_scan=True`, csrc/jmd_nbr_cellscan.cuh):
+  same lists as the oracle, element by element, on allocate and on update."""
+  rng = np.random.default_rng(11)
+  box = np.array([21.0, 16.5, 18.25][:dim], np.float32)
+  n = 9000 if dim == 3 else 1500
+  R = (rng.random((n, dim)) * box).astype(dtype)
+  d_o, _ = ospace.periodic(box)
+  nf_o = opart.neighbor_list(d_o, box, 2.1, 0.3, format=opart.Format[fmt])
+  jmd = _mods()
+  d_g, _ = jmd.space.periodic(box)
+  nf_g = jmd.partition.neighbor_list(d_g, box, 2.1, 0.3, format=jmd.partition.NeighborListFormat[fmt],
+                                     cell_scan=True)
+  nb_o = nf_o.allocate(R)
+  nb_g = nf_g.allocate(_dev(R))
+  assert nb_g._ws.c.cell_scan == 1
+  _assert_same(nb_o, nb_g)
+  R2 = np.mod(R + rng.normal(0, 0.25, R.shape).astype(dtype), box).astype(dtype)
+  _assert_same(nb_o.update(R2), nb_g.update(_dev(R2)))
+
+
 def test_always_rebuild_when_skin_zero():
   R, L = util.fcc(6, dtype=np.float32)
   nf_o, nf_g = _build_both(R, L, 2.0, 0.0, 'Dense')

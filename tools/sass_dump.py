@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'jax_md_b200', 'libjmd_b200.so')
 # (file tag, regex on the demangled function name) -- the instance the headline / config benches run
 WANT = [
-    ('k_pair_force_f32_3d_lj_scalar_kick', r'k_pair_force<float, 3, 0, 1, 1, 1>'),
-    ('k_nbr_stencil_scan_f32_3d_ordered_filter', r'k_nbr_stencil_scan<float, 3, 2, 1, 1, 1>'),
+    ('k_pair_force_f32_3d_lj_scalar_kick', r'k_pair_force<float, 3, 0, true, 1, true>'),
+    ('k_nbr_stencil_scan_f32_3d_ordered_filter', r'k_nbr_stencil_scan<float, 3, 2, true, 1, true>'),
     ('k_nbr_export_fin_f32_3d', r'k_nbr_export_fin<float, 3>'),
     ('k_nbr_offsets_f32_3d', r'k_nbr_offsets<float, 3>'),
     ('k_update_f32_3d', r'k_update<float, 3>'),
