@@ -6,10 +6,10 @@
 //   k_sw_compact  walks the Verlet row once, applies the exact in-range test
 //                 (r < cutoff; 4 of ~16-27 entries in cold Si, up to ~12 at 300 K) and
 //                 writes, per in-range neighbour, a 2 x 16-byte record to compact
-//                 TRANSPOSED rows: (dx, dy, dz, slot) and (r, h(r), h'(r), -) with
+//                 TRANSPOSED rows: (dx, dy, dz, slot) and (r, h(r), h'(r), 1/r) with
 //                 h = exp(gamma / (r/sigma - a)).  Uniform trip counts, predicated appends.
 //   k_sw          works on the compact records only -- no position gathers, no min-image,
-//                 no sqrt / exp in the triplet loops:
+//                 no sqrt / exp and one reciprocal per triplet in the loops:
 //     (1) the unordered pairs (a, b) of its own compact row: triplets centred
 //         on i (energy + force on i + virial); the records are coalesced loads,
 //     (2) for every compact neighbour j, j's compact row: triplets centred on j
@@ -39,7 +39,7 @@ struct SwP {
   const int* perm;
   int* ccnt;                              // [n_pad] in-range neighbours per slot
   typename Vec4<T>::type* geo;            // [m_int, n_pad] (dx, dy, dz, slot of the neighbour)
-  typename Vec4<T>::type* hd;             // [m_int, n_pad] (r, h, dh/dr, unused)
+  typename Vec4<T>::type* hd;             // [m_int, n_pad] (r, h, dh/dr, 1/r)
   T sigma, A, B, lam, gamma, eps, tbs, cutoff, a, cutoff2;
   T* force;
   double* red;
@@ -62,23 +62,30 @@ __device__ __forceinline__ void sw_h(const SwP<T>& S, T r, T& h, T& dh) {
 
 // triplet term g = h1 h2 (cos + 1/3)^2 with cos = d1.d2 / ((r1+1e-7)(r2+1e-7)),
 // clipped to [-1, 1] (quantity.py:285-289).  Returns g and dg/dd1, dg/dd2.
-template <typename T>
-__device__ __forceinline__ T sw_triplet(const T* d1, T r1, T h1, T dh1, const T* d2, T r2, T h2, T dh2,
-                                        T* g1, T* g2) {
-  const T n1 = r1 + T(1e-7), n2 = r2 + T(1e-7);
+// i1 = 1/r1, i2 = 1/r2 (from the records), m1 = 1/(r1+1e-7), m2 = 1/(r2+1e-7): the gradient
+//   dg/dd1 = h1' h2 ct^2 d1/r1 + 2 h1 h2 ct [ d2/(n1 n2) - c d1/(n1 r1) ]
+// is evaluated with these four reciprocals instead of ~18 IEEE divides per triplet.
+template <typename T, bool WANT_G2>
+__device__ __forceinline__ T sw_triplet(const T* d1, T h1, T dh1, T i1, T m1,
+                                        const T* d2, T h2, T dh2, T i2, T m2, T* g1, T* g2) {
   const T dot = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
-  T c = dot / n1 / n2;
+  const T mm = m1 * m2;
+  const T c = dot * mm;
   const bool live = (c >= T(-1)) && (c <= T(1));
   const T cc = c < T(-1) ? T(-1) : (c > T(1) ? T(1) : c);
   const T ct = cc + T(1.0 / 3.0);
   const T hh = h1 * h2;
-  const T g = hh * ct * ct;
+  const T ct2 = ct * ct;
+  const T g = hh * ct2;
   const T pre = live ? T(2) * hh * ct : T(0);
+  const T cross = pre * mm;                                // coefficient of the other vector
+  const T own1 = dh1 * h2 * ct2 * i1 - pre * c * m1 * i1;  // coefficient of d1 in dg/dd1
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const T u1 = d1[k] / r1, u2 = d2[k] / r2;
-    g1[k] = dh1 * h2 * ct * ct * u1 + pre * (d2[k] / (n1 * n2) - c / n1 * u1);
-    g2[k] = dh2 * h1 * ct * ct * u2 + pre * (d1[k] / (n1 * n2) - c / n2 * u2);
+  for (int k = 0; k < 3; ++k) g1[k] = own1 * d1[k] + cross * d2[k];
+  if (WANT_G2) {
+    const T own2 = dh2 * h1 * ct2 * i2 - pre * c * m2 * i2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g2[k] = own2 * d2[k] + cross * d1[k];
   }
   return g;
 }
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(SWB) k_sw_compact(SwP<T> S) {
           sw_h(S, r, h, dh);
           V4 g, q;
           g.x = dx; g.y = dy; g.z = dz; g.w = sw_pack_idx(j, T(0));
-          q.x = r; q.y = h; q.z = dh; q.w = T(0);
+          q.x = r; q.y = h; q.z = dh; q.w = T(1) / r;
           og[(size_t)kc * S.n_pad] = g;
           oh[(size_t)kc * S.n_pad] = q;
           ++kc;
@@ -154,6 +161,7 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
       const int j = sw_unpack_idx(ga.w);
       const T da[3] = {ga.x, ga.y, ga.z};
       const T ra = ha.x;
+      const T ma = T(1) / (ra + T(1e-7));
       // two-body, energy.py:883-893: [B (r/s)^-4 - 1] exp(1/(r/s - a))
       {
         const T x = ra / S.sigma;
@@ -175,9 +183,9 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
         const V4 hb = hcol[(size_t)kb * S.n_pad];
         const T db[3] = {gb.x, gb.y, gb.z};
         const T s0 = da[0] - db[0], s1 = da[1] - db[1], s2 = da[2] - db[2];
-        if (!(sqrt(s0 * s0 + s1 * s1 + s2 * s2) > T(1e-5))) continue;    // energy.py:872-874
+        if (!(s0 * s0 + s1 * s1 + s2 * s2 > T(1e-5) * T(1e-5))) continue;    // energy.py:872-874 (|d_ab| > 1e-5)
         T g1[3], g2[3];
-        e3 += sw_triplet(da, ra, ha.y, ha.z, db, hb.x, hb.y, hb.z, g1, g2);
+        e3 += sw_triplet<T, true>(da, ha.y, ha.z, ha.w, ma, db, hb.y, hb.z, hb.w, T(1) / (hb.x + T(1e-7)), g1, g2);
         // d_a = R_j - R_i, so dE/dR_i = -(g1 + g2); force = +w (g1 + g2)
         f[0] += w * (g1[0] + g2[0]); f[1] += w * (g1[1] + g2[1]); f[2] += w * (g1[2] + g2[2]);
         // own-centre triplets carry the whole three-body energy: dU/d(eps_ab) = w (g1_a d1_b + g2_a d2_b)
@@ -201,9 +209,9 @@ __global__ void __launch_bounds__(SWB) k_sw(SwP<T> S) {
           const V4 hc = sw_ld(hj + (size_t)kc * S.n_pad);
           const T dc[3] = {gc.x, gc.y, gc.z};
           const T s0 = d1[0] - dc[0], s1 = d1[1] - dc[1], s2 = d1[2] - dc[2];
-          if (!(sqrt(s0 * s0 + s1 * s1 + s2 * s2) > T(1e-5))) continue;
-          T g1[3], g2[3];
-          sw_triplet(d1, ra, ha.y, ha.z, dc, hc.x, hc.y, hc.z, g1, g2);
+          if (!(s0 * s0 + s1 * s1 + s2 * s2 > T(1e-5) * T(1e-5))) continue;
+          T g1[3];
+          sw_triplet<T, false>(d1, ha.y, ha.z, ha.w, ma, dc, hc.y, hc.z, hc.w, T(1) / (hc.x + T(1e-7)), g1, (T*)nullptr);
           f[0] -= w * g1[0]; f[1] -= w * g1[1]; f[2] -= w * g1[2];
         }
       }
