@@ -49,8 +49,8 @@ typedef struct {
   int32_t dim;        /* 2 or 3 */
   int32_t kind;       /* JMD_SPACE_* */
   int32_t wrapped;    /* shift_fn wraps into [0, side) */
-  int32_t general;    /* 0: space.periodic / free; 1: space.periodic_general (space.py:332-472)
-                         with an orthorhombic box (scalar, vector or diagonal matrix): the
+  int32_t general;    /* 0: space.periodic / free; 1: space.periodic_general (space.py:332-472);
+                         with an orthorhombic box (scalar, vector or diagonal matrix) the
                          exact displacement is box * (mod(sa - sb + 1/2, 1) - 1/2) on the
                          unit cube; `side` is the box diagonal, `inv_box` = 1 / box in the
                          position dtype */
@@ -59,8 +59,13 @@ typedef struct {
   int32_t fractional; /* general: positions are stored in the unit cube (fractional_coordinates=True);
                          the cell-sorted float4 copy and everything the force kernels see stay in
                          real space (fractional * side) */
-  int32_t _pad;
+  int32_t triclinic;  /* general: the box is a full matrix (off-diagonal elements).  `box_m` / `inv_box_m`
+                         (row-major, real_i = sum_j box_m[i][j] * frac_j) replace side / inv_box in
+                         the metric; `half` then holds per-axis bounds under which a raw real-space
+                         difference is already the minimum image (sum_j |inv_box_m[i][j]| half[j] <= 1/2) */
   double inv_box[3];
+  double box_m[9];
+  double inv_box_m[9];
 } jmd_space_t;
 
 /* Slots of the device scalar block `jmd_nbr_t.state` (int64 each). */

@@ -33,8 +33,8 @@ RED_COUNT = 16
 class SpaceT(C.Structure):
   _fields_ = [('dim', C.c_int32), ('kind', C.c_int32), ('wrapped', C.c_int32),
               ('general', C.c_int32), ('side', C.c_double * 3),
-              ('half', C.c_double * 3), ('fractional', C.c_int32), ('_pad', C.c_int32),
-              ('inv_box', C.c_double * 3)]
+              ('half', C.c_double * 3), ('fractional', C.c_int32), ('triclinic', C.c_int32),
+              ('inv_box', C.c_double * 3), ('box_m', C.c_double * 9), ('inv_box_m', C.c_double * 9)]
 
 
 class NbrT(C.Structure):

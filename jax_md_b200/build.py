@@ -22,7 +22,8 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
           '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
           '--expt-relaxed-constexpr', '-Xptxas', '-v']
 RDC_UNITS = []
-UNITS = ['jmd_neighbor.cu', 'jmd_pair.cu', 'jmd_pair_staged.cu', 'jmd_integrate.cu', 'jmd_sw.cu', 'jmd_domain.cu']
+UNITS = ['jmd_neighbor.cu', 'jmd_pair.cu', 'jmd_pair_staged.cu', 'jmd_pair_tric.cu', 'jmd_integrate.cu', 'jmd_sw.cu',
+         'jmd_domain.cu']
 
 
 def _sources():

@@ -82,11 +82,20 @@ struct Space {
   int general;       // space.periodic_general, orthorhombic (see jmd_space_t)
   int frac;          // ... with positions stored in the unit cube
   T ibox[DIM];       // 1 / box
+  int tric;          // ... with a full box matrix: H (row-major) and its inverse replace side / ibox
+  T H[DIM * DIM];
+  T Hi[DIM * DIM];
   __host__ void init(const jmd_space_t& s) {
     periodic = s.kind == JMD_SPACE_PERIODIC;
     wrapped = s.wrapped;
     general = periodic && s.general;
     frac = general && s.fractional;
+    tric = general && s.triclinic;
+    for (int i = 0; i < DIM; ++i)
+      for (int j = 0; j < DIM; ++j) {
+        H[i * DIM + j] = tric ? (T)s.box_m[i * 3 + j] : T(i == j);
+        Hi[i * DIM + j] = tric ? (T)s.inv_box_m[i * 3 + j] : T(i == j);
+      }
     for (int k = 0; k < DIM; ++k) ibox[k] = general ? (T)s.inv_box[k] : T(1);
     for (int k = 0; k < DIM; ++k) {
       side[k] = (T)s.side[k];
@@ -149,11 +158,100 @@ struct Space {
   }
   // fractional -> real (what the cell-sorted copy holds)
   __device__ __forceinline__ T to_real(T r, int k) const { return frac ? mul_rn(r, side[k]) : r; }
+
+  // ---- full-matrix boxes (space.raw_transform with a 2-d box, space.py:128-150): the einsum's
+  // summation order is XLA's to choose; here (and in the oracle) it is j = 0, 1, 2 with
+  // separately rounded products and sums.
+  __device__ __forceinline__ void matvec(const T* M, const T* v, T* out) const {
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      T acc = mul_rn(M[i * DIM], v[0]);
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) acc = add_rn(acc, mul_rn(M[i * DIM + j], v[j]));
+      out[i] = acc;
+    }
+  }
+  // all components at once; handles every kind of space
+  __device__ __forceinline__ void to_real_v(const T* r, T* out) const {
+    if (tric && frac) { matvec(H, r, out); return; }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) out[k] = to_real(r[k], k);
+  }
+  __device__ __forceinline__ void shift_v(const T* r, const T* dr, T* out) const {
+    if (!tric) {
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) out[k] = shift(r[k], dr[k], k);
+      return;
+    }
+    if (!frac && !wrapped) {
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) out[k] = add_rn(r[k], dr[k]);
+      return;
+    }
+    T du[DIM], u[DIM];
+    matvec(Hi, dr, du);
+    if (frac) {
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) u[k] = r[k];
+    } else {
+      matvec(Hi, r, u);
+    }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      u[k] = add_rn(u[k], du[k]);
+      if (wrapped) u[k] = mod_pos(u[k], T(1));
+    }
+    if (frac) {
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) out[k] = u[k];
+    } else {
+      matvec(H, u, out);
+    }
+  }
+  // exact squared distance of periodic_general with a matrix box
+  __device__ __forceinline__ T dist2_tric(const T* a, const T* b) const {
+    T ua[DIM], ub[DIM], m[DIM], g[DIM];
+    if (frac) {
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) { ua[k] = a[k]; ub[k] = b[k]; }
+    } else {
+      matvec(Hi, a, ua);
+      matvec(Hi, b, ub);
+    }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k)
+      m[k] = sub_rn(mod_pos(add_rn(sub_rn(ua[k], ub[k]), T(0.5)), T(1)), T(0.5));
+    matvec(H, m, g);
+    T acc = mul_rn(g[0], g[0]);
+#pragma unroll
+    for (int k = 1; k < DIM; ++k) acc = add_rn(acc, mul_rn(g[k], g[k]));
+    return acc;
+  }
+  // minimum image of a real-space difference, tolerance-level (force kernels):
+  // d - H rint(H^-1 d)
+  __device__ __forceinline__ void wrap_tric(T* d) const {
+    T f[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      T acc = Hi[i * DIM] * d[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) acc += Hi[i * DIM + j] * d[j];
+      f[i] = rint_magic(acc);
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      T acc = d[i];
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) acc -= H[i * DIM + j] * f[j];
+      d[i] = acc;
+    }
+  }
 };
 
 // Exact squared distance sum_k d_k^2, sequential (space.py:227-235).
 template <typename T, int DIM>
 __device__ __forceinline__ T dist2_exact(const Space<T, DIM>& sp, const T* a, const T* b) {
+  if (sp.tric) return sp.dist2_tric(a, b);
   if (sp.general) {
     T g = sp.disp_general(a[0], b[0], 0);
     T acc = mul_rn(g, g);

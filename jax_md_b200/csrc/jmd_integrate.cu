@@ -55,20 +55,38 @@ __global__ void __launch_bounds__(IB) k_kick_drift(StepP<T, DIM> S) {
     const T scale = S.scale_dev ? *S.scale_dev : T(1);
     const T m = S.mass_is_array ? S.mass[a] : S.mass[0];
     T r[3] = {T(0), T(0), T(0)};
+    if (!S.sp.tric) {
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-      const size_t o = (size_t)a * DIM + k;
-      T p = S.p_in[o];
-      if (S.scale_dev) p *= scale;
-      p = p + dt_2 * S.f_in[o];
-      S.p_out[o] = p;
-      r[k] = S.sp.shift(S.r_in[o], dt * p / m, k);
-      S.r_out[o] = r[k];
+      for (int k = 0; k < DIM; ++k) {
+        const size_t o = (size_t)a * DIM + k;
+        T p = S.p_in[o];
+        if (S.scale_dev) p *= scale;
+        p = p + dt_2 * S.f_in[o];
+        S.p_out[o] = p;
+        r[k] = S.sp.shift(S.r_in[o], dt * p / m, k);
+        S.r_out[o] = r[k];
+      }
+    } else {                        // full-matrix periodic_general: the shift couples the components
+      T r0[DIM], dr[DIM];
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) {
+        const size_t o = (size_t)a * DIM + k;
+        T p = S.p_in[o];
+        if (S.scale_dev) p *= scale;
+        p = p + dt_2 * S.f_in[o];
+        S.p_out[o] = p;
+        r0[k] = S.r_in[o];
+        dr[k] = dt * p / m;
+      }
+      S.sp.shift_v(r0, dr, r);
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) S.r_out[(size_t)a * DIM + k] = r[k];
     }
     if (S.pos_sorted) {
       T w = S.species ? (T)S.species[a] : T(0);
-      S.pos_sorted[S.inv_perm[a]] = mk4<T>(S.sp.to_real(r[0], 0), S.sp.to_real(r[1], 1),
-                                           DIM == 3 ? S.sp.to_real(r[2], DIM - 1) : T(0), w);
+      T q[3] = {T(0), T(0), T(0)};
+      S.sp.to_real_v(r, q);
+      S.pos_sorted[S.inv_perm[a]] = mk4<T>(q[0], q[1], DIM == 3 ? q[DIM - 1] : T(0), w);
     }
     if (S.skin_blk && a < s_rows) {
       // the next NeighborList.update(R') asks: did any atom move further than skin/2

@@ -176,9 +176,10 @@ template <typename T, int DIM>
 __device__ __forceinline__ typename Vec4<T>::type load_atom(const NbrP<T, DIM>& P, int i) {
   const T* r = P.position + (size_t)i * DIM;
   // (periodic_general with fractional coordinates: the sorted copy is in real space)
-  T z = DIM == 3 ? P.sp.to_real(r[DIM - 1], DIM - 1) : T(0);
+  T q[3] = {T(0), T(0), T(0)};
+  P.sp.to_real_v(r, q);
   T w = P.species ? (T)P.species[i] : T(0);
-  return make_v4<T>(P.sp.to_real(r[0], 0), P.sp.to_real(r[1], 1), z, w);
+  return make_v4<T>(q[0], q[1], DIM == 3 ? q[DIM - 1] : T(0), w);
 }
 
 
@@ -1516,6 +1517,9 @@ int fill(NbrP<T, DIM>& P, const jmd_nbr_t* nb, const void* position) {
   }
   for (int k = 0; k < DIM; ++k)
     if (P.cps[k] < 2 * P.sw + 3) P.filter = 0;
+  // full-matrix boxes: every candidate takes the exact metric (the pre-filter's image shift and
+  // band are derived for axis-aligned cells)
+  if (nb->space.general && nb->space.triclinic) P.filter = 0;
   P.cell_count = nb->cell_count; P.cell_start = nb->cell_start; P.cell_cursor = nb->cell_cursor;
   P.scan_tmp = nb->scan_tmp; P.hash = nb->hash; P.tmp_ids = nb->tmp_ids; P.perm = nb->perm;
   P.inv_perm = nb->inv_perm; P.ref_count = nb->ref_count;

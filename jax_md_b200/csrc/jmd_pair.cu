@@ -20,6 +20,12 @@ int jmd_launch_pair_staged(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* forc
                            double* dparam, double* partials, void* momentum, const void* mass,
                            int mass_is_array, double dt_2, const void* dt_dev, bool want_e, cudaStream_t s);
 
+// full-matrix periodic_general boxes live in jmd_pair_tric.cu
+template <typename T, int DIM>
+int jmd_launch_pair_tric(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, void* e_atom, double* red,
+                         double* dparam, double* partials, void* momentum, const void* mass,
+                         int mass_is_array, double dt_2, const void* dt_dev, bool want_e, cudaStream_t s);
+
 namespace {
 // The staged kernel serves scalar and per-species parameters (the species id
 // travels in pos.w); per-atom / matrix parameters need the neighbour's atom id.
@@ -27,6 +33,9 @@ template <typename T, int DIM>
 int launch_pair_any(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, void* e_atom, double* red,
                     double* dparam, double* partials, void* momentum, const void* mass, int mass_is_array,
                     double dt_2, const void* dt_dev, bool want_e, cudaStream_t s) {
+  if (nb->space.general && nb->space.triclinic)
+    return jmd_launch_pair_tric<T, DIM>(nb, pp, force, e_atom, red, dparam, partials, momentum, mass,
+                                        mass_is_array, dt_2, dt_dev, want_e, s);
   bool stage = nb->staged && nb->nl16 && nb->blk_table && nb->use_cells;
   for (int k = 0; k < 3; ++k)
     if (pp->mode[k] == JMD_PARAM_PER_ATOM || pp->mode[k] == JMD_PARAM_MATRIX) stage = false;

@@ -1,15 +1,23 @@
 // Shared implementation of the pair-force kernels; included twice:
 //   jmd_pair.cu          JMD_PAIR_STAGED 0  neighbour positions gathered from global memory
 //   jmd_pair_staged.cu   JMD_PAIR_STAGED 1  ... from a per-block shared-memory staging buffer
+//   jmd_pair_tric.cu     JMD_PAIR_TRIC 1    global gathers, minimum image through the full box matrix
+//                                            (space.periodic_general with off-diagonal elements)
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 #include <type_traits>
 #include "jmd_common.cuh"
 
+#ifndef JMD_PAIR_TRIC
+#define JMD_PAIR_TRIC 0
+#endif
 #if JMD_PAIR_STAGED
 #define JMD_PAIR_KERNEL k_pair_force_staged
 #define JMD_PAIR_LAUNCHER launch_pair_staged_impl
+#elif JMD_PAIR_TRIC
+#define JMD_PAIR_KERNEL k_pair_force_tric
+#define JMD_PAIR_LAUNCHER launch_pair_tric_impl
 #else
 #define JMD_PAIR_KERNEL k_pair_force
 #define JMD_PAIR_LAUNCHER launch_pair_impl
@@ -309,11 +317,16 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
       d[2] = DIM == 3 ? pi.z - pj.z : T(0);
       bool far = fabs(d[0]) > hx || fabs(d[1]) > hy;
       if (DIM == 3) far = far || fabs(d[2]) > hz;
+#if JMD_PAIR_TRIC
+      if (far) Q.sp.wrap_tric(d);      // full-matrix box: d - H rint(H^-1 d); half[] holds the bounds
+                                       // under which the raw difference already is that image
+#else
       if (JMD_PAIR_ALWAYS_WRAP || far) {
         d[0] = Q.sp.wrap_fast(d[0], 0);
         d[1] = Q.sp.wrap_fast(d[1], 1);
         if (DIM == 3) d[2] = Q.sp.wrap_fast(d[2], DIM - 1);
       }
+#endif
       const T r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
       T sigma = sig0, eps = eps0, alpha = alp0;
       if (!SCALAR) {

@@ -118,8 +118,15 @@ __global__ void __launch_bounds__(SWB) k_sw_compact(SwP<T> S) {
     for (int k = 0; k < cnt; ++k) {
       const int j = __ldcs(col + (size_t)k * S.n_pad);
       const V4 pj = S.pos_sorted[j];
-      const T dx = S.sp.disp_fast(pj.x, pi.x, 0), dy = S.sp.disp_fast(pj.y, pi.y, 1),
-              dz = S.sp.disp_fast(pj.z, pi.z, 2);
+      T dx, dy, dz;
+      if (S.sp.tric) {                        // full-matrix box (periodic_general)
+        T d[3] = {pj.x - pi.x, pj.y - pi.y, pj.z - pi.z};
+        S.sp.wrap_tric(d);
+        dx = d[0]; dy = d[1]; dz = d[2];
+      } else {
+        dx = S.sp.disp_fast(pj.x, pi.x, 0); dy = S.sp.disp_fast(pj.y, pi.y, 1);
+        dz = S.sp.disp_fast(pj.z, pi.z, 2);
+      }
       const T r2 = dx * dx + dy * dy + dz * dz;
       if (r2 > T(0) && r2 < S.cutoff2) {      // conservative, skips the sqrt of skin-only entries
         const T r = sqrt(r2);

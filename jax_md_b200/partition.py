@@ -524,6 +524,11 @@ def neighbor_list(displacement_or_metric,
                      'space.periodic_general(box, fractional_coordinates=True)')
   if np.ndim(box_np) == 2 and not fractional_coordinates:
     box_np = np.asarray(space._box_diagonal(box_np), f32)
+    if box_np.ndim == 2 and not disable_cell_list:
+      raise NotImplementedError(
+          'a triclinic box with real-space positions has no cell grid here: use '
+          'space.periodic_general(box) with fractional_coordinates=True (the reference\'s own '
+          'recommendation, space.py:360-372), or disable_cell_list=True.')
   # the box currently in force (fractional coordinates: `box=` overrides, partition.py:1045)
   current = {'box': box_np, 'metric_box': None}
 

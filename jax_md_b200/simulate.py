@@ -406,7 +406,11 @@ def _box_volume(dim, box):
   # determinant is the product of the diagonal
   if box.ndim == 0:
     return box ** dim
-  return torch.prod(box) if box.ndim == 1 else torch.prod(torch.diagonal(box))
+  if box.ndim == 1:
+    return torch.prod(box)
+  if bool((torch.triu(box) == box).all()) or bool((torch.tril(box) == box).all()):
+    return torch.prod(torch.diagonal(box))            # triangular: det without an LU
+  return torch.linalg.det(box)
 
 
 def _npt_box_info(state):

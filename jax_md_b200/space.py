@@ -52,6 +52,8 @@ def space_struct(spec: SpaceSpec, dim: int, torch_dtype) -> '_lib.SpaceT':
   st.wrapped = 1 if spec.wrapped else 0
   if spec.kind == _lib.SPACE_PERIODIC:
     side = _box_diagonal(spec.side) if spec.general else spec.side
+    if spec.general and isinstance(side, np.ndarray) and side.ndim == 2:
+      return _triclinic_struct(st, spec, side, dim, np_dtype)
     full, half = _side_vectors(side, dim, np_dtype)
     for k in range(dim):
       st.side[k] = float(full[k])
@@ -70,18 +72,44 @@ def space_struct(spec: SpaceSpec, dim: int, torch_dtype) -> '_lib.SpaceT':
 
 
 def _box_diagonal(box):
-  """Scalar / vector / DIAGONAL-matrix box -> scalar or vector; a box with non-zero
-  off-diagonal elements (triclinic) is not served by the kernels."""
+  """Scalar / vector / DIAGONAL-matrix box -> scalar or vector (the orthorhombic kernels);
+  a matrix with off-diagonal elements is returned as it is (triclinic kernels)."""
   if isinstance(box, torch.Tensor):
     box = box.detach().cpu().numpy()
   b = np.asarray(box) if not isinstance(box, (float, int)) else box
   if isinstance(b, np.ndarray) and b.ndim == 2:
     if not np.array_equal(np.diag(np.diag(b)), b):
-      raise NotImplementedError(
-          'space.periodic_general with a triclinic box (off-diagonal elements): the CUDA kernels '
-          'serve scalar, vector and diagonal-matrix boxes (SURVEY.md 8f row 3).')
+      return b
     return np.diag(b).copy()
   return b
+
+
+def is_triclinic(box) -> bool:
+  b = _box_diagonal(box)
+  return isinstance(b, np.ndarray) and b.ndim == 2
+
+
+def _triclinic_struct(st, spec, box, dim, np_dtype):
+  """jmd_space_t for a full-matrix box: real = box @ fractional (space.py:128-150).  The inverse
+  is formed in the box's own precision like `space.inverse` (space.py:110-121)."""
+  if box.shape != (dim, dim):
+    raise ValueError(f'box matrix must be [{dim}, {dim}], found {box.shape}')
+  mdt = box.dtype.type if box.dtype in (np.float32, np.float64) else np_dtype
+  H = box.astype(mdt)
+  Hi = np.linalg.inv(H).astype(mdt)
+  st.general, st.triclinic = 1, 1
+  st.fractional = 1 if spec.fractional else 0
+  for i in range(dim):
+    for j in range(dim):
+      st.box_m[3 * i + j] = float(np_dtype(H[i, j]))
+      st.inv_box_m[3 * i + j] = float(np_dtype(Hi[i, j]))
+  for k in range(dim):
+    st.side[k] = float(H[k, k])
+    st.inv_box[k] = float(1.0 / H[k, k])
+    # |d_j| <= half[j] for all j  =>  |(H^-1 d)_i| <= 1/2: the raw difference is the minimum image
+    col = np.abs(Hi[:, k].astype(np.float64)).max()
+    st.half[k] = 0.5 / (dim * col) * (1.0 - 1e-3)
+  return st
 
 
 def _as_like(x, ref):

@@ -50,7 +50,17 @@ def raw_transform(box, R):
     return R * box
   if box.ndim == 1:
     return R * box
-  return np.einsum('ij,...j->...i', box, R)
+  # 'ij,...j->...i'.  XLA does not pin the summation order of this contraction (parity for matrix
+  # boxes is unpinned beyond rounding); the restatement and the kernels both sum j = 0, 1, 2 with
+  # separately rounded products, which makes them comparable bit for bit.
+  R = np.asarray(R)
+  out = np.empty(R.shape, np.result_type(box, R))
+  for i in range(box.shape[0]):
+    acc = box[i, 0] * R[..., 0]
+    for j in range(1, box.shape[1]):
+      acc = acc + box[i, j] * R[..., j]
+    out[..., i] = acc
+  return out
 
 
 def free():

@@ -32,7 +32,7 @@ def test_struct_layout_matches_header():
   """ctypes mirrors of the PODs must have the C layout (sizes from the header
   arithmetic: no hidden padding surprises)."""
   from jax_md_b200 import _lib
-  assert ctypes.sizeof(_lib.SpaceT) == 16 + 48 + 8 + 24
+  assert ctypes.sizeof(_lib.SpaceT) == 16 + 48 + 8 + 24 + 2 * 72
   assert ctypes.sizeof(_lib.SwT) == 64
   assert ctypes.sizeof(_lib.PairT) == 8 + 12 + 4 + 8 + 24 + 24 + 40
   n = _lib.NbrT
