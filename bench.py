@@ -198,6 +198,15 @@ def measure_single(cells, steps, warmup, fmt_name, unroll):
   return out
 
 
+def untimed_steps(args):
+  """Steps every arm (1 GPU or N) runs before the timed window: the warm-up, one block of
+  `unroll` steps in which the loop's CUDA graph is captured when the warm-up was too short to
+  do it, and one more replayed block."""
+  if args.loop != 'graph' or args.steps < args.unroll:
+    return args.warmup
+  return args.warmup + (args.unroll if args.warmup >= args.unroll else 2 * args.unroll)
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -454,6 +463,7 @@ def run_b200(args):
                              f'kT={KT} NVE, neighbour format {args.format}',
                  'atoms': N, 'l2_policy': 'working set (idx rows %.0f MB + state) exceeds L2'
                  % (pairs * 4 / 1e6), 'rebuilds_in_timed_region': int(builds),
+                 'untimed_steps_before_window': untimed_steps(args),
                  'loop': ('jax_md_b200.lax.fori_loop: CUDA graph of %d steps, replayed' % args.unroll)
                  if args.loop == 'graph' else 'eager Python loop',
                  'neighbor_overflow': overflow},

@@ -683,6 +683,12 @@ class SlabDomain:
 # bench.py entry for N > 1
 # ----------------------------------------------------------------------------------
 
+def untimed_steps(args):
+  """Steps run before the timed window: the same count as the single-GPU arm (bench.py)."""
+  import bench
+  return bench.untimed_steps(args)
+
+
 def measure_domain(args, comm, rank, world, dev, cells):
   """value / ms_per_step of `args.steps` steps for a slab of `cells` fcc cells per rank
   (stacked along x): the extra points of the multi-GPU JSON line."""
@@ -702,7 +708,7 @@ def measure_domain(args, comm, rank, world, dev, cells):
   Rd, Pd = torch.as_tensor(R_loc, device=dev), torch.as_tensor(P_loc, device=dev)
   Pd -= (comm.sum(Pd.sum(0, dtype=torch.float64)) / (world * N_loc)).to(Pd.dtype)
   st = dom.init(Rd, Pd, torch.arange(N_loc, device=dev) + rank * N_loc)
-  for _ in range(max(args.warmup, 4)):
+  for _ in range(untimed_steps(args)):
     st = dom.step(st)
   torch.cuda.synchronize()
   dist.barrier()
@@ -756,7 +762,7 @@ def bench_domain(args, world, rank, dev):
   Pd -= (psum / (world * N_loc)).to(Pd.dtype)
   gid = torch.arange(N_loc, device=dev) + rank * N_loc
   st = dom.init(Rd, Pd, gid)
-  for _ in range(args.warmup):
+  for _ in range(untimed_steps(args)):
     st = dom.step(st)
   torch.cuda.synchronize()
   dist.barrier()
@@ -892,6 +898,7 @@ def bench_domain(args, world, rank, dev):
                    'atoms': N, 'ghost_atoms_per_gpu': int(n_ghost.item()),
                    'halo_bytes_per_step_per_gpu': face_bytes,
                    'rebuilds_in_timed_region': rebuilds_timed,
+                   'untimed_steps_before_window': untimed_steps(args),
                    'loop': ('CUDA graph of the 4 step kernels (drift, peer-memory push, wait+unpack, force); '
                             'host polls the device-written rebuild decision; rebuilds host-driven')
                    if dom_graph else 'eager loop',
