@@ -70,6 +70,53 @@ __device__ __forceinline__ double rint_magic(double x) {
   return __dadd_rn(__dadd_rn(x, 6755399441055744.0), -6755399441055744.0);
 }
 
+// Full-matrix box of space.periodic_general (row-major H: real_i = sum_j H[i][j] frac_j) and its
+// inverse.  The exact metric for it is deliberately NOT inlined into the neighbour-list kernels:
+// inlined, it pushed the Dense stencil scan past ptxas' inlining budget, the kernel-parameter
+// struct got materialised in local memory and the scan went from 0.8 to 4.8 ms for ORTHORHOMBIC
+// boxes.  As a call it costs the common path one uniform branch.
+template <typename T, int DIM>
+struct TricM {
+  T H[DIM * DIM];
+  T Hi[DIM * DIM];
+  int frac;
+};
+
+template <typename T, int DIM>
+__device__ __forceinline__ void tric_matvec(const T* M, const T* v, T* out) {
+  // space.raw_transform's einsum (space.py:128-150): XLA does not pin the summation order; here
+  // (and in the oracle) it is j = 0, 1, 2 with separately rounded products and sums
+  if (DIM == 2) {
+    out[0] = add_rn(mul_rn(M[0], v[0]), mul_rn(M[1], v[1]));
+    out[1] = add_rn(mul_rn(M[2], v[0]), mul_rn(M[3], v[1]));
+  } else {
+    constexpr int Q = DIM * DIM, Z = 2 % DIM;      // (keeps indices in range where DIM == 2 is compiled)
+    out[0] = add_rn(add_rn(mul_rn(M[0], v[0]), mul_rn(M[1], v[1])), mul_rn(M[2 % Q], v[Z]));
+    out[1] = add_rn(add_rn(mul_rn(M[3], v[0]), mul_rn(M[4 % Q], v[1])), mul_rn(M[5 % Q], v[Z]));
+    out[Z] = add_rn(add_rn(mul_rn(M[6 % Q], v[0]), mul_rn(M[7 % Q], v[1])), mul_rn(M[8 % Q], v[Z]));
+  }
+}
+
+// exact squared distance of periodic_general with a matrix box (space.py:419-433):
+// |H (mod(ua - ub + 1/2, 1) - 1/2)|^2, ua = a (unit cube) or H^-1 a
+template <typename T, int DIM>
+__device__ __noinline__ T dist2_tric_call(TricM<T, DIM> m, T a0, T a1, T a2, T b0, T b1, T b2) {
+  const T a[3] = {a0, a1, a2}, b[3] = {b0, b1, b2};
+  T ua[3] = {a0, a1, a2}, ub[3] = {b0, b1, b2}, w[3] = {T(0), T(0), T(0)}, g[3] = {T(0), T(0), T(0)};
+  if (!m.frac) {
+    tric_matvec<T, DIM>(m.Hi, a, ua);
+    tric_matvec<T, DIM>(m.Hi, b, ub);
+  }
+#pragma unroll
+  for (int k = 0; k < DIM; ++k)
+    w[k] = sub_rn(mod_pos(add_rn(sub_rn(ua[k], ub[k]), T(0.5)), T(1)), T(0.5));
+  tric_matvec<T, DIM>(m.H, w, g);
+  T acc = mul_rn(g[0], g[0]);
+#pragma unroll
+  for (int k = 1; k < DIM; ++k) acc = add_rn(acc, mul_rn(g[k], g[k]));
+  return acc;
+}
+
 template <typename T, int DIM>
 struct Space {
   T side[DIM];
@@ -82,9 +129,8 @@ struct Space {
   int general;       // space.periodic_general, orthorhombic (see jmd_space_t)
   int frac;          // ... with positions stored in the unit cube
   T ibox[DIM];       // 1 / box
-  int tric;          // ... with a full box matrix: H (row-major) and its inverse replace side / ibox
-  T H[DIM * DIM];
-  T Hi[DIM * DIM];
+  int tric;          // ... with a full box matrix: tm.H and its inverse replace side / ibox
+  TricM<T, DIM> tm;
   __host__ void init(const jmd_space_t& s) {
     periodic = s.kind == JMD_SPACE_PERIODIC;
     wrapped = s.wrapped;
@@ -93,9 +139,10 @@ struct Space {
     tric = general && s.triclinic;
     for (int i = 0; i < DIM; ++i)
       for (int j = 0; j < DIM; ++j) {
-        H[i * DIM + j] = tric ? (T)s.box_m[i * 3 + j] : T(i == j);
-        Hi[i * DIM + j] = tric ? (T)s.inv_box_m[i * 3 + j] : T(i == j);
+        tm.H[i * DIM + j] = tric ? (T)s.box_m[i * 3 + j] : T(i == j);
+        tm.Hi[i * DIM + j] = tric ? (T)s.inv_box_m[i * 3 + j] : T(i == j);
       }
+    tm.frac = frac;
     for (int k = 0; k < DIM; ++k) ibox[k] = general ? (T)s.inv_box[k] : T(1);
     for (int k = 0; k < DIM; ++k) {
       side[k] = (T)s.side[k];
@@ -159,21 +206,9 @@ struct Space {
   // fractional -> real (what the cell-sorted copy holds)
   __device__ __forceinline__ T to_real(T r, int k) const { return frac ? mul_rn(r, side[k]) : r; }
 
-  // ---- full-matrix boxes (space.raw_transform with a 2-d box, space.py:128-150): the einsum's
-  // summation order is XLA's to choose; here (and in the oracle) it is j = 0, 1, 2 with
-  // separately rounded products and sums.
-  __device__ __forceinline__ void matvec(const T* M, const T* v, T* out) const {
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      T acc = mul_rn(M[i * DIM], v[0]);
-#pragma unroll
-      for (int j = 1; j < DIM; ++j) acc = add_rn(acc, mul_rn(M[i * DIM + j], v[j]));
-      out[i] = acc;
-    }
-  }
-  // all components at once; handles every kind of space
+  // ---- full-matrix boxes: all components at once (drift kernel, packing) -----------------
   __device__ __forceinline__ void to_real_v(const T* r, T* out) const {
-    if (tric && frac) { matvec(H, r, out); return; }
+    if (tric && frac) { tric_matvec<T, DIM>(tm.H, r, out); return; }
 #pragma unroll
     for (int k = 0; k < DIM; ++k) out[k] = to_real(r[k], k);
   }
@@ -189,12 +224,12 @@ struct Space {
       return;
     }
     T du[DIM], u[DIM];
-    matvec(Hi, dr, du);
+    tric_matvec<T, DIM>(tm.Hi, dr, du);
     if (frac) {
 #pragma unroll
       for (int k = 0; k < DIM; ++k) u[k] = r[k];
     } else {
-      matvec(Hi, r, u);
+      tric_matvec<T, DIM>(tm.Hi, r, u);
     }
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
@@ -205,45 +240,25 @@ struct Space {
 #pragma unroll
       for (int k = 0; k < DIM; ++k) out[k] = u[k];
     } else {
-      matvec(H, u, out);
+      tric_matvec<T, DIM>(tm.H, u, out);
     }
-  }
-  // exact squared distance of periodic_general with a matrix box
-  __device__ __forceinline__ T dist2_tric(const T* a, const T* b) const {
-    T ua[DIM], ub[DIM], m[DIM], g[DIM];
-    if (frac) {
-#pragma unroll
-      for (int k = 0; k < DIM; ++k) { ua[k] = a[k]; ub[k] = b[k]; }
-    } else {
-      matvec(Hi, a, ua);
-      matvec(Hi, b, ub);
-    }
-#pragma unroll
-    for (int k = 0; k < DIM; ++k)
-      m[k] = sub_rn(mod_pos(add_rn(sub_rn(ua[k], ub[k]), T(0.5)), T(1)), T(0.5));
-    matvec(H, m, g);
-    T acc = mul_rn(g[0], g[0]);
-#pragma unroll
-    for (int k = 1; k < DIM; ++k) acc = add_rn(acc, mul_rn(g[k], g[k]));
-    return acc;
   }
   // minimum image of a real-space difference, tolerance-level (force kernels):
   // d - H rint(H^-1 d)
   __device__ __forceinline__ void wrap_tric(T* d) const {
-    T f[DIM];
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      T acc = Hi[i * DIM] * d[0];
-#pragma unroll
-      for (int j = 1; j < DIM; ++j) acc += Hi[i * DIM + j] * d[j];
-      f[i] = rint_magic(acc);
-    }
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      T acc = d[i];
-#pragma unroll
-      for (int j = 0; j < DIM; ++j) acc -= H[i * DIM + j] * f[j];
-      d[i] = acc;
+    if (DIM == 2) {
+      const T f0 = rint_magic(tm.Hi[0] * d[0] + tm.Hi[1] * d[1]);
+      const T f1 = rint_magic(tm.Hi[2] * d[0] + tm.Hi[3] * d[1]);
+      d[0] -= tm.H[0] * f0 + tm.H[1] * f1;
+      d[1] -= tm.H[2] * f0 + tm.H[3] * f1;
+    } else {
+      constexpr int Q = DIM * DIM, Z = 2 % DIM;      // (keeps the indices in range when DIM == 2 is compiled)
+      const T f0 = rint_magic(tm.Hi[0] * d[0] + tm.Hi[1] * d[1] + tm.Hi[2 % Q] * d[Z]);
+      const T f1 = rint_magic(tm.Hi[3] * d[0] + tm.Hi[4 % Q] * d[1] + tm.Hi[5 % Q] * d[Z]);
+      const T f2 = rint_magic(tm.Hi[6 % Q] * d[0] + tm.Hi[7 % Q] * d[1] + tm.Hi[8 % Q] * d[Z]);
+      d[0] -= tm.H[0] * f0 + tm.H[1] * f1 + tm.H[2 % Q] * f2;
+      d[1] -= tm.H[3] * f0 + tm.H[4 % Q] * f1 + tm.H[5 % Q] * f2;
+      d[Z] -= tm.H[6 % Q] * f0 + tm.H[7 % Q] * f1 + tm.H[8 % Q] * f2;
     }
   }
 };
@@ -251,7 +266,9 @@ struct Space {
 // Exact squared distance sum_k d_k^2, sequential (space.py:227-235).
 template <typename T, int DIM>
 __device__ __forceinline__ T dist2_exact(const Space<T, DIM>& sp, const T* a, const T* b) {
-  if (sp.tric) return sp.dist2_tric(a, b);
+  if (sp.tric)
+    return dist2_tric_call<T, DIM>(sp.tm, a[0], a[1], DIM == 3 ? a[DIM - 1] : T(0), b[0], b[1],
+                                   DIM == 3 ? b[DIM - 1] : T(0));
   if (sp.general) {
     T g = sp.disp_general(a[0], b[0], 0);
     T acc = mul_rn(g, g);

@@ -1168,7 +1168,7 @@ inline int grid_for(long long work_items, int per_block, int cap_blocks) {
 // FMT: 0 Dense (forward + reverse test), 1 Sparse, 2 OrderedSparse.  Each variant
 // is its own kernel so that it gets its own register allocation.
 template <typename T, int DIM, int FMT, bool PERIODIC, int W, bool FILTER>
-__global__ void __launch_bounds__(NB, sizeof(T) == 8 ? 2 : JMD_SCAN_MIN_BLOCKS) k_nbr_stencil_scan(NbrP<T, DIM> P, int gated) {
+__global__ void __launch_bounds__(NB, sizeof(T) == 8 ? 2 : JMD_SCAN_MIN_BLOCKS) k_nbr_stencil_scan(const __grid_constant__ NbrP<T, DIM> P, int gated) {
   if (gate_closed(P.state, gated)) return;
   constexpr int MODE = (FMT == 0 && PERIODIC) ? 1 : 0;
   // COUNT (OrderedSparse occupancy pass of allocate: no rows are written, so the

@@ -34,3 +34,21 @@ def test_headline_force_kernel_issues_four_index_loads_before_the_first_gather()
   assert len(streamed_before) == 4, loads[:first_gather + 1]
   # no local-memory traffic: a spilled parameter struct was the 0.36 ms variant
   assert not any(o.startswith(('LDL', 'STL')) for o in ops)
+
+
+@pytest.mark.skipif(shutil.which('cuobjdump') is None or not os.path.exists(LIB),
+                    reason='needs cuobjdump and the built library')
+def test_no_kernel_keeps_its_parameter_struct_in_local_memory():
+  """A device function that takes the kernel-parameter struct by reference and is NOT inlined makes
+  ptxas materialise the whole struct (0.9 - 1.2 KB) in local memory; every field read then goes
+  through the stack (measured: the Dense stencil scan 0.8 -> 4.8 ms).  The stack size cuobjdump
+  reports (kernel + callees) stays well under the struct size when that has not happened."""
+  out = subprocess.run(['cuobjdump', '-res-usage', LIB], capture_output=True, text=True, check=True).stdout
+  names = re.findall(r'Function ([^:\s]+):', out)
+  stacks = [int(x) for x in re.findall(r'STACK:(\d+)', out)]
+  assert names and len(names) == len(stacks)
+  dem = subprocess.run(['c++filt'], input='\n'.join(names), capture_output=True, text=True,
+                       check=True).stdout.split('\n')
+  bad = [(d[:120], s) for d, s in zip(dem, stacks)
+         if s >= (1000 if '<double' in d else 600)]
+  assert not bad, bad
