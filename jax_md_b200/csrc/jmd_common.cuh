@@ -264,9 +264,12 @@ struct Space {
 };
 
 // Exact squared distance sum_k d_k^2, sequential (space.py:227-235).
-template <typename T, int DIM>
+// TRIC_OK = false compiles the full-matrix branch out: the pre-filtered stencil scans never see a
+// triclinic box (their filter is off for it), and even as a rarely taken CALL the branch cost the
+// Dense scan its register allocation (0.8 -> 4.9 ms at N = 1M).
+template <typename T, int DIM, bool TRIC_OK = true>
 __device__ __forceinline__ T dist2_exact(const Space<T, DIM>& sp, const T* a, const T* b) {
-  if (sp.tric)
+  if (TRIC_OK && sp.tric)
     return dist2_tric_call<T, DIM>(sp.tm, a[0], a[1], DIM == 3 ? a[DIM - 1] : T(0), b[0], b[1],
                                    DIM == 3 ? b[DIM - 1] : T(0));
   if (sp.general) {

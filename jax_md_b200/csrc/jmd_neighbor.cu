@@ -657,7 +657,7 @@ __device__ __forceinline__ void append_if_below(double a2, double lo, int rank, 
 // periodic_general: the reference evaluates the metric on the USER's coordinates (unit cube
 // or real space, space.py:419-433), not on the real-space sorted copy: fetch them by id.
 // Dense (MODE 1) keeps a pair only if both orientations pass (partition.py:960-980).
-template <typename T, int DIM, int MODE>
+template <typename T, int DIM, int MODE, bool TRIC_OK = true>
 __device__ __forceinline__ bool general_keep(const NbrP<T, DIM>& P, int home_id, int cand_id, T c2) {
   T a[DIM], b[DIM];
 #pragma unroll
@@ -665,15 +665,15 @@ __device__ __forceinline__ bool general_keep(const NbrP<T, DIM>& P, int home_id,
     a[k] = P.position[(size_t)home_id * DIM + k];
     b[k] = P.position[(size_t)cand_id * DIM + k];
   }
-  bool keep = dist2_exact<T, DIM>(P.sp, a, b) < c2;
-  if (MODE == 1) keep = keep && (dist2_exact<T, DIM>(P.sp, b, a) < c2);
+  bool keep = dist2_exact<T, DIM, TRIC_OK>(P.sp, a, b) < c2;
+  if (MODE == 1) keep = keep && (dist2_exact<T, DIM, TRIC_OK>(P.sp, b, a) < c2);
   return keep;
 }
 
 // The reference's candidate test on one (home, candidate) pair, bit for bit:
 // forward d2(R_i, R_c) < cutoff^2 (partition.py:945-951) and, for Dense (MODE 1),
 // the reverse-orientation re-test inside the rounding band (partition.py:960-980).
-template <typename T, int DIM, int MODE, bool PERIODIC>
+template <typename T, int DIM, int MODE, bool PERIODIC, bool TRIC_OK = true>
 __device__ __forceinline__ bool exact_keep(const NbrP<T, DIM>& P, const T (&hp)[3],
                                            const typename Vec4<T>::type& cv, const T (&hh)[3],
                                            const T (&qq)[3], T c2) {
@@ -702,14 +702,14 @@ __device__ __forceinline__ bool exact_keep(const NbrP<T, DIM>& P, const T (&hp)[
       }
     } else {
       const T cp[3] = {cv.x, cv.y, cv.z};
-      d2 = dist2_exact<T, DIM>(P.sp, hp, cp);
+      d2 = dist2_exact<T, DIM, TRIC_OK>(P.sp, hp, cp);
     }
   }
   bool keep = d2 < c2;
   if (MODE == 1 && PERIODIC) {
     if (slow || (fabs(d2 - c2) <= P.band)) {
       const T cp[3] = {cv.x, cv.y, cv.z};
-      keep = keep && (dist2_exact<T, DIM>(P.sp, cp, hp) < c2);
+      keep = keep && (dist2_exact<T, DIM, TRIC_OK>(P.sp, cp, hp) < c2);
     }
   }
   return keep;
@@ -832,8 +832,8 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
             T a2 = ax * ax + ay * ay;
             if (DIM == 3) { const T az = h2 - cv.z; a2 += az * az; }
             if (!(a2 < lo_c) && !(a2 > hi_c))     // rare: inside the band / dirty cell
-              a2 = (P.sp.general ? general_keep<T, DIM, MODE>(P, hid, __ldg(&P.perm[rank]), c2)
-                                 : exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2)) ? T(-2) : (T)INFINITY;
+              a2 = (P.sp.general ? general_keep<T, DIM, MODE, !FILTER>(P, hid, __ldg(&P.perm[rank]), c2)
+                                 : exact_keep<T, DIM, MODE, PERIODIC, !FILTER>(P, hp, cv, hh, qq, c2)) ? T(-2) : (T)INFINITY;
             const int k_before = k;
             append_if_below<STAGE>(a2, lo_c, rank, self, off_end, (unsigned)P.n_pad, P.nl, P.nl16, lbase, off, k);
             if (ORDERED && COUNT) { if (k != k_before) kl += (__ldg(&P.perm[rank]) < hid); }
@@ -852,8 +852,8 @@ __device__ void ph_build_cells(const NbrP<T, DIM>& P) {
         } else {
           for (int rank = start; rank < end; ++rank) {
             const V4 cv = pos[rank];
-            bool keep = P.sp.general ? general_keep<T, DIM, MODE>(P, hid, __ldg(&P.perm[rank]), c2)
-                                     : exact_keep<T, DIM, MODE, PERIODIC>(P, hp, cv, hh, qq, c2);
+            bool keep = P.sp.general ? general_keep<T, DIM, MODE, !FILTER>(P, hid, __ldg(&P.perm[rank]), c2)
+                                     : exact_keep<T, DIM, MODE, PERIODIC, !FILTER>(P, hp, cv, hh, qq, c2);
             keep = keep && (rank != self);
             if (keep) {
               if (off < off_end) {
