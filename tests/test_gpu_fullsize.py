@@ -168,3 +168,30 @@ def test_soft_sphere_256k_fire_reduces_energy():
   E1 = float(efn(st.position, neighbor=nbrs))
   assert E1 < 0.5 * E0
   assert torch.isfinite(st.position).all()
+
+
+def test_every_format_rebuilds_at_the_same_speed():
+  """The three formats run the same candidate scan; one of them coming out several times slower
+  is a code-generation accident (round 2: a rarely taken CALL left in the Dense scan's loop cost
+  it 6x and with it the domain decomposition's rebuild).  Ratios, not absolute times."""
+  from jax_md_b200 import _lib
+  jmd = _jmd()
+  R, L = _lj_1m()
+  d, _ = jmd.space.periodic(L)
+  t = {}
+  for fmt in ('Dense', 'Sparse', 'OrderedSparse'):
+    nf = jmd.partition.neighbor_list(d, L, 2.5, 0.3, format=jmd.partition.NeighborListFormat[fmt])
+    nb = nf.allocate(R)
+    ws, st, pp = nb._ws, _lib.stream(), _lib.ptr(R)
+    best = 1e9
+    for _ in range(3):
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      _lib.call('jmd_nbr_build', ws.ref(), pp, 0, 0, st)
+      b.record()
+      torch.cuda.synchronize()
+      best = min(best, a.elapsed_time(b))
+    t[fmt] = best
+    del nb, nf
+    torch.cuda.empty_cache()
+  assert max(t.values()) < 2.0 * min(t.values()), t

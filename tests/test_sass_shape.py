@@ -52,3 +52,10 @@ def test_no_kernel_keeps_its_parameter_struct_in_local_memory():
   bad = [(d[:120], s) for d, s in zip(dem, stacks)
          if s >= (1000 if '<double' in d else 600)]
   assert not bad, bad
+  # the pre-filtered f32 scans (every production rebuild: LJ / soft-sphere / SW lists, the domain
+  # decomposition's Dense list) run without any stack at all; a CALL left in their loop body was
+  # enough to cost the Dense one 6x
+  hot = [(d[:120], s) for d, s in zip(dem, stacks)
+         if re.search(r'k_nbr_stencil_scan<float, \d, \d, true, \d, true>', d) and s != 0]
+  assert not hot, hot
+  assert any(re.search(r'k_nbr_stencil_scan<float, 3, 0, true, 1, true>', d) for d in dem)
