@@ -326,13 +326,13 @@ class StillingerWeberFn:
       raise TypeError('energy_fn(R, neighbor=...) needs a NeighborList')
     fn = self
     box = kwargs.get('box')
-    if box is not None and neighbor._ws is not None:
+    if neighbor._ws is not None:
       neighbor._ws.set_box(self.spec, box)
     if torch.is_grad_enabled() and R.requires_grad:
       class _E(torch.autograd.Function):
         @staticmethod
         def forward(ctx, Rin):
-          out = fn.launch(Rin.detach(), neighbor)
+          out = fn.launch(Rin.detach(), neighbor, box=box)
           ctx.force = out['force']
           return out['red'][_lib.RED_ENERGY].to(Rin.dtype)
 
@@ -340,7 +340,7 @@ class StillingerWeberFn:
         def backward(ctx, g):
           return -(g * ctx.force)
       return _E.apply(R)
-    out = self.launch(R, neighbor)
+    out = self.launch(R, neighbor, box=box)
     return out['red'][_lib.RED_ENERGY].to(R.dtype)
 
 

@@ -133,9 +133,18 @@ class Workspace:
     self.c.species = species.data_ptr()
 
   def set_box(self, spec, box):
-    """`box=` of an energy / force call on a periodic_general space: later kernels use it."""
-    if box is None or not getattr(spec, 'general', False):
+    """The box of ONE call on a periodic_general space: `box=` when the call passes it, else the
+    box the displacement function was made with -- the reference's calls are functional, a
+    `box=` of an earlier call never carries over (space.py:419-433, partition.py:1145)."""
+    if not getattr(spec, 'general', False):
       return
+    if box is None:
+      if getattr(self, '_box_token', None) == 'default':
+        return
+      self._box_token = 'default'
+      self.c.space = space.space_struct(spec, self.dim, self.dtype)
+      return
+    self._box_token = 'call'
     b = box.detach().cpu().numpy() if isinstance(box, torch.Tensor) else box
     self.c.space = space.space_struct(spec._replace(side=b), self.dim, self.dtype)
 
@@ -657,8 +666,11 @@ def neighbor_list(displacement_or_metric,
     reads occupancies back to the host)."""
     if 'box' in kwargs:
       _box_kwarg(kwargs['box'])
+    else:                                    # (a box= of an earlier call does not carry over)
+      current['box'], current['metric_box'] = box_np, None
     position = position.contiguous()
     ws = _make_workspace(position, extra_capacity, n_capacity)
+    ws._box_token = 'call' if 'box' in kwargs else 'default'
     if fractional_coordinates and not disable_cell_list and is_box_valid(current['box']):
       # partition.py:1049: `err.update(MALFORMED_BOX, is_box_valid(box))` -- the bit is set
       # when the box IS valid (reference quirk, SURVEY appendix C.2; replicated, not fixed)
@@ -745,6 +757,11 @@ def neighbor_list(displacement_or_metric,
     elif 'box' in kwargs and ws is not None and spec.general:      # all-pairs: box only feeds the metric
       _box_kwarg(kwargs['box'])
       ws.c.space = space.space_struct(spec._replace(side=current['metric_box']), ws.dim, ws.dtype)
+    if ws is not None and spec.general:
+      if 'box' in kwargs:
+        ws._box_token = 'call'
+      else:
+        ws.set_box(spec, None)          # no box= on this call: the displacement function's own box
     if ws is None:
       raise ValueError('This NeighborList was not allocated by jax_md_b200.')
     if position.shape != (ws.n, ws.dim) or position.dtype != ws.dtype:

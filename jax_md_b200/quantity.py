@@ -76,7 +76,7 @@ def pressure(energy_fn, position, box, kinetic_energy=0.0, **kwargs):
   vol_0 = volume(dim, box)
   if getattr(energy_fn, '_jmd_fused', None) and not getattr(energy_fn, 'always_generic', False) \
       and getattr(kwargs.get('neighbor'), '_ws', None) is not None:
-    dUdV = torch.trace(energy_fn.virial(position, **kwargs))
+    dUdV = torch.trace(energy_fn.virial(position, box=box, **kwargs))     # U(eps) is evaluated AT `box` (:226)
   else:
     zero = torch.zeros((), dtype=position.dtype, device=position.device)
     dUdV = _dU_deps(energy_fn, position, zero, lambda e: 1 + e, kwargs)
@@ -89,7 +89,7 @@ def stress(energy_fn, position, box, mass=1.0, velocity=None, **kwargs):
   vol_0 = volume(dim, box)
   if getattr(energy_fn, '_jmd_fused', None) and not getattr(energy_fn, 'always_generic', False) \
       and getattr(kwargs.get('neighbor'), '_ws', None) is not None:
-    dUdV = energy_fn.virial(position, **kwargs)
+    dUdV = energy_fn.virial(position, box=box, **kwargs)
   else:
     zero = torch.zeros((dim, dim), dtype=position.dtype, device=position.device)
     eye = torch.eye(dim, dtype=position.dtype, device=position.device)

@@ -157,6 +157,7 @@ class _Stepper:
         ws.set_species(self.fn._species_tensor(species, R.device))
       else:
         ws.set_species(None)
+        ws.set_box(self.fn.spec, kwargs.get('box'))
       nb_ref = ws.ref()
     _lib.call('jmd_nve_kick_drift', C.byref(sp), dtc, N, nb_ref, _lib.ptr(R),
               _lib.ptr(P), _lib.ptr(F), _lib.ptr(mass), mass_is_array, dt_h,
@@ -174,7 +175,7 @@ class _Stepper:
       F2 = out['force']
     elif fused:
       out = self.fn.launch(R2, neighbor, momentum=P2, mass=mass, dt_2=dt2_h,
-                           dt_dev=dt_dev, red=red, refresh_positions=False)
+                           dt_dev=dt_dev, red=red, refresh_positions=False, box=kwargs.get('box'))
       F2 = out['force']
     else:
       F2 = self.force(R2, kwargs).contiguous()

@@ -12,6 +12,9 @@ Sources (read-only):
       used by tests/quantity_test.py:134-150, tests/simulate_test.py:121-150
   tests/data/lammps_lj_stress_test{,_states} -> lammps_lj.npz
       parser semantics: jax_md/test_util.py:370-405; tests/quantity_test.py:436-455
+  tests/data/lammps_npt_test               -> lammps_npt.npz
+      parser semantics: jax_md/test_util.py:423-444 (columns 2:5 unit-cube positions, 5:8
+      velocities, box 21.724 * I); the state of tests/simulate_test.py:586-690
 Scalar goldens quoted in the reference tests are written to goldens.json.
 """
 import json
@@ -45,6 +48,12 @@ def lammps():
            V=np.array(V), energy_per_atom=row[1], stress_row=np.array(row[2:]))
 
 
+def lammps_npt():
+  d = np.loadtxt(os.path.join(REF, 'lammps_npt_test'))
+  np.savez_compressed(os.path.join(OUT, 'lammps_npt.npz'), box=np.eye(3) * 21.724,
+                      position=d[:, 2:5], velocity=d[:, 5:8])
+
+
 def scalars():
   g = {
       'sw_diamond_energy_per_atom': -4.336503155764325,   # tests/energy_test.py:429,464-466
@@ -62,5 +71,6 @@ def scalars():
 if __name__ == '__main__':
   jammed()
   lammps()
+  lammps_npt()
   scalars()
   print('wrote', sorted(os.listdir(OUT)))

@@ -152,3 +152,48 @@ def test_sw_npt_runs_and_conserves():
   assert abs(inv1 - inv0) / len(R) < 1e-3, (inv0, inv1)
   T = float(jmd.simulate.temperature(st)) / unit['temperature']
   assert 100 < T < 400
+
+
+@pytest.mark.parametrize('dtype_name', ['float32', 'float64'])
+def test_sw_npt_reference_lammps_case(dtype_name):
+  """The reference's own NPT acceptance test (tests/simulate_test.py:586-690) on its own data
+  (tests/data/lammps_npt_test -> tests/golden/lammps_npt.npz): Stillinger-Weber silicon, 512 atoms
+  on unit-cube coordinates in a 21.724 A box, 800 steps of 1 fs at 300 K and zero pressure; the
+  mean temperature and pressure of the second half and the extended Hamiltonian are held to the
+  reference's tolerances."""
+  import os
+  import torch
+  jmd = _jmd()
+  dtype = np.dtype(dtype_name).type
+  tdt = torch.float32 if dtype_name == 'float32' else torch.float64
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lammps_npt.npz'))
+  box, pos = g['box'].astype(dtype), g['position'].astype(dtype)
+  units = {'mass': 1, 'time': 98.22694788, 'temperature': 8.617330337217213e-05,
+           'pressure': 6.241509125883258e-07}                         # simulate_test.py:597-607
+  dt = 1e-3 * units['time']
+  T_init, P_init, Mass = 300 * units['temperature'], 0.0 * units['pressure'], 28.0855 * units['mass']
+  steps = 800                                                          # DYNAMICS_STEPS
+  displacement, shift = jmd.space.periodic_general(box)
+  neighbor_fn, energy_fn = jmd.energy.stillinger_weber_neighbor_list(displacement, box)
+  R = _dev(pos)
+  # (the reference calls allocate(pos, box=box) on a list made WITHOUT fractional_coordinates:
+  #  its cell grid then treats the unit cube as a corner of a 21.7 A box -- every atom in one
+  #  cell; same neighbour sets)
+  nbrs = neighbor_fn.allocate(R, box=box, extra_capacity=8)
+  init_fn, apply_fn = jmd.simulate.npt_nose_hoover(energy_fn, shift, dt=dt, pressure=P_init, kT=T_init)
+  state = init_fn(121, R, box=box, mass=Mass, neighbor=nbrs)
+  kT, P, H = np.zeros(steps), np.zeros(steps), np.zeros(steps)
+  for i in range(steps):
+    state = apply_fn(state, neighbor=nbrs)
+    nbrs = nbrs.update(state.position)
+    kT[i] = float(jmd.quantity.temperature(momentum=state.momentum, mass=state.mass))
+    KE = jmd.quantity.kinetic_energy(momentum=state.momentum, mass=Mass)
+    P[i] = float(jmd.quantity.pressure(energy_fn, state.position, box=_dev(box), kinetic_energy=KE,
+                                       neighbor=nbrs))
+    H[i] = float(jmd.simulate.npt_nose_hoover_invariant(energy_fn, state, pressure=P_init, kT=T_init,
+                                                        neighbor=nbrs))
+  assert not bool(nbrs.did_buffer_overflow)
+  assert state.position.dtype == tdt
+  np.testing.assert_allclose(np.mean(kT[-steps // 2:]), T_init, atol=1e-2, rtol=1e-2)
+  np.testing.assert_allclose(np.mean(P[-steps // 2:]), P_init, atol=2e-3, rtol=2e-3)
+  np.testing.assert_allclose(H, np.ones(steps) * H[0], rtol=2e-3, atol=2e-3)
