@@ -531,13 +531,9 @@ def neighbor_list(displacement_or_metric,
   if fractional_coordinates and not (spec.general and spec.fractional):
     raise ValueError('fractional_coordinates=True needs a displacement function from '
                      'space.periodic_general(box, fractional_coordinates=True)')
-  if np.ndim(box_np) == 2 and not fractional_coordinates:
-    box_np = np.asarray(space._box_diagonal(box_np), f32)
-    if box_np.ndim == 2 and not disable_cell_list:
-      raise NotImplementedError(
-          'a triclinic box with real-space positions has no cell grid here: use '
-          'space.periodic_general(box) with fractional_coordinates=True (the reference\'s own '
-          'recommendation, space.py:360-372), or disable_cell_list=True.')
+  # (a MATRIX box without fractional_coordinates=True stays a matrix here: the reference's test
+  #  `all(cell_size < box / 3)`, partition.py:1052, then sees its zero off-diagonal elements and
+  #  never builds a cell list -- all-pairs candidates, as in tests/simulate_test.py:591-620)
   # the box currently in force (fractional coordinates: `box=` overrides, partition.py:1045)
   current = {'box': box_np, 'metric_box': None}
 
@@ -549,8 +545,6 @@ def neighbor_list(displacement_or_metric,
     if spec.general:
       current['metric_box'] = b                 # in the caller's precision, like the reference's metric
     b = f32(b) if np.ndim(b) == 0 else np.asarray(b, f32)
-    if np.ndim(b) == 2 and not fractional_coordinates:
-      b = np.asarray(space._box_diagonal(b), f32)
     current['box'] = b
     return b
   cutoff = r_cutoff + dr_threshold                                # :899
@@ -588,6 +582,9 @@ def neighbor_list(displacement_or_metric,
         cell_size = _fractional_cell_size(current['box'], cutoff)
         _box = 1.0
       if np.all(np.asarray(cell_size) < _box / 3.0):               # :1052
+        if np.ndim(_box) == 2:
+          raise NotImplementedError('cell grid for a matrix box in real-space coordinates: use '
+                                    'fractional_coordinates=True (space.py:360-372)')
         _, cs, cpside, n_cells = _cell_dimensions(dim, _box, cell_size)
         use_cells = True
         cps[:dim] = np.broadcast_to(np.reshape(cpside, (-1,)), (dim,))
@@ -632,6 +629,12 @@ def neighbor_list(displacement_or_metric,
     # exact_scan=True (static kwarg): evaluate the reference arithmetic on every
     # candidate instead of only inside the pre-filter's rounding band (testing).
     c.no_filter = 1 if static_kwargs.get('exact_scan', False) else 0
+    if spec.general and spec.fractional and not fractional_coordinates:
+      # unit-cube positions binned on a REAL-space grid (what the reference does when the list is
+      # made without fractional_coordinates=True, e.g. tests/simulate_test.py:593-620): every atom
+      # lands in the corner cells, so a cell says nothing about where its atoms are and the
+      # pre-filter's image shift does not apply: exact metric for every candidate
+      c.no_filter = 1
     # lazy_idx=True (static kwarg): see NeighborList.idx
     c.lazy_idx = 1 if static_kwargs.get('lazy_idx', False) else 0
     return use_cells, cell_size, n_cells, fine

@@ -184,3 +184,37 @@ def test_sw_nvt_with_periodic_general_as_in_the_example():
   assert bool(((st.position >= 0) & (st.position < 1)).all())        # still unit-cube coordinates
   T = float(jmd.simulate.temperature(st)) / unit['temperature']
   assert 50 < T < 600
+
+
+@pytest.mark.parametrize('fmt', ['Dense', 'OrderedSparse'])
+def test_unit_cube_positions_on_a_real_space_grid(fmt):
+  """tests/simulate_test.py:591-620 builds its list WITHOUT fractional_coordinates=True from a
+  periodic_general displacement and unit-cube positions: the cell grid is sized for the 21.7 A box
+  and every atom falls into its corner cell.  Same lists as the oracle, periodic images included."""
+  jmd = _jmd()
+  R, L = util.diamond(4, a=5.431, dtype=np.float64)
+  S = np.mod(util.jitter(R, L, 0.05, seed=4) / L, 1.0)
+  box = np.eye(3) * L
+  d_o, _ = ospace.periodic_general(box)
+  d_g, _ = jmd.space.periodic_general(box)
+  nf_o = opart.neighbor_list(d_o, box, np.float32(3.77118), np.float32(0.5), format=opart.Format[fmt])
+  nf_g = jmd.partition.neighbor_list(d_g, box, np.float32(3.77118), np.float32(0.5),
+                                     format=jmd.partition.NeighborListFormat[fmt])
+  nb_o, nb_g = nf_o.allocate(S, box=box), nf_g.allocate(_dev(S), box=box)
+  # a MATRIX box: `all(cell_size < box / 3)` (partition.py:1052) is false for its zero elements
+  assert nb_g._ws.c.use_cells == 0 and nb_o.cell_list_capacity is None and nb_g.cell_list_capacity is None
+  np.testing.assert_array_equal(nb_g.idx.cpu().numpy(), nb_o.idx)
+  assert nb_g.max_occupancy == nb_o.max_occupancy
+  # the same with a VECTOR box does build the (degenerate) grid: unit-cube positions, 21.7 A cells
+  bv = np.full(3, L)
+  d_o2, _ = ospace.periodic_general(bv)
+  d_g2, _ = jmd.space.periodic_general(bv)
+  nf_o2 = opart.neighbor_list(d_o2, bv, np.float32(3.77118), np.float32(0.5), format=opart.Format[fmt])
+  nf_g2 = jmd.partition.neighbor_list(d_g2, bv, np.float32(3.77118), np.float32(0.5),
+                                      format=jmd.partition.NeighborListFormat[fmt])
+  nb_o2, nb_g2 = nf_o2.allocate(S), nf_g2.allocate(_dev(S))
+  assert nb_g2._ws.c.use_cells == 1 and nb_g2.cell_list_capacity == nb_o2.cell_list_capacity
+  np.testing.assert_array_equal(nb_g2.idx.cpu().numpy(), nb_o2.idx)
+  counts = (nb_g.idx.cpu().numpy() < len(S)).sum(-1) if fmt == 'Dense' else None
+  if counts is not None:
+    assert counts.min() >= 4                 # every atom sees its 4 bonded neighbours, faces included

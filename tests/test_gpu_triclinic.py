@@ -59,7 +59,7 @@ def test_triclinic_neighbor_lists_match_oracle(fmt, dim, dtype):
 
 @pytest.mark.parametrize('fmt', ['Dense', 'OrderedSparse'])
 def test_triclinic_real_space_positions_all_pairs(fmt):
-  """fractional_coordinates=False with a matrix box: no cell grid (raises), all-pairs path works."""
+  """fractional_coordinates=False with a matrix box: no cell grid (like the reference), all-pairs."""
   jmd = _jmd()
   rng = np.random.default_rng(6)
   H = _tric(9.0, np.float64)
@@ -67,13 +67,12 @@ def test_triclinic_real_space_positions_all_pairs(fmt):
   X = S @ H.T
   d_o, _ = ospace.periodic_general(H, fractional_coordinates=False)
   d_g, _ = jmd.space.periodic_general(H, fractional_coordinates=False)
-  with pytest.raises(NotImplementedError):
-    jmd.partition.neighbor_list(d_g, H, 2.0, 0.3)
-  nf_o = opart.neighbor_list(d_o, H, np.float32(2.0), np.float32(0.3), disable_cell_list=True,
-                             format=opart.Format[fmt])
-  nf_g = jmd.partition.neighbor_list(d_g, H, np.float32(2.0), np.float32(0.3), disable_cell_list=True,
+  # (no disable_cell_list needed: partition.py:1052 never builds a grid for a matrix box)
+  nf_o = opart.neighbor_list(d_o, H, np.float32(2.0), np.float32(0.3), format=opart.Format[fmt])
+  nf_g = jmd.partition.neighbor_list(d_g, H, np.float32(2.0), np.float32(0.3),
                                      format=jmd.partition.NeighborListFormat[fmt])
   nb_o, nb_g = nf_o.allocate(X), nf_g.allocate(_dev(X))
+  assert nb_g._ws.c.use_cells == 0 and nb_g.cell_list_capacity is None and nb_o.cell_list_capacity is None
   np.testing.assert_array_equal(nb_g.idx.cpu().numpy(), nb_o.idx)
 
 
