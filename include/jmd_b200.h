@@ -40,6 +40,7 @@ enum { JMD_POT_LJ = 0, JMD_POT_SOFT_SPHERE = 1, JMD_POT_MORSE = 2 };
 /* smap.py:697-846 parameter modes */
 enum { JMD_PARAM_SCALAR = 0, JMD_PARAM_PER_ATOM = 1, JMD_PARAM_SPECIES = 2,
        JMD_PARAM_MATRIX = 3 };
+#define JMD_DPARAM_MAX_SPECIES 8   /* jmd_pair_t.dparam_rows */
 
 /* space.py:258-329: free() / periodic(side).  `side` and `half` hold the
  * values of `side` and `f32(0.5) * side` in the position dtype, widened to
@@ -228,7 +229,12 @@ typedef struct {
   int32_t n_species;       /* table side for SPECIES / MATRIX modes */
   int32_t transposed;      /* table lookups as p[neighbour, row] (Sparse formats:
                               smap.py:716,792 index with idx[0]=receiver first) */
-  int32_t _pad;
+  int32_t dparam_rows;     /* SPECIES-mode gradients: 0 = `dparam` holds two [S, S] tables filled with
+                              atomicAdd (summation order varies from run to run); 1 = `dparam` holds
+                              two [n, S] arrays, row i = atom i's sums per NEIGHBOUR species, no
+                              atomics: table[s_i][s_j] = sum of the rows of species s_i, folded by
+                              the caller in a fixed order (needs S <= JMD_DPARAM_MAX_SPECIES; swap
+                              the table's axes when `transposed`) */
   double scalar[3];        /* sigma, epsilon, alpha when SCALAR */
   const void* array[3];    /* device arrays (position dtype) otherwise */
   double r_onset, r_cutoff;
@@ -247,8 +253,8 @@ enum {
  *   force      [n, dim] out (user order)
  *   e_atom     [n] out or NULL: per-atom energy (reduce_axis=(1,), smap.py:958)
  *   red        double[JMD_RED_COUNT] out or NULL (energy, virial, dE/dparam)
- *   dparam     out or NULL: dE/dsigma then dE/depsilon tables (SPECIES mode:
- *              2 * n_species^2 doubles; PER_ATOM: 2 * n doubles)
+ *   dparam     out or NULL: dE/dsigma then dE/depsilon (SPECIES mode: 2 * n_species^2
+ *              doubles, or 2 * n * n_species with pp->dparam_rows; PER_ATOM: 2 * n doubles)
  *   partials   scratch double[>= jmd_red_scratch_doubles(n)]
  * want_energy != 0 also produces red[ENERGY, VIRIAL.., DSIGMA, DEPSILON]
  * (dparam tables must be zeroed by the caller).

@@ -65,10 +65,13 @@ class NbrT(C.Structure):
       ('n_dev', C.c_void_p)]
 
 
+DPARAM_MAX_SPECIES = 8        # JMD_DPARAM_MAX_SPECIES
+
+
 class PairT(C.Structure):
   _fields_ = [('kind', C.c_int32), ('has_cutoff', C.c_int32),
               ('mode', C.c_int32 * 3), ('n_species', C.c_int32),
-              ('transposed', C.c_int32), ('_pad', C.c_int32),
+              ('transposed', C.c_int32), ('dparam_rows', C.c_int32),
               ('scalar', C.c_double * 3), ('array', C.c_void_p * 3),
               ('r_onset', C.c_double), ('r_cutoff', C.c_double),
               ('r_onset2', C.c_double), ('r_cutoff2', C.c_double),

@@ -64,7 +64,7 @@ struct PairP {
   const int* cnt;
   const int* perm;
   // potential
-  int kind, has_cutoff, n_species, transposed;
+  int kind, has_cutoff, n_species, transposed, dparam_rows;
   int mode[3];
   T scalar[3];
   const T* array[3];
@@ -288,6 +288,15 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
     // force itself stays in the position dtype like the reference's)
     double e = 0.0, ds = 0.0, de = 0.0;
     double vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    // species-table gradients without atomics (jmd_pair_t.dparam_rows): this atom's sums per
+    // NEIGHBOUR species; the host folds the rows of equal home species in a fixed order
+    constexpr int DP = (WANT_E && !SCALAR) ? JMD_DPARAM_MAX_SPECIES : 1;
+    double dps[DP], dpe[DP];
+    const bool dp_rows = WANT_E && !SCALAR && Q.dparam && Q.dparam_rows;
+    if (dp_rows) {
+#pragma unroll
+      for (int k = 0; k < DP; ++k) { dps[k] = 0.0; dpe[k] = 0.0; }
+    }
     const int* col = Q.nl + t;
     const T sig0 = Q.scalar[0], eps0 = Q.scalar[1], alp0 = Q.scalar[2];
     // free space: half = +inf, never "far"
@@ -356,10 +365,16 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
         }
         if (!SCALAR && Q.dparam) {
           const int sj = (int)pj.w;
-          const int cell = Q.transposed ? sj * Q.n_species + si : si * Q.n_species + sj;
-          if (Q.mode[0] == JMD_PARAM_SPECIES) atomicAdd(&Q.dparam[cell], 0.5 * (double)dus);
-          if (Q.mode[1] == JMD_PARAM_SPECIES)
-            atomicAdd(&Q.dparam[Q.n_species * Q.n_species + cell], 0.5 * (double)due);
+          if (dp_rows) {
+            const int b = sj < DP ? sj : DP - 1;        // (n_species <= DP is checked at launch)
+            dps[b] += 0.5 * (double)dus;
+            dpe[b] += 0.5 * (double)due;
+          } else {
+            const int cell = Q.transposed ? sj * Q.n_species + si : si * Q.n_species + sj;
+            if (Q.mode[0] == JMD_PARAM_SPECIES) atomicAdd(&Q.dparam[cell], 0.5 * (double)dus);
+            if (Q.mode[1] == JMD_PARAM_SPECIES)
+              atomicAdd(&Q.dparam[Q.n_species * Q.n_species + cell], 0.5 * (double)due);
+          }
         }
       }
     };
@@ -476,8 +491,16 @@ JMD_PAIR_KERNEL(PairP<T, DIM> Q) {
     if (WANT_E) {
       if (Q.e_atom) Q.e_atom[ai] = (T)(0.5 * e);        // smap.py:955-958: / normalization
       if (!SCALAR && Q.dparam) {
-        if (Q.mode[0] == JMD_PARAM_PER_ATOM) Q.dparam[ai] = 0.5 * ds;
-        if (Q.mode[1] == JMD_PARAM_PER_ATOM) Q.dparam[Q.n + ai] = 0.5 * de;
+        if (dp_rows) {
+          const int S = Q.n_species;
+          for (int k = 0; k < S && k < DP; ++k) {
+            Q.dparam[(size_t)ai * S + k] = dps[k];
+            Q.dparam[((size_t)Q.n + ai) * S + k] = dpe[k];
+          }
+        } else {
+          if (Q.mode[0] == JMD_PARAM_PER_ATOM) Q.dparam[ai] = 0.5 * ds;
+          if (Q.mode[1] == JMD_PARAM_PER_ATOM) Q.dparam[Q.n + ai] = 0.5 * de;
+        }
       }
     }
     T ke = T(0), pp = T(0), fp = T(0), ff = T(0);
@@ -578,6 +601,8 @@ int JMD_PAIR_LAUNCHER(const jmd_nbr_t* nb, const jmd_pair_t* pp, void* force, vo
   Q.nl = nb->nl; Q.cnt = nb->cnt; Q.perm = nb->perm;
   Q.kind = pp->kind; Q.has_cutoff = pp->has_cutoff; Q.n_species = pp->n_species;
   Q.transposed = pp->transposed;
+  Q.dparam_rows = pp->dparam_rows;
+  if (Q.dparam_rows && (pp->n_species > JMD_DPARAM_MAX_SPECIES || pp->n_species < 1)) return JMD_EINVAL;
   bool scalar = true;
   for (int k = 0; k < 3; ++k) {
     Q.mode[k] = pp->mode[k];

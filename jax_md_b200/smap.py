@@ -277,10 +277,15 @@ class PairNeighborListFn:
     partials = Scratch.get(N, dev)
     e_atom = torch.empty((N,), dtype=R.dtype, device=dev) if per_atom else None
     dparam = None
+    pt.dparam_rows = 0
     if want_energy and any(m in (_lib.PARAM_SPECIES, _lib.PARAM_PER_ATOM)
                            for m in modes[:2]):
       size = 2 * N if _lib.PARAM_PER_ATOM in modes[:2] else 2 * pt.n_species ** 2
       size = max(size, 2 * pt.n_species ** 2)
+      if _lib.PARAM_PER_ATOM not in modes[:2] and 1 <= pt.n_species <= _lib.DPARAM_MAX_SPECIES:
+        # per-atom rows instead of atomics into the [S, S] tables: reproducible sums
+        pt.dparam_rows = 1
+        size = 2 * N * pt.n_species
       dparam = torch.zeros(size, dtype=torch.float64, device=dev)
     mass_is_array = 0
     if momentum is not None:
@@ -290,8 +295,23 @@ class PairNeighborListFn:
               _lib.ptr(partials), _lib.ptr(momentum), _lib.ptr(mass),
               mass_is_array, float(dt_2), _lib.ptr(dt_dev),
               1 if want_energy else 0, _lib.stream())
+    if pt.dparam_rows:
+      dparam = self._fold_species_rows(dparam, ws, N, pt.n_species, bool(pt.transposed))
     return dict(force=force, red=red, e_atom=e_atom, dparam=dparam, modes=modes,
                 n_species=pt.n_species, keep=keep)
+
+  @staticmethod
+  def _fold_species_rows(rows, ws, N, S, transposed):
+    """[2, N, S] per-atom sums (home atom i, neighbour species) -> the two [S, S] tables the
+    autograd function reads: table[s_i] = sum of the rows of species s_i.  One f64 GEMM with the
+    one-hot species matrix: a fixed summation order, unlike atomics."""
+    species = ws.species
+    onehot = torch.zeros((N, S), dtype=torch.float64, device=rows.device)
+    onehot.scatter_(1, species[:N].long().reshape(-1, 1), 1.0)
+    tables = torch.matmul(onehot.T.unsqueeze(0), rows.view(2, N, S))      # [2, S, S]
+    if transposed:
+      tables = tables.transpose(1, 2)
+    return tables.contiguous().reshape(-1)
 
   def force_and_virial(self, R, neighbor=None, **dynamic_kwargs):
     """One launch -> (force [N, dim], trace of `virial()` as a 0-d tensor): what

@@ -144,6 +144,16 @@ def test_species_tables_and_per_particle(kind, dtype):
   E.backward()
   t = dict(rtol=5e-5, atol=1e-3) if dtype == np.float32 else dict(rtol=1e-9, atol=1e-9)
   np.testing.assert_allclose(sig.grad.cpu().numpy(), dp_o['sigma'], **t)
+  # ... and they are bitwise reproducible: per-atom rows folded by a GEMM, no atomics
+  # (jmd_pair_t.dparam_rows)
+  g0 = sig.grad.clone()
+  for _ in range(3):
+    sig.grad = None
+    s['e_g'](Rd, neighbor=nb_g, sigma=sig).backward()
+    assert torch.equal(sig.grad, g0)
+  eps_t = _dev(np.asarray(s['params']['epsilon'], dtype)).requires_grad_(True)
+  s['e_g'](Rd, neighbor=nb_g, epsilon=eps_t).backward()
+  np.testing.assert_allclose(eps_t.grad.cpu().numpy(), dp_o['epsilon'], **t)
   # per-particle energies (reduce_axis=(1,), smap.py:958-977)
   if kind == 'lj':
     d_g, _ = jmd.space.periodic(s['L'])
