@@ -209,16 +209,22 @@ _Stepper._step_generic_shift = _generic_shift_step
 
 
 def dispatch_by_state(fn):
-  """simulate.py:100-116: single dispatch on the type of the `state` argument (second
-  argument if the first is not a state-like dataclass)."""
+  """simulate.py:100-116: call `fn(state, ...)` unless an override was registered for the TYPE OF
+  `state.position` (how the reference routes rigid-body states through the same step functions):
+  `@step.register(RigidBody)`."""
   import functools
-  dispatcher = functools.singledispatch(fn)
+  overrides = {}
 
   @functools.wraps(fn)
-  def wrapper(state, *args, **kwargs):
-    return dispatcher.dispatch(state.__class__)(state, *args, **kwargs)
-  wrapper.register = dispatcher.register
-  return wrapper
+  def call(state, *args, **kwargs):
+    return overrides.get(type(state.position), fn)(state, *args, **kwargs)
+
+  def register(oftype):
+    def add(override):
+      overrides[oftype] = override
+    return add
+  call.register = register
+  return call
 
 
 def nve(energy_or_force_fn, shift_fn, dt=1e-3, **sim_kwargs):

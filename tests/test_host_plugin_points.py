@@ -96,3 +96,24 @@ def test_fori_loop_reference_semantics_without_device():
   assert torch.equal(x, torch.full((3,), float(2 + 3 + 4 + 5 + 6))) and d['n'] == 5
   init = (torch.ones(2), {'n': 0})
   assert lax.fori_loop(5, 5, body, init) is init
+
+
+def test_dispatch_by_state_routes_on_the_position_type():
+  """simulate.py:100-116."""
+  from types import SimpleNamespace
+  from jax_md_b200 import simulate
+
+  class Quaternions(tuple):
+    pass
+
+  @simulate.dispatch_by_state
+  def step(state, scale=1):
+    return ('default', scale)
+
+  @step.register(Quaternions)
+  def _(state, scale=1):
+    return ('rigid', scale)
+
+  assert step(SimpleNamespace(position=[1.0]), scale=2) == ('default', 2)
+  assert step(SimpleNamespace(position=Quaternions((1.0,))), scale=3) == ('rigid', 3)
+  assert step(SimpleNamespace(position=(1.0,))) == ('default', 1)      # a plain tuple is not the subclass
