@@ -27,7 +27,7 @@ n = 40
 R_h, box = bench.fcc((n, n, n))
 L = float(box[0])
 rng = np.random.default_rng(0)
-S = np.mod(R_h / L + rng.normal(0, 0.002, R_h.shape), 1.0).astype(np.float32)
+S = np.mod((R_h + rng.normal(0, 0.03, R_h.shape)) / L, 1.0).astype(np.float32)
 Sd = torch.as_tensor(S, device='cuda')
 for tag, H in (('orthorhombic (vector box)', np.full(3, L, np.float32)),
                ('triclinic (matrix box)  ', np.array([[L, 0.2 * L, 0.1 * L], [0, L, 0.15 * L], [0, 0, L]], np.float32))):
