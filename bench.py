@@ -125,13 +125,16 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  n = args.cpu_cells
+  # the B200 arm's own single-GPU workload (N = 4 * cells^3 = 1,000,188 by default), its K and W
+  # capped so that the run ends within minutes on the host cores; under torchrun (N GPUs) the
+  # CPU arm still runs this one-GPU system on rank 0 -- a bounded sample of the N-GPU workload
+  n = args.cpu_cells if args.cpu_cells > 0 else args.cells
   steps = max(1, min(args.steps, args.cpu_steps))
-  warm = max(1, min(args.warmup, 2))
+  warm = max(1, min(args.warmup, 5))
   v, N, secs, th = cpu_port_run(n, steps, warm)
   ms = secs / steps * 1e3
-  sample = (f'LJ fcc N={N} (n={n}), {steps} update+NVE steps through the C port of the '
-            f'reference path on {th} threads (jax is not installable here: the reference '
+  sample = (f'LJ fcc N={N} (n={n}), {steps} update+NVE steps after {warm} warm-up steps through the C '
+            f'port of the reference path on {th} threads (jax is not installable here: the reference '
             f'itself is not runnable)')
   line = {
       'impl': 'reference', 'metric': 'atom-timesteps/s', 'value': v,
@@ -139,8 +142,9 @@ def run_reference(args):
       'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
       'data': 'synthetic',
-      'config': {'workload': f'LJ fcc rho={RHO} rc={R_CUT} skin={SKIN} NVE, '
-                             f'bounded CPU sample N={N}'},
+      'config': {'workload': f'LJ fcc N={N} rho={RHO} rc={R_CUT} skin={SKIN} dt={DT} kT={KT} NVE, '
+                             'C port of the reference path (CSR cell list, closed-form forces)',
+                 'atoms': N},
       'cpu_baseline': {'value': v, 'unit': 'atom-timesteps/s', 'cores': th,
                        'kind': 'port', 'sample': sample},
       'e2e': {'value': v, 'unit': 'atom-timesteps/s', 'h2d_bytes_per_step': 0,
@@ -430,7 +434,7 @@ def run_b200(args):
   # ---- CPU baseline (oracle port, bounded sample) -------------------------------
   cpu = None
   if not args.no_cpu:
-    v, Nc, secs, th = cpu_port_run(args.cpu_cells, args.cpu_steps, 2)
+    v, Nc, secs, th = cpu_port_run(args.cpu_cells if args.cpu_cells > 0 else args.cells, args.cpu_steps, 2)
     cpu = {'value': v, 'unit': 'atom-timesteps/s', 'cores': th, 'kind': 'port',
            'sample': f'LJ fcc N={Nc}, {args.cpu_steps} update+NVE steps, C port of the '
                      f'reference path on {th} threads ({secs:.1f} s)'}
@@ -487,8 +491,9 @@ def main():
                   choices=['Dense', 'Sparse', 'OrderedSparse'])
   ap.add_argument('--block', type=int, default=100)
   ap.add_argument('--kernel-reps', type=int, default=20)
-  ap.add_argument('--cpu-cells', type=int, default=40)
-  ap.add_argument('--cpu-steps', type=int, default=40)
+  ap.add_argument('--cpu-cells', type=int, default=0,
+                  help='fcc cells per side of the CPU arms (0: the same system as the GPU arm)')
+  ap.add_argument('--cpu-steps', type=int, default=30)
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--no-variants', action='store_true')
   ap.add_argument('--no-extra', action='store_true', help='skip the 4M / 8M-atom extra points')
