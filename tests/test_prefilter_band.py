@@ -85,3 +85,63 @@ def test_prefilter_error_is_inside_the_band(dtype, L, cells):
   acc, rej = a2 < lo, a2 > hi
   assert (d_fwd[acc] < cutoff_sq).all() and (d_rev[acc] < cutoff_sq).all()
   assert (d_fwd[rej] >= cutoff_sq).all() and (d_rev[rej] >= cutoff_sq).all()
+
+
+def _general_d2(sa, sb, side, dtype):
+  """space.periodic_general with unit-cube positions (space.py:419-433) in separately rounded
+  ops: box * (mod(fl(sa - sb) + 1/2, 1) - 1/2), sum of squares."""
+  d = (sa - sb).astype(dtype)
+  m = (np.mod((d + dtype(0.5)).astype(dtype), dtype(1.0)).astype(dtype) - dtype(0.5)).astype(dtype)
+  g = (m * side.astype(dtype)).astype(dtype)
+  sq = (g * g).astype(dtype)
+  acc = sq[:, 0]
+  for k in range(1, sq.shape[1]):
+    acc = (acc + sq[:, k]).astype(dtype)
+  return acc
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('L,cells', [(33.592, 11), (105.81, 37)])
+def test_prefilter_band_for_unit_cube_positions(dtype, L, cells):
+  """periodic_general: the metric is evaluated on unit-cube coordinates, the pre-filter on the
+  real-space sorted copy fl(s * side) -- one more rounding of ulp(L)/2 per coordinate than the
+  orthorhombic derivation counts.  fill() doubles the band for general spaces; the emulated error
+  stays inside it."""
+  rng = np.random.default_rng(int(L) + 1)
+  dim, cut = 3, 2.8
+  side = np.array([L, L * 1.07, L * 0.93])
+  cutoff_sq = float(dtype(cut) ** 2)
+  band = 2.0 * _band(float(side.max()), cutoff_sq, dim, dtype)      # P.band of a general space
+  n = 400_000
+  a_real = rng.random((n, dim)) * side
+  u = rng.normal(size=(n, dim))
+  u /= np.linalg.norm(u, axis=1, keepdims=True)
+  eps = np.finfo(dtype).eps
+  scale = 1.0 + rng.integers(-8, 9, (n, 1)) * eps * rng.choice([0, 1, 4, 32, 1e3, 1e5], (n, 1))
+  scale = np.where(rng.random((n, 1)) < 0.2, rng.random((n, 1)) * 1.2, scale)
+  b_real = a_real + u * cut * scale
+  sa = (a_real / side).astype(dtype)
+  sb = np.mod(b_real / side, 1.0).astype(dtype)
+  ok = (sb >= 0).all(1) & (sb < 1).all(1) & (sa < 1).all(1)
+  sa, sb = sa[ok], sb[ok]
+  # the cell-sorted copy the pre-filter reads: real = fl(s * side)
+  ra = (sa * side.astype(dtype)).astype(dtype)
+  rb = (sb * side.astype(dtype)).astype(dtype)
+  cs = 1.0 / cells                                                   # unit-cube grid
+  ca = np.minimum((sa / dtype(cs)).astype(np.int64), cells - 1)
+  cb = np.minimum((sb / dtype(cs)).astype(np.int64), cells - 1)
+  dc = cb - ca
+  wrap = np.where(dc > cells // 2, 1.0, np.where(dc < -(cells // 2), -1.0, 0.0))
+  stencil = (np.abs(dc - np.round(dc / cells) * cells) <= 1).all(1)
+  ra, rb, sa, sb, wrap = ra[stencil], rb[stencil], sa[stencil], sb[stencil], wrap[stencil]
+  assert len(ra) > 100_000
+  a2 = _filter_a2(ra, rb, wrap * side, dtype).astype(np.float64)    # home shifted by +-side (real space)
+  d_fwd = _general_d2(sa, sb, side, dtype).astype(np.float64)
+  d_rev = _general_d2(sb, sa, side, dtype).astype(np.float64)
+  near = np.abs(d_fwd - cutoff_sq) < 50 * band
+  worst = max(np.abs(a2 - d_fwd)[near].max(), np.abs(a2 - d_rev)[near].max())
+  assert worst < 0.5 * band, (worst, band)
+  lo, hi = cutoff_sq - band, cutoff_sq + band
+  acc, rej = a2 < lo, a2 > hi
+  assert (d_fwd[acc] < cutoff_sq).all() and (d_rev[acc] < cutoff_sq).all()
+  assert (d_fwd[rej] >= cutoff_sq).all() and (d_rev[rej] >= cutoff_sq).all()
